@@ -1,0 +1,91 @@
+/* walrus_b200 — C ABI of the B200-native exponential-sum hot path of The Walrus.
+ *
+ * The reference (XanaduAI/thewalrus v0.23.0-dev) is Python + Numba and has no FFI layer; these entry
+ * points are what a ctypes binding placed at the reference's numba call sites would bind.  Each entry
+ * cites the reference driver it replaces.  All matrices are row-major complex128 stored as interleaved
+ * (re, im) doubles and are ALREADY in "matched" order (vertex i paired with i + n/2), exactly what the
+ * reference passes to its numba drivers after matched_reps (thewalrus/_hafnian.py:501-505, 617-628).
+ *
+ * Every sum entry point evaluates a half-open range [j0, j1) of the reference's subset index, so the same
+ * symbol serves single-GPU calls and contiguous multi-GPU shards; partial results come back as
+ * compensated (hi, lo) pairs: out[0..3] = {re_hi, re_lo, im_hi, im_lo}, value = hi + lo, WITHOUT the final
+ * power-of-two scaling (0.5^(N/2-1), 2^(1-n), ...), which the caller applies after combining shards.
+ *
+ * Return value: 0 on success, negative WB200_E* code otherwise (wb200_last_error() gives the text).
+ * No C++ exceptions cross the boundary. `*_dev` variants take device pointers and a cudaStream_t
+ * (as void*) and do not synchronise; `*_host` variants take host pointers, copy in/out and synchronise.
+ */
+#ifndef WALRUS_B200_H
+#define WALRUS_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WB200_OK 0
+#define WB200_EINVAL -1   /* bad argument (size, parity, null pointer) */
+#define WB200_ECUDA -2    /* CUDA runtime error, see wb200_last_error() */
+#define WB200_ENOSUP -3   /* size outside what the kernels are built for */
+
+const char* wb200_last_error(void);
+int wb200_version(void);
+int wb200_device_count(int* count);
+
+/* FP64 pipe micro-benchmark used as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
+ * kind 0 = DFMA chains, 1 = DMMA m8n8k4 chains.  Result in TFLOP/s. */
+int wb200_fp64_peak(int device, int kind, double* tflops);
+
+/* ---- hafnian / loop hafnian, all edge repetitions 1, Glynn sieve (fast DMMA path) -------------------
+ * Replaces _calc_hafnian (thewalrus/_hafnian.py:416-467) and _calc_loop_hafnian (:512-577) for
+ * edge_reps = [1]*m, glynn=True, no odd vertex.  n even, 2 <= n <= 64.  Subset index j in
+ * [0, 2^(n/2-1)) as in :433/:536.  D = NULL: hafnian; D != NULL (n complex): loop hafnian.
+ * Final scale (caller): 0.5^(n/2-1). */
+size_t wb200_hafnian_workspace_bytes(int n);
+int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint64_t j0, uint64_t j1,
+                      double* d_out4, void* d_workspace, size_t workspace_bytes, void* stream);
+int wb200_hafnian_host(int device, const double* A, const double* D, int n, uint64_t j0, uint64_t j1,
+                       double out4[4], double* kernel_ms);
+
+/* ---- general (repeated edges, inclusion/exclusion, odd vertex) loop hafnian ------------------------
+ * Replaces _calc_hafnian / _calc_loop_hafnian for arbitrary edge_reps (thewalrus/_hafnian.py:416-577):
+ * mixed-radix subset index (find_kept_edges :162-180), binomial weights (:447-449), delta = 0 row/column
+ * deletion (get_submatrices :315-356), f / f_loop / f_loop_odd (:183-285).
+ * A: n x n (n = 2*n_edges) complex; D: n complex or NULL (no loops); oddV: n complex and oddloop: 2
+ * doubles, or NULL when there is no unpaired vertex; edge_reps: n_edges int32.
+ * out4 excludes the final 0.5^(N/2-1) (or 0.5^(N/2) with an odd vertex) Glynn scale. */
+int wb200_lhaf_general_host(int device, const double* A, const double* D, const double* oddV,
+                            const double* oddloop, int n, const int32_t* edge_reps, int glynn,
+                            uint64_t j0, uint64_t j1, double out4[4], double* kernel_ms);
+/* total number of subset indices for these arguments (reference `steps`, _hafnian.py:432-435, 535-538) */
+int wb200_lhaf_general_steps(const int32_t* edge_reps, int n_edges, int glynn, int has_odd, uint64_t* steps);
+
+/* ---- permanent --------------------------------------------------------------------------------------
+ * Replaces perm_bbfg (thewalrus/_permanent.py:130-168; method 0, steps k in [0, 2^(n-1)), final scale
+ * 2^(1-n)) and perm_ryser (:86-127; method 1, steps k in [0, 2^n), no scale).  Step k evaluates the
+ * Gray code g(k) = k ^ (k >> 1) with sign (-1)^k, as the reference's loop does.  M: n x n complex,
+ * 2 <= n <= 40. */
+int wb200_perm_dev(const double* dM, int n, int method, uint64_t k0, uint64_t k1, double* d_out4,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+size_t wb200_perm_workspace_bytes(int n);
+int wb200_perm_host(int device, const double* M, int n, int method, uint64_t k0, uint64_t k1,
+                    double out4[4], double* kernel_ms);
+/* exact int64 permanent (numba specialises perm_* on int64 input and sums in wrapping int64).
+ * out = sum over [k0,k1) WITHOUT the bbfg division by 2^(n-1). */
+int wb200_perm_int64_host(int device, const int64_t* M, int n, int method, uint64_t k0, uint64_t k1,
+                          int64_t* out, double* kernel_ms);
+
+/* ---- torontonian ------------------------------------------------------------------------------------
+ * Replaces rec_torontonian / numba_tor (thewalrus/_torontonian.py:123-154, 189-247):
+ * sum over S subset of [N] of (-1)^(N-|S|) / sqrt(det(I - O_S)).  O: 2N x 2N complex Hermitian in the
+ * reference's (x..., p...) block order (mode i <-> rows i and i+N).  The subset space is cut in
+ * 2^P "prefixes" (choices for the first P modes); this call evaluates prefixes [p0, p1).
+ * wb200_tor_num_prefixes gives 2^P for N.  out2 = {hi, lo} (the sum is real). */
+int wb200_tor_num_prefixes(int n_modes, uint64_t* count);
+int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
+                   double* kernel_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,20 @@
+"""walrus_b200 — B200-native (sm_100a CUDA) exponential-sum hot path of The Walrus.
+
+Drop-in for the reference's matrix functions on that path:
+``hafnian``, ``loop_hafnian``, ``hafnian_repeated``, ``perm``, ``tor``, ``loop_hafnian_batch`` and the
+batched GBS-probability front end.  See DESIGN.md for scope and INTEGRATION.md for the binding.
+"""
+from ._hafnian import (  # noqa: F401
+    _haf,
+    find_kept_edges,
+    hafnian,
+    hafnian_repeated,
+    input_validation,
+    loop_hafnian,
+    matched_reps,
+    reduction,
+)
+from ._permanent import perm, perm_bbfg, perm_ryser  # noqa: F401
+from ._torontonian import tor, tor_input_checks  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,209 @@
+"""Device plumbing between the NumPy-facing API and the C ABI.
+
+PyTorch is used only for what it is good at here: device buffers, the current CUDA stream and
+``torch.distributed``.  All arithmetic happens inside libwalrus_b200.so.
+"""
+import ctypes
+import threading
+
+import numpy as np
+
+from . import _lib
+from ._prep import dd_sum, shard_range
+
+_ws_cache = {}
+_ws_lock = threading.Lock()
+
+
+def _torch():
+    import torch  # imported lazily: `import thewalrus_b200` must work where torch is slow to load
+
+    return torch
+
+
+def require_cuda(device=None):
+    """Return the torch device to run on; raise if there is no GPU (no CPU fallback by design)."""
+    torch = _torch()
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("walrus_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _workspace(dev, nbytes):
+    torch = _torch()
+    key = (dev.index, threading.get_ident())
+    with _ws_lock:
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() * 8 < nbytes:
+            ws = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+            _ws_cache[key] = ws
+    return ws
+
+
+def _to_dev(arr_c128, dev):
+    torch = _torch()
+    host = torch.from_numpy(np.ascontiguousarray(arr_c128, dtype=np.complex128).view(np.float64).reshape(-1))
+    return host.to(dev, non_blocking=False)
+
+
+def combine4(parts):
+    """Fixed-order double-double sum of (re_hi, re_lo, im_hi, im_lo) partials -> complex."""
+    parts = np.asarray(parts, dtype=np.float64).reshape(-1, 4)
+    re, re_lo = dd_sum([(p[0], p[1]) for p in parts])
+    im, im_lo = dd_sum([(p[2], p[3]) for p in parts])
+    return complex(re + re_lo, im + im_lo)
+
+
+def allreduce_partials(part, group=None):
+    """Combine per-rank partials with ONE all-reduce and a fixed rank-order double-double sum.
+
+    Every rank writes its (hi, lo) partial into its own row of a zero [world, k] table; the sum
+    all-reduce then reproduces each row exactly (x + 0 = x), so every rank ends up with the same table
+    and the same rank-ordered compensated total: results are bit-identical on all ranks and independent
+    of the reduction tree.  Works on NCCL (CUDA tensor) and gloo (CPU tensor).
+    """
+    torch = _torch()
+    import torch.distributed as dist
+
+    part = np.asarray(part, dtype=np.float64).reshape(-1)
+    if not (dist.is_available() and dist.is_initialized()):
+        return part.reshape(1, -1)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    table = torch.zeros((world, part.size), dtype=torch.float64, device=dev)
+    table[rank] = torch.from_numpy(part).to(dev)
+    dist.all_reduce(table, op=dist.ReduceOp.SUM, group=group)
+    return table.cpu().numpy()
+
+
+def _rank_world(group, shard):
+    if shard is not None:
+        return int(shard[0]), int(shard[1])
+    if group is False:
+        return 0, 1
+    import torch.distributed as dist
+
+    if group is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group if group is not True else None), dist.get_world_size(group if group is not True else None)
+    return 0, 1
+
+
+def run_sharded(total, runner, group=None, width=4):
+    """Evaluate ``runner(lo, hi) -> partial[width]`` on this rank's contiguous shard and combine.
+
+    ``group``: None/False = single process; True = default process group; or a ProcessGroup.
+    """
+    rank, world = _rank_world(group, None)
+    lo, hi = shard_range(total, rank, world)
+    part = runner(lo, hi) if hi > lo else np.zeros(width)
+    if world == 1:
+        return np.asarray(part, dtype=np.float64).reshape(1, -1)
+    return allreduce_partials(part, None if group is True else group)
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel runners (single device, range of the subset index)
+# ---------------------------------------------------------------------------------------------------
+def hafnian_range(Ax, Dx, j0, j1, device=None):
+    """Partial Glynn (loop) hafnian sum over subset indices [j0, j1) -> 4 doubles (no final scale)."""
+    torch = _torch()
+    dev = require_cuda(device)
+    lib = _lib.load()
+    n = Ax.shape[0]
+    with torch.cuda.device(dev):
+        dA = _to_dev(Ax, dev)
+        dD = _to_dev(Dx, dev) if Dx is not None else None
+        nbytes = lib.wb200_hafnian_workspace_bytes(n)
+        if nbytes == 0:
+            raise NotImplementedError(f"hafnian DMMA kernel supports even n in [2, 64], got {n}")
+        ws = _workspace(dev, nbytes)
+        out = torch.empty(4, dtype=torch.float64, device=dev)
+        rc = lib.wb200_hafnian_dev(dA.data_ptr(), dD.data_ptr() if dD is not None else None, n, j0, j1,
+                                   out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                   torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "wb200_hafnian_dev")
+        return out.cpu().numpy()
+
+
+def perm_range(M, method, k0, k1, device=None):
+    """Partial permanent sum over Gray-code steps [k0, k1) -> 4 doubles (complex kernel)."""
+    torch = _torch()
+    dev = require_cuda(device)
+    lib = _lib.load()
+    n = M.shape[0]
+    with torch.cuda.device(dev):
+        dM = _to_dev(M, dev)
+        ws = _workspace(dev, lib.wb200_perm_workspace_bytes(n))
+        out = torch.empty(4, dtype=torch.float64, device=dev)
+        rc = lib.wb200_perm_dev(dM.data_ptr(), n, method, k0, k1, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "wb200_perm_dev")
+        return out.cpu().numpy()
+
+
+def _dev_index(device):
+    return require_cuda(device).index or 0
+
+
+def perm_f64_range(M, method, k0, k1, device=None):
+    lib = _lib.load()
+    idx = _dev_index(device)
+    M = np.ascontiguousarray(M, dtype=np.float64)
+    out = np.zeros(2)
+    rc = lib.wb200_perm_f64_host(idx, _lib.dptr(M), M.shape[0], method, k0, k1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_perm_f64_host")
+    return np.array([out[0], out[1], 0.0, 0.0])
+
+
+def perm_int64_range(M, method, k0, k1, device=None):
+    lib = _lib.load()
+    idx = _dev_index(device)
+    M = np.ascontiguousarray(M, dtype=np.int64)
+    out = ctypes.c_int64(0)
+    rc = lib.wb200_perm_int64_host(idx, M.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), M.shape[0], method,
+                                   k0, k1, ctypes.byref(out), None)
+    _lib.check(rc, "wb200_perm_int64_host")
+    return int(out.value)
+
+
+def lhaf_general_range(Ax, Dx, oddV, oddloop, edge_reps, glynn, j0, j1, device=None):
+    """Partial general (repeated-edge) loop-hafnian sum over mixed-radix indices [j0, j1)."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    n = Ax.shape[0]
+    Ax, pA = _lib.as_c128(Ax)
+    pD = pV = pL = None
+    if Dx is not None:
+        Dx, pD = _lib.as_c128(Dx)
+    if oddV is not None:
+        oddV, pV = _lib.as_c128(oddV)
+        ol = np.array([complex(oddloop)], dtype=np.complex128)
+        pL = ol.view(np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    er = np.ascontiguousarray(edge_reps, dtype=np.int32)
+    out = np.zeros(4)
+    rc = lib.wb200_lhaf_general_host(idx, pA, pD, pV, pL, n, er.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                     1 if glynn else 0, j0, j1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_lhaf_general_host")
+    return out
+
+
+def tor_range(O, p0, p1, device=None):
+    """Partial torontonian sum over prefixes [p0, p1) -> (hi, lo)."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    O, pO = _lib.as_c128(O)
+    out = np.zeros(2)
+    rc = lib.wb200_tor_host(idx, pO, O.shape[0] // 2, p0, p1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_tor_host")
+    return out
+
+
+def tor_num_prefixes(n_modes):
+    lib = _lib.load()
+    c = ctypes.c_uint64(0)
+    _lib.check(lib.wb200_tor_num_prefixes(n_modes, ctypes.byref(c)), "wb200_tor_num_prefixes")
+    return int(c.value)
