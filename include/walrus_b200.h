@@ -70,6 +70,9 @@ int wb200_perm_dev(const double* dM, int n, int method, uint64_t k0, uint64_t k1
 size_t wb200_perm_workspace_bytes(int n);
 int wb200_perm_host(int device, const double* M, int n, int method, uint64_t k0, uint64_t k1,
                     double out4[4], double* kernel_ms);
+/* real (float64) matrix: same sweep in real arithmetic (the reference keeps the input dtype).  out2 = {hi, lo}. */
+int wb200_perm_f64_host(int device, const double* M, int n, int method, uint64_t k0, uint64_t k1,
+                        double out2[2], double* kernel_ms);
 /* exact int64 permanent (numba specialises perm_* on int64 input and sums in wrapping int64).
  * out = sum over [k0,k1) WITHOUT the bbfg division by 2^(n-1). */
 int wb200_perm_int64_host(int device, const int64_t* M, int n, int method, uint64_t k0, uint64_t k1,

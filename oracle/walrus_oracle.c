@@ -1,0 +1,364 @@
+/* CPU ORACLE (C restatement) — TEST / BASELINE INFRASTRUCTURE ONLY.  Not part of the product.
+ *
+ * Plain-C, OpenMP restatement of the reference's hot path (XanaduAI/thewalrus v0.23.0-dev) for the cases
+ * the headline configurations use: all edge repetitions 1, Glynn sieve.  It follows the reference's
+ * ALGORITHM (full product chain for the power traces, the `comb` exponential-series loop, Gray-code
+ * permanent, Cholesky-updating torontonian recursion), not the GPU's:
+ *   oracle_hafnian_range       thewalrus/_hafnian.py:416-467 + charpoly.py:301-318 + _hafnian.py:183-209
+ *   oracle_loop_hafnian_range  thewalrus/_hafnian.py:512-577 + :212-242
+ *   oracle_perm_range          thewalrus/_permanent.py:86-168
+ *   oracle_tor_recursive       thewalrus/_torontonian.py:157-247
+ *   oracle_tor_direct_range    thewalrus/_torontonian.py:123-154
+ * Built twice by oracle/build.py: REAL = double (liboracle.so: checker + CPU baseline) and REAL = long
+ * double (liboracle_ld.so: extended-precision yardstick for sampled ranges at n = 50/56).
+ * Parity status: PINNED — tests/test_oracle_golden.py checks these against the committed outputs of the
+ * reference itself (tests/golden/reference_outputs.json) and its known-answer tests.
+ * Used only by tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifdef ORACLE_LONG_DOUBLE
+typedef long double REAL;
+#define SQRT sqrtl
+#else
+typedef double REAL;
+#define SQRT sqrt
+#endif
+
+#define NPAD(n) (((n) + 7) & ~7)
+
+/* C = A * B for complex matrices stored as separate re/im planes with leading dimension ld (multiple of 8).
+ * Register-blocked (4 rows x 16 columns) so the CPU baseline is not handicapped against the reference's
+ * BLAS zgemm (`A @ H`, thewalrus/charpoly.py:317). */
+#ifndef ORACLE_LONG_DOUBLE
+typedef double v8d __attribute__((vector_size(64), aligned(8)));
+static void cmatmul(int n, int ld, const REAL* restrict Ar, const REAL* restrict Ai, const REAL* restrict Br,
+                    const REAL* restrict Bi, REAL* restrict Cr, REAL* restrict Ci) {
+    for (int i0 = 0; i0 < n; i0 += 4) {
+        const int ib = (n - i0) < 4 ? (n - i0) : 4;
+        for (int j0 = 0; j0 < ld; j0 += 8) {
+            v8d cr0 = {0}, cr1 = {0}, cr2 = {0}, cr3 = {0}, ci0 = {0}, ci1 = {0}, ci2 = {0}, ci3 = {0};
+            const REAL* a0r = Ar + (size_t)(i0 + 0) * ld; const REAL* a0i = Ai + (size_t)(i0 + 0) * ld;
+            const REAL* a1r = Ar + (size_t)(i0 + (ib > 1 ? 1 : 0)) * ld; const REAL* a1i = Ai + (size_t)(i0 + (ib > 1 ? 1 : 0)) * ld;
+            const REAL* a2r = Ar + (size_t)(i0 + (ib > 2 ? 2 : 0)) * ld; const REAL* a2i = Ai + (size_t)(i0 + (ib > 2 ? 2 : 0)) * ld;
+            const REAL* a3r = Ar + (size_t)(i0 + (ib > 3 ? 3 : 0)) * ld; const REAL* a3i = Ai + (size_t)(i0 + (ib > 3 ? 3 : 0)) * ld;
+            for (int k = 0; k < n; ++k) {
+                const v8d br = *(const v8d*)(Br + (size_t)k * ld + j0);
+                const v8d bi = *(const v8d*)(Bi + (size_t)k * ld + j0);
+                cr0 += a0r[k] * br - a0i[k] * bi; ci0 += a0r[k] * bi + a0i[k] * br;
+                cr1 += a1r[k] * br - a1i[k] * bi; ci1 += a1r[k] * bi + a1i[k] * br;
+                cr2 += a2r[k] * br - a2i[k] * bi; ci2 += a2r[k] * bi + a2i[k] * br;
+                cr3 += a3r[k] * br - a3i[k] * bi; ci3 += a3r[k] * bi + a3i[k] * br;
+            }
+            *(v8d*)(Cr + (size_t)(i0 + 0) * ld + j0) = cr0; *(v8d*)(Ci + (size_t)(i0 + 0) * ld + j0) = ci0;
+            if (ib > 1) { *(v8d*)(Cr + (size_t)(i0 + 1) * ld + j0) = cr1; *(v8d*)(Ci + (size_t)(i0 + 1) * ld + j0) = ci1; }
+            if (ib > 2) { *(v8d*)(Cr + (size_t)(i0 + 2) * ld + j0) = cr2; *(v8d*)(Ci + (size_t)(i0 + 2) * ld + j0) = ci2; }
+            if (ib > 3) { *(v8d*)(Cr + (size_t)(i0 + 3) * ld + j0) = cr3; *(v8d*)(Ci + (size_t)(i0 + 3) * ld + j0) = ci3; }
+        }
+    }
+}
+#else
+static void cmatmul(int n, int ld, const REAL* restrict Ar, const REAL* restrict Ai, const REAL* restrict Br,
+                    const REAL* restrict Bi, REAL* restrict Cr, REAL* restrict Ci) {
+    for (int i = 0; i < n; ++i) {
+        REAL* restrict cr = Cr + (size_t)i * ld;
+        REAL* restrict ci = Ci + (size_t)i * ld;
+        for (int j = 0; j < ld; ++j) { cr[j] = 0; ci[j] = 0; }
+        for (int k = 0; k < n; ++k) {
+            const REAL ar = Ar[(size_t)i * ld + k], ai = Ai[(size_t)i * ld + k];
+            const REAL* restrict br = Br + (size_t)k * ld;
+            const REAL* restrict bi = Bi + (size_t)k * ld;
+            for (int j = 0; j < ld; ++j) {
+                cr[j] += ar * br[j] - ai * bi[j];
+                ci[j] += ar * bi[j] + ai * br[j];
+            }
+        }
+    }
+}
+#endif
+
+/* coefficients 0..order of exp(sum_i fac[i] eta^i): the reference's comb loop (_hafnian.py:196-209) */
+static void exp_series(int order, const REAL* facr, const REAL* faci, REAL* outr, REAL* outi, REAL* tmpr, REAL* tmpi) {
+    REAL* cr = outr; REAL* ci = outi; REAL* nr = tmpr; REAL* ni = tmpi;
+    for (int k = 0; k <= order; ++k) { cr[k] = 0; ci[k] = 0; }
+    cr[0] = 1;
+    for (int i = 1; i <= order; ++i) {
+        memcpy(nr, cr, sizeof(REAL) * (order + 1));
+        memcpy(ni, ci, sizeof(REAL) * (order + 1));
+        REAL pr = 1, pi = 0;
+        for (int j = 1; j <= order / i; ++j) {
+            const REAL tr = (pr * facr[i] - pi * faci[i]) / j, ti = (pr * faci[i] + pi * facr[i]) / j;
+            pr = tr; pi = ti;
+            for (int k = i * j; k <= order; ++k) {
+                nr[k] += cr[k - i * j] * pr - ci[k - i * j] * pi;
+                ni[k] += cr[k - i * j] * pi + ci[k - i * j] * pr;
+            }
+        }
+        REAL* t = cr; cr = nr; nr = t; t = ci; ci = ni; ni = t;
+    }
+    if (cr != outr) { memcpy(outr, cr, sizeof(REAL) * (order + 1)); memcpy(outi, ci, sizeof(REAL) * (order + 1)); }
+}
+
+/* Kahan accumulator so that the oracle's own summation error does not pollute comparisons */
+typedef struct { REAL s, c; } kahan_t;
+static inline void kadd(kahan_t* k, REAL x) { REAL y = x - k->c; REAL t = k->s + y; k->c = (t - k->s) - y; k->s = t; }
+
+/* A: n x n complex128 interleaved, matched order (vertex i paired with i + n/2); D: n complex or NULL.
+ * Sum over Glynn subset indices [j0, j1) without the final 0.5^(m-1) scale.  out = {re, im}. */
+static void hafnian_range_impl(const double* A, const double* D, int n, uint64_t j0, uint64_t j1, int nthreads, double* out) {
+    const int m = n / 2, ld = NPAD(n);
+    kahan_t tot_r = {0, 0}, tot_i = {0, 0};
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        const size_t msz = (size_t)n * ld;
+        REAL* buf = (REAL*)calloc(6 * msz + 8 * (size_t)ld + 8 * (size_t)(m + 2), sizeof(REAL));
+        REAL *Mr = buf, *Mi = Mr + msz, *Pr = Mi + msz, *Pi = Pr + msz, *Qr = Pi + msz, *Qi = Qr + msz;
+        REAL *xdr = Qi + msz, *xdi = xdr + ld, *dr = xdi + ld, *di = dr + ld, *tr_ = di + ld, *ti_ = tr_ + ld;
+        REAL *facr = ti_ + ld + 2 * ld, *faci = facr + (m + 2), *cr = faci + (m + 2), *ci = cr + (m + 2), *t1 = ci + (m + 2), *t2 = t1 + (m + 2);
+        REAL *ptr_r = t2 + (m + 2), *ptr_i = ptr_r + (m + 2);
+        kahan_t acc_r = {0, 0}, acc_i = {0, 0};
+#pragma omp for schedule(dynamic, 4)
+        for (uint64_t j = j0; j < j1; ++j) {
+            /* delta_i = 2 kept_i - 1, kept = bits of j MSB first (find_kept_edges); AX = A X diag(delta,delta) */
+            int nk = 0;
+            for (int c = 0; c < n; ++c) {
+                const int e = c % m;
+                const int kept = (int)((j >> (m - 1 - e)) & 1ull);
+                if (c < m) nk += kept;
+                const REAL dlt = kept ? 1 : -1;
+                const int sc = c < m ? c + m : c - m;
+                for (int r = 0; r < n; ++r) {
+                    Mr[(size_t)r * ld + c] = dlt * A[2 * ((size_t)r * n + sc)];
+                    Mi[(size_t)r * ld + c] = dlt * A[2 * ((size_t)r * n + sc) + 1];
+                }
+                if (D) {
+                    xdr[c] = dlt * D[2 * sc]; xdi[c] = dlt * D[2 * sc + 1];
+                    dr[c] = D[2 * c]; di[c] = D[2 * c + 1];
+                }
+            }
+            /* power traces tr(AX^k), k = 1..m, by the full product chain (charpoly.powertrace) */
+            memcpy(Pr, Mr, sizeof(REAL) * msz); memcpy(Pi, Mi, sizeof(REAL) * msz);
+            REAL *cPr = Pr, *cPi = Pi, *nPr = Qr, *nPi = Qi;
+            for (int k = 1; k <= m; ++k) {
+                if (k > 1) {
+                    cmatmul(n, ld, cPr, cPi, Mr, Mi, nPr, nPi);
+                    REAL* t = cPr; cPr = nPr; nPr = t; t = cPi; cPi = nPi; nPi = t;
+                }
+                REAL sr = 0, si = 0;
+                for (int r = 0; r < n; ++r) { sr += cPr[(size_t)r * ld + r]; si += cPi[(size_t)r * ld + r]; }
+                ptr_r[k] = sr; ptr_i[k] = si;
+            }
+            for (int i = 1; i <= m; ++i) {
+                facr[i] = ptr_r[i] / (2 * i); faci[i] = ptr_i[i] / (2 * i);
+                if (D) {
+                    /* + (XD . D)/2 then XD <- XD AX  (f_loop) */
+                    REAL sr = 0, si = 0;
+                    for (int c = 0; c < n; ++c) { sr += xdr[c] * dr[c] - xdi[c] * di[c]; si += xdr[c] * di[c] + xdi[c] * dr[c]; }
+                    facr[i] += sr / 2; faci[i] += si / 2;
+                    for (int c = 0; c < n; ++c) { tr_[c] = 0; ti_[c] = 0; }
+                    for (int r = 0; r < n; ++r)
+                        for (int c = 0; c < n; ++c) {
+                            tr_[c] += xdr[r] * Mr[(size_t)r * ld + c] - xdi[r] * Mi[(size_t)r * ld + c];
+                            ti_[c] += xdr[r] * Mi[(size_t)r * ld + c] + xdi[r] * Mr[(size_t)r * ld + c];
+                        }
+                    memcpy(xdr, tr_, sizeof(REAL) * n); memcpy(xdi, ti_, sizeof(REAL) * n);
+                }
+            }
+            exp_series(m, facr, faci, cr, ci, t1, t2);
+            const REAL sg = ((m - nk) & 1) ? -1 : 1;
+            kadd(&acc_r, sg * cr[m]); kadd(&acc_i, sg * ci[m]);
+        }
+#pragma omp critical
+        { kadd(&tot_r, acc_r.s); kadd(&tot_r, -acc_r.c); kadd(&tot_i, acc_i.s); kadd(&tot_i, -acc_i.c); }
+        free(buf);
+    }
+    out[0] = (double)tot_r.s; out[1] = (double)tot_i.s;
+#ifdef ORACLE_LONG_DOUBLE
+    out[2] = (double)(tot_r.s - (REAL)out[0]); out[3] = (double)(tot_i.s - (REAL)out[1]);
+#else
+    out[2] = 0; out[3] = 0;
+#endif
+}
+
+void oracle_hafnian_range(const double* A, int n, uint64_t j0, uint64_t j1, int nthreads, double* out4) {
+    hafnian_range_impl(A, NULL, n, j0, j1, nthreads, out4);
+}
+void oracle_loop_hafnian_range(const double* A, const double* D, int n, uint64_t j0, uint64_t j1, int nthreads, double* out4) {
+    hafnian_range_impl(A, D, n, j0, j1, nthreads, out4);
+}
+
+/* Gray-code permanent over steps [k0, k1): method 0 = bbfg (no 2^(1-n) scale), 1 = ryser.  Serial per
+ * thread like the reference; threads split the range (the reference itself is single-threaded). */
+void oracle_perm_range(const double* M, int n, int method, uint64_t k0, uint64_t k1, int nthreads, double* out4) {
+    kahan_t tot_r = {0, 0}, tot_i = {0, 0};
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        int tid = 0, nt = 1;
+#ifdef _OPENMP
+        tid = omp_get_thread_num(); nt = omp_get_num_threads();
+#endif
+        const uint64_t len = k1 - k0;
+        const uint64_t a = k0 + (len * tid) / nt, b = k0 + (len * (tid + 1)) / nt;
+        REAL rr[64], ri[64];
+        kahan_t acc_r = {0, 0}, acc_i = {0, 0};
+        if (a < b) {
+            uint64_t gray = a ^ (a >> 1);
+            for (int c = 0; c < n; ++c) { rr[c] = 0; ri[c] = 0; }
+            for (int r = 0; r < n; ++r) {
+                const int set = (int)((gray >> r) & 1ull);
+                const REAL d = method ? (set ? -1 : 0) : (set ? -1 : 1);
+                for (int c = 0; c < n; ++c) { rr[c] += d * M[2 * ((size_t)r * n + c)]; ri[c] += d * M[2 * ((size_t)r * n + c) + 1]; }
+            }
+            const REAL step = method ? 1 : 2;
+            for (uint64_t k = a; k < b; ++k) {
+                REAL pr = rr[0], pi = ri[0];
+                for (int c = 1; c < n; ++c) { const REAL t = pr * rr[c] - pi * ri[c]; pi = pr * ri[c] + pi * rr[c]; pr = t; }
+                if (k & 1ull) { kadd(&acc_r, -pr); kadd(&acc_i, -pi); } else { kadd(&acc_r, pr); kadd(&acc_i, pi); }
+                const uint64_t k1n = k + 1;
+                const int row = __builtin_ctzll(k1n);
+                if (row < n) {
+                    const int set = (int)(((k1n ^ (k1n >> 1)) >> row) & 1ull);
+                    const REAL d = set ? -step : step;
+                    for (int c = 0; c < n; ++c) { rr[c] += d * M[2 * ((size_t)row * n + c)]; ri[c] += d * M[2 * ((size_t)row * n + c) + 1]; }
+                }
+            }
+        }
+#pragma omp critical
+        { kadd(&tot_r, acc_r.s); kadd(&tot_r, -acc_r.c); kadd(&tot_i, acc_i.s); kadd(&tot_i, -acc_i.c); }
+    }
+    out4[0] = (double)tot_r.s; out4[1] = (double)tot_i.s;
+#ifdef ORACLE_LONG_DOUBLE
+    out4[2] = (double)(tot_r.s - (REAL)out4[0]); out4[3] = (double)(tot_i.s - (REAL)out4[1]);
+#else
+    out4[2] = 0; out4[3] = 0;
+#endif
+}
+
+/* ---- torontonian ------------------------------------------------------------------------------ */
+typedef struct { REAL re, im; } cplx;
+static inline cplx cmulconj(cplx a, cplx b) { cplx r = {a.re * b.re + a.im * b.im, a.im * b.re - a.re * b.im}; return r; }
+
+/* Cholesky (lower) of the Hermitian matrix B (dim x dim, stride ld) starting from row `from`, rows < from
+ * of L already valid.  Returns product of the diagonal from row `from` on. */
+static REAL chol_from(const cplx* B, cplx* L, int dim, int ld, int from) {
+    REAL prod = 1;
+    for (int i = from; i < dim; ++i) {
+        for (int j = from; j < i; ++j) {   /* columns < from are inherited (quad_cholesky :175-181) */
+            cplx z = {0, 0};
+            for (int k = 0; k < j; ++k) { cplx q = cmulconj(L[i * ld + k], L[j * ld + k]); z.re += q.re; z.im += q.im; }
+            const REAL dj = L[j * ld + j].re;
+            L[i * ld + j].re = (B[i * ld + j].re - z.re) / dj;
+            L[i * ld + j].im = (B[i * ld + j].im - z.im) / dj;
+        }
+        REAL z = 0;
+        for (int k = 0; k < i; ++k) z += L[i * ld + k].re * L[i * ld + k].re + L[i * ld + k].im * L[i * ld + k].im;
+        L[i * ld + i].re = SQRT(B[i * ld + i].re - z);
+        L[i * ld + i].im = 0;
+        prod *= L[i * ld + i].re;
+    }
+    return prod;
+}
+
+/* recursiveTor (_torontonian.py:189-224): B = I - A interleaved, L its Cholesky factor; delete mode i >= start */
+static REAL rec_tor(const cplx* B, const cplx* L, int nm, int ndel, int start, int n) {
+    REAL tot = 0;
+    const int dim = 2 * nm;
+    if (nm == 0) return 0;
+    const int cd = dim - 2;
+    cplx* Bz = (cplx*)malloc(sizeof(cplx) * (size_t)(cd > 0 ? cd * cd : 1) * 2);
+    cplx* Lz = Bz + (size_t)(cd > 0 ? cd * cd : 1);
+    for (int i = start; i < n; ++i) {
+        const int idx = (i - ndel) * 2;
+        /* Z = all rows but idx, idx+1 */
+        for (int r = 0, rr = 0; r < dim; ++r) {
+            if (r == idx || r == idx + 1) continue;
+            for (int c = 0, cc = 0; c < dim; ++c) {
+                if (c == idx || c == idx + 1) continue;
+                Bz[rr * cd + cc] = B[r * dim + c];
+                Lz[rr * cd + cc] = L[r * dim + c];
+                ++cc;
+            }
+            ++rr;
+        }
+        /* quad_cholesky: rows >= idx recomputed, earlier rows reused; det = (prod diag)^2 over ALL rows */
+        chol_from(Bz, Lz, cd, cd, idx);
+        REAL pd = 1;
+        for (int r = 0; r < cd; ++r) pd *= Lz[r * cd + r].re;
+        const REAL sign = ((ndel + 1) & 1) ? -1 : 1;
+        tot += sign / pd + rec_tor(Bz, Lz, nm - 1, ndel + 1, i + 1, n);
+    }
+    free(Bz);
+    return tot;
+}
+
+/* O: 2N x 2N complex interleaved doubles, block order.  Returns the torontonian (real). */
+double oracle_tor_recursive(const double* O, int N) {
+    const int dim = 2 * N;
+    cplx* B = (cplx*)malloc(sizeof(cplx) * (size_t)dim * dim * 2);
+    cplx* L = B + (size_t)dim * dim;
+    for (int r = 0; r < dim; ++r)
+        for (int c = 0; c < dim; ++c) {
+            const int sr = (r >> 1) + (r & 1) * N, sc = (c >> 1) + (c & 1) * N;
+            B[r * dim + c].re = (r == c ? 1 : 0) - O[2 * ((size_t)sr * dim + sc)];
+            B[r * dim + c].im = -O[2 * ((size_t)sr * dim + sc) + 1];
+            L[r * dim + c].re = 0; L[r * dim + c].im = 0;
+        }
+    const REAL pd = chol_from(B, L, dim, dim, 0);
+    const REAL res = 1 / pd + rec_tor(B, L, N, 0, 0, N);
+    free(B);
+    return (double)res;
+}
+
+/* numba_tor: flat loop over subsets [j0, j1), bit (N-1-i) of j <-> mode i kept */
+double oracle_tor_direct_range(const double* O, int N, uint64_t j0, uint64_t j1, int nthreads) {
+    kahan_t tot = {0, 0};
+    const int dimO = 2 * N;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        cplx* B = (cplx*)malloc(sizeof(cplx) * (size_t)dimO * dimO * 2);
+        cplx* L = B + (size_t)dimO * dimO;
+        int rows[128];
+        kahan_t acc = {0, 0};
+#pragma omp for schedule(dynamic, 64)
+        for (uint64_t j = j0; j < j1; ++j) {
+            int k = 0;
+            for (int i = 0; i < N; ++i)
+                if ((j >> (N - 1 - i)) & 1ull) { rows[2 * k] = i; rows[2 * k + 1] = i + N; ++k; }
+            const int dim = 2 * k;
+            for (int r = 0; r < dim; ++r)
+                for (int c = 0; c < dim; ++c) {
+                    B[r * dim + c].re = (r == c ? 1 : 0) - O[2 * ((size_t)rows[r] * dimO + rows[c])];
+                    B[r * dim + c].im = -O[2 * ((size_t)rows[r] * dimO + rows[c]) + 1];
+                }
+            const REAL pd = dim ? chol_from(B, L, dim, dim, 0) : 1;
+            kadd(&acc, (((N - k) & 1) ? -1 : 1) / pd);
+        }
+#pragma omp critical
+        { kadd(&tot, acc.s); kadd(&tot, -acc.c); }
+        free(B);
+    }
+    return (double)tot.s;
+}
+
+int oracle_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

@@ -1,0 +1,44 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_outputs.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Make sure the CUDA library and the oracle are built (nvcc cross-compiles without a GPU)."""
+    import __graft_entry__ as ge
+
+    ge.build()
+
+
+def dec(d):
+    return np.array(d["re"]) + 1j * np.array(d["im"])
+
+
+def rel(a, b):
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def random_symmetric(rng, n, kind="complex"):
+    if kind == "complex":
+        G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    else:
+        G = rng.standard_normal((n, n))
+    return G + G.T

@@ -59,7 +59,7 @@ struct HafSmem {
     static constexpr int MP = 4 * T;                      // padded m
     static constexpr int NSLOT = MP / 2 + 1;              // >= nprod + 1
     static constexpr int FRAG_D = 2 * T * T * 64;         // doubles in fragment table
-    static constexpr int PART_D = NSLOT * 32 * 4;         // per-lane partial inner products
+    static constexpr int PART_D = NSLOT * 8 * 4;          // per-row (g) partial inner products
     static constexpr int P_D = (MP + 2) * 4 * 2;          // P[k][q] complex
     static constexpr int WARP_D = PART_D + 3 * P_D;       // partials, P, L, c
     static constexpr size_t BYTES = sizeof(double) * (FRAG_D + HAF_WARPS * WARP_D);
@@ -134,7 +134,7 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
     double* wsm = smem + L::FRAG_D + warp * L::WARP_D;
-    double4* part = reinterpret_cast<double4*>(wsm);  // [slot][lane] -> (odd.re, odd.im, even.re, even.im)
+    double4* part = reinterpret_cast<double4*>(wsm);  // [slot][g] -> (odd.re, odd.im, even.re, even.im), written by t == 0
     double* Pk = wsm + L::PART_D;                     // P[k][q] complex: Pk[(k*4+q)*2 + {0,1}]
     double* Lk = Pk + L::P_D;                         // loop terms
     double* Ck = Lk + L::P_D;                         // series coefficients
@@ -158,7 +158,7 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
             const unsigned kept = (i < m) ? (unsigned)((jq >> (m - 1 - i)) & 1ull) : 1u;
             sm[tau] = kept ? 0u : 0x80000000u;
         }
-        for (int s = 0; s <= nprod; ++s) part[s * 32 + lane] = make_double4(0.0, 0.0, 0.0, 0.0);
+        for (int s = lane; s < (nprod + 1) * 8; s += 32) part[s] = make_double4(0.0, 0.0, 0.0, 0.0);
         __syncwarp();
 
         const int npanels = m + (loop ? 1 : 0);
@@ -203,9 +203,13 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
                         orr = __ldg(A + 2 * ((size_t)v * n + sv));
                         oi = __ldg(A + 2 * ((size_t)v * n + sv) + 1);
                     }
-                    double4 p = part[lane];
-                    p.x += rs * orr; p.y += rs * oi; p.z += rs * er; p.w += rs * ei;
-                    part[lane] = p;
+                    er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
+                    er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
+                    if (t == 0) {
+                        double4 p = part[g];
+                        p.x += rs * orr; p.y += rs * oi; p.z += rs * er; p.w += rs * ei;
+                        part[g] = p;
+                    }
                 } else {
                     haf_ip<T>(wr, wi, yr, yi, orr, oi);  // l_1 = <Z_0, S Z_0>
                     orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1);
@@ -235,13 +239,15 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
                 haf_ip<T>(xr, xi, yr, yi, orr, oi);       // with Y_old
                 haf_applyS<T>(wr, wi, sm, yr, yi);        // Y_new
                 haf_ip<T>(xr, xi, yr, yi, er, ei);        // with Y_new
+                orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1); er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
+                orr += shfl_xor_d(orr, 2); oi += shfl_xor_d(oi, 2); er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
                 if (!isD) {
-                    double4 p = part[k * 32 + lane];       // odd: p_{2k+1}, even: p_{2k+2}
-                    p.x += rs * orr; p.y += rs * oi; p.z += rs * er; p.w += rs * ei;
-                    part[k * 32 + lane] = p;
+                    if (t == 0) {
+                        double4 p = part[k * 8 + g];       // odd: p_{2k+1}, even: p_{2k+2}
+                        p.x += rs * orr; p.y += rs * oi; p.z += rs * er; p.w += rs * ei;
+                        part[k * 8 + g] = p;
+                    }
                 } else {                                   // l_{2k}, l_{2k+1}
-                    orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1); er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
-                    orr += shfl_xor_d(orr, 2); oi += shfl_xor_d(oi, 2); er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
                     if (t == 0 && half == 0) {
                         Lk[((2 * k) * 4 + q) * 2] = orr; Lk[((2 * k) * 4 + q) * 2 + 1] = oi;
                         Lk[((2 * k + 1) * 4 + q) * 2] = er; Lk[((2 * k + 1) * 4 + q) * 2 + 1] = ei;
@@ -250,18 +256,12 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
             }
         }
         __syncwarp();
-        // ---- reduce per-lane partials over the 8 lanes of each subset q (t bits and half bit)
-        for (int s = 0; s <= nprod; ++s) {
-            double4 p = part[s * 32 + lane];
-#pragma unroll
-            for (int off = 1; off <= 16; off = (off == 2 ? 16 : off * 2)) {
-                p.x += shfl_xor_d(p.x, off); p.y += shfl_xor_d(p.y, off);
-                p.z += shfl_xor_d(p.z, off); p.w += shfl_xor_d(p.w, off);
-            }
-            if (t == 0 && half == 0) {
-                Pk[((2 * s + 1) * 4 + q) * 2] = p.x; Pk[((2 * s + 1) * 4 + q) * 2 + 1] = p.y;
-                Pk[((2 * s + 2) * 4 + q) * 2] = p.z; Pk[((2 * s + 2) * 4 + q) * 2 + 1] = p.w;
-            }
+        // ---- combine the two rows (vertex i and i + m) of each subset q
+        for (int s = lane; s < (nprod + 1) * 4; s += 32) {
+            const int slot = s >> 2, qq = s & 3;
+            const double4 a = part[slot * 8 + qq], b = part[slot * 8 + qq + 4];
+            Pk[((2 * slot + 1) * 4 + qq) * 2] = a.x + b.x; Pk[((2 * slot + 1) * 4 + qq) * 2 + 1] = a.y + b.y;
+            Pk[((2 * slot + 2) * 4 + qq) * 2] = a.z + b.z; Pk[((2 * slot + 2) * 4 + qq) * 2 + 1] = a.w + b.w;
         }
         __syncwarp();
         // ---- coefficient [eta^m] of exp(sum_i a_i eta^i), a_i = p_i/(2i) (+ l_i/2): c_t = (1/t) sum_i i a_i c_{t-i}
@@ -325,6 +325,7 @@ extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint
     if (workspace_bytes < wb200_hafnian_workspace_bytes(n)) { set_error("hafnian: workspace too small"); return WB200_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0, sms = 0;
+    (void)cudaGetLastError();  // drop any stale non-sticky error from earlier calls
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
     double2* frag = reinterpret_cast<double2*>(d_workspace);
