@@ -11,17 +11,22 @@
 // by the fixed matrix A' whose B-operand fragments are staged once per CTA in shared memory.  The
 // D-fragment (accumulator) register layout of m8n8k4 is reused directly as the next A-fragment by
 // choosing the K-chunk <-> column mapping accordingly, so the chain needs no shuffles or smem traffic
-// for the iterate.  Power traces use the pairing identity
-//     tr(M^(a+b)) = sum_c delta_c <row c of B_a, S_j (row sigma(c) of B_b)>,
-// so only ceil(m/2)-1 products are needed for tr(M^1..M^m) (the reference does m-1, charpoly.py:316-318).
-// Loop hafnian: one more register row per subset, Z_k = (M^k D)^T, with
+// for the iterate.  Power traces:
+//     tr(M^k)     = sum_c delta_c B_k[c, sigma(c)]                          (one element per row: free)
+//     tr(M^(a+b)) = sum_c delta_c <row c of B_a, S_j (row sigma(c) of B_b)>  (pairing, for k > K)
+// so only K - 1 = ceil(m/2) - 1 products are needed for tr(M^1..M^m) (the reference does m-1,
+// charpoly.py:316-318).  Loop hafnian: one more register row per subset, Z_k = (M^k D)^T, with
 //     XD^T M^(a+b) D = <Z_a, S_j Z_b>            (reference: _hafnian.py:233-234).
+//
+// Register layout of a row for thread (g = lane >> 2, t = lane & 3):
+//   full tile tau < TF : w[tau][r] = element 4 tau + t + r m   (partners share a thread: swap is free)
+//   tail tile (TAIL)   : (wt_r, wt_i) = element 4 TF + (t >> 1) + (t & 1) m, partner in lane ^ 1.
+// The tail tile packs the last m mod 4 in {1, 2} vertex pairs with (re, im) interleaved so that sizes
+// like n = 50 (m = 25) waste one quarter of one tile instead of a whole tile row and column.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace wb {
-
-constexpr int HAF_THREADS = 256;  // 8 warps / CTA, 1 CTA / SM (2 warps per SMSP)
-constexpr int HAF_WARPS = HAF_THREADS / 32;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -33,235 +38,304 @@ __device__ __forceinline__ double flipsign(double x, unsigned mask) {
     return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
 }
 
-// Fragment table: for K-chunk kappa = 2*tau + r (elements 4*tau + k + r*m, k = lane & 3) and N-tile taup
-// (elements 4*taup + (ncol >> 1) + (ncol & 1)*m, ncol = lane >> 2): (re, im) of A'[e_k, e_n], 0 in padding.
-__global__ void haf_prep_kernel(const double* __restrict__ A, int n, int m, int T, double2* __restrict__ frag) {
-    const int total = 2 * T * T * 32;
+// element held at K-chunk kappa, position k (or -1 for padding)
+__device__ __forceinline__ int haf_chunk_elem(int kappa, int k, int m, int TF, int tp) {
+    if (kappa < 2 * TF) {
+        const int iv = 4 * (kappa >> 1) + k;
+        return iv < m ? iv + (kappa & 1) * m : -1;
+    }
+    return (k >> 1) < tp ? 4 * TF + (k >> 1) + (k & 1) * m : -1;
+}
+
+// Fragment table, (kappa * NT + tile) * 32 + lane:
+//   standard tile taup: (Ar, Ai)[e_k, e_n], e_n = 4 taup + (ncol >> 1) + (ncol & 1) m
+//   tail tile        : (F1, F2) with column ncol <-> vertex u(ncol >> 1), output part ncol & 1:
+//                      re: (Ar, -Ai), im: (Ai, Ar)   so that  D += yr * F1 + yi * F2
+__global__ void haf_prep_kernel(const double* __restrict__ A, int n, int m, int TF, int tail,
+                                double2* __restrict__ frag) {
+    const int tp = tail ? m - 4 * TF : 0;
+    const int NK = 2 * TF + (tail ? 1 : 0), NT = TF + (tail ? 1 : 0);
+    const int total = NK * NT * 32;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int lane = idx & 31, pair = idx >> 5;
-        const int taup = pair % T, kappa = pair / T;
-        const int tau = kappa >> 1, r = kappa & 1;
+        const int tile = pair % NT, kappa = pair / NT;
         const int k = lane & 3, ncol = lane >> 2;
-        const int ik = 4 * tau + k, in = 4 * taup + (ncol >> 1);
+        const int ek = haf_chunk_elem(kappa, k, m, TF, tp);
         double2 v = make_double2(0.0, 0.0);
-        if (ik < m && in < m) {
-            const int ek = ik + r * m, en = in + (ncol & 1) * m;
-            v.x = A[2 * ((size_t)ek * n + en)];
-            v.y = A[2 * ((size_t)ek * n + en) + 1];
+        if (ek >= 0) {
+            if (tile < TF) {
+                const int in = 4 * tile + (ncol >> 1);
+                if (in < m) {
+                    const int en = in + (ncol & 1) * m;
+                    v.x = A[2 * ((size_t)ek * n + en)];
+                    v.y = A[2 * ((size_t)ek * n + en) + 1];
+                }
+            } else {
+                const int tq = ncol >> 1;
+                if ((tq >> 1) < tp) {
+                    const int en = 4 * TF + (tq >> 1) + (tq & 1) * m;
+                    const double ar = A[2 * ((size_t)ek * n + en)], ai = A[2 * ((size_t)ek * n + en) + 1];
+                    v = (ncol & 1) ? make_double2(ai, ar) : make_double2(ar, -ai);
+                }
+            }
         }
         frag[idx] = v;
     }
 }
 
-// per-warp shared scratch layout (doubles)
-template <int T>
-struct HafSmem {
-    static constexpr int MP = 4 * T;                      // padded m
-    static constexpr int NSLOT = MP / 2 + 1;              // >= nprod + 1
-    static constexpr int FRAG_D = 2 * T * T * 64;         // doubles in fragment table
-    static constexpr int PART_D = NSLOT * 8 * 4;          // per-row (g) partial inner products
-    static constexpr int P_D = (MP + 2) * 4 * 2;          // P[k][q] complex
-    static constexpr int WARP_D = PART_D + 3 * P_D;       // partials, P, L, c
-    static constexpr size_t BYTES = sizeof(double) * (FRAG_D + HAF_WARPS * WARP_D);
+template <int TF, bool TAIL, int WARPS>
+struct HafCfg {
+    static constexpr int NK = 2 * TF + (TAIL ? 1 : 0);
+    static constexpr int NT = TF + (TAIL ? 1 : 0);
+    static constexpr int MP = 4 * TF + (TAIL ? 2 : 0);     // upper bound on m
+    static constexpr int FRAG_D = NK * NT * 64;            // doubles in fragment table
+    static constexpr int PART_D = (MP + 2) * 8 * 2;        // part[j][g] complex, j = 0..MP+1
+    static constexpr int P_D = (MP + 2) * 4 * 2;           // P[k][q] complex
+    static constexpr int WARP_D = PART_D + 3 * P_D;        // partials, P, L, c
+    static constexpr size_t BYTES = sizeof(double) * (FRAG_D + WARPS * WARP_D);
 };
 
-// One multiply W_new = Y * A' on the tensor pipe: 2T K-chunks x T N-tiles x 4 DMMA.
-template <int T>
-__device__ __forceinline__ void haf_step(const double2* __restrict__ sfrag, int lane, const double (&yr)[2 * T],
-                                         const double (&yi)[2 * T], double (&cr)[T][2], double (&ci)[T][2]) {
+template <int TF, bool TAIL>
+struct HafRow {  // one 8-row panel slice held by a thread
+    double wr[TF > 0 ? TF : 1][2], wi[TF > 0 ? TF : 1][2];
+    double wtr, wti;
+};
+template <int TF, bool TAIL>
+struct HafY {
+    double yr[TF > 0 ? 2 * TF : 1], yi[TF > 0 ? 2 * TF : 1];
+    double ytr, yti;
+};
+
+// W <- Y * A' on the tensor pipe
+template <int TF, bool TAIL>
+__device__ __forceinline__ void haf_step(const double2* __restrict__ sfrag, int lane, const HafY<TF, TAIL>& y,
+                                         HafRow<TF, TAIL>& w) {
+    constexpr int NK = 2 * TF + (TAIL ? 1 : 0), NT = TF + (TAIL ? 1 : 0);
 #pragma unroll
-    for (int tp = 0; tp < T; ++tp) {
-        cr[tp][0] = cr[tp][1] = 0.0;
-        ci[tp][0] = ci[tp][1] = 0.0;
+    for (int tp = 0; tp < TF; ++tp) {
+        w.wr[tp][0] = w.wr[tp][1] = 0.0;
+        w.wi[tp][0] = w.wi[tp][1] = 0.0;
     }
+    w.wtr = w.wti = 0.0;
 #pragma unroll
-    for (int kap = 0; kap < 2 * T; ++kap) {
+    for (int kap = 0; kap < NK; ++kap) {
+        const double ar = kap < 2 * TF ? y.yr[kap < 2 * TF ? kap : 0] : y.ytr;
+        const double ai = kap < 2 * TF ? y.yi[kap < 2 * TF ? kap : 0] : y.yti;
 #pragma unroll
-        for (int tp = 0; tp < T; ++tp) {
-            const double2 b = sfrag[(kap * T + tp) * 32 + lane];
+        for (int tp = 0; tp < TF; ++tp) {
+            const double2 b = sfrag[(kap * NT + tp) * 32 + lane];
             const double nbi = -b.y;
-            dmma884(cr[tp][0], cr[tp][1], yr[kap], b.x);
-            dmma884(ci[tp][0], ci[tp][1], yr[kap], b.y);
-            dmma884(cr[tp][0], cr[tp][1], yi[kap], nbi);
-            dmma884(ci[tp][0], ci[tp][1], yi[kap], b.x);
+            dmma884(w.wr[tp][0], w.wr[tp][1], ar, b.x);
+            dmma884(w.wi[tp][0], w.wi[tp][1], ar, b.y);
+            dmma884(w.wr[tp][0], w.wr[tp][1], ai, nbi);
+            dmma884(w.wi[tp][0], w.wi[tp][1], ai, b.x);
+        }
+        if (TAIL) {
+            const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
+            dmma884(w.wtr, w.wti, ar, b.x);
+            dmma884(w.wtr, w.wti, ai, b.y);
         }
     }
 }
 
-// Y = S_j applied to the row held in (wr, wi): swap partners (same tile, other register), sign delta.
-template <int T>
-__device__ __forceinline__ void haf_applyS(const double (&wr)[T][2], const double (&wi)[T][2],
-                                           const unsigned (&sm)[T], double (&yr)[2 * T], double (&yi)[2 * T]) {
+#define WB_CFMA(sr, si, xr_, xi_, yr_, yi_)                  \
+    do {                                                       \
+        sr = fma(xr_, yr_, sr); sr = fma(-(xi_), yi_, sr);     \
+        si = fma(xr_, yi_, si); si = fma(xi_, yr_, si);        \
+    } while (0)
+
+// Y <- S_j W (swap partners, sign delta).  If IP: also odd = <X, Y_old>, even = <X, Y_new> over this
+// thread's slots, X = W of the partner row (lane ^ 16) or W itself (SELF, the loop row).
+template <int TF, bool TAIL, bool IP, bool SELF>
+__device__ __forceinline__ void haf_advance(const HafRow<TF, TAIL>& w, HafY<TF, TAIL>& y, const unsigned* sm,
+                                            unsigned smt, double& orr, double& oi, double& er, double& ei) {
+    double o2r = 0.0, o2i = 0.0, e2r = 0.0, e2i = 0.0;  // second chains for ILP
+    orr = oi = er = ei = 0.0;
 #pragma unroll
-    for (int tau = 0; tau < T; ++tau) {
-        yr[2 * tau + 0] = flipsign(wr[tau][1], sm[tau]);
-        yr[2 * tau + 1] = flipsign(wr[tau][0], sm[tau]);
-        yi[2 * tau + 0] = flipsign(wi[tau][1], sm[tau]);
-        yi[2 * tau + 1] = flipsign(wi[tau][0], sm[tau]);
+    for (int tau = 0; tau < TF; ++tau) {
+        double x0r = 0, x0i = 0, x1r = 0, x1i = 0;
+        if (IP) {
+            x0r = SELF ? w.wr[tau][0] : shfl_xor_d(w.wr[tau][0], 16);
+            x0i = SELF ? w.wi[tau][0] : shfl_xor_d(w.wi[tau][0], 16);
+            x1r = SELF ? w.wr[tau][1] : shfl_xor_d(w.wr[tau][1], 16);
+            x1i = SELF ? w.wi[tau][1] : shfl_xor_d(w.wi[tau][1], 16);
+            WB_CFMA(orr, oi, x0r, x0i, y.yr[2 * tau], y.yi[2 * tau]);
+            WB_CFMA(o2r, o2i, x1r, x1i, y.yr[2 * tau + 1], y.yi[2 * tau + 1]);
+        }
+        y.yr[2 * tau + 0] = flipsign(w.wr[tau][1], sm[tau]);
+        y.yr[2 * tau + 1] = flipsign(w.wr[tau][0], sm[tau]);
+        y.yi[2 * tau + 0] = flipsign(w.wi[tau][1], sm[tau]);
+        y.yi[2 * tau + 1] = flipsign(w.wi[tau][0], sm[tau]);
+        if (IP) {
+            WB_CFMA(er, ei, x0r, x0i, y.yr[2 * tau], y.yi[2 * tau]);
+            WB_CFMA(e2r, e2i, x1r, x1i, y.yr[2 * tau + 1], y.yi[2 * tau + 1]);
+        }
+    }
+    if (TAIL) {
+        double xr = 0, xi = 0;
+        if (IP) {
+            xr = SELF ? w.wtr : shfl_xor_d(w.wtr, 16);
+            xi = SELF ? w.wti : shfl_xor_d(w.wti, 16);
+            WB_CFMA(orr, oi, xr, xi, y.ytr, y.yti);
+        }
+        y.ytr = flipsign(shfl_xor_d(w.wtr, 1), smt);
+        y.yti = flipsign(shfl_xor_d(w.wti, 1), smt);
+        if (IP) WB_CFMA(er, ei, xr, xi, y.ytr, y.yti);
+    }
+    if (IP) {
+        orr += o2r; oi += o2i; er += e2r; ei += e2i;
+        orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1); er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
+        orr += shfl_xor_d(orr, 2); oi += shfl_xor_d(oi, 2); er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
     }
 }
 
-// bilinear (not Hermitian) inner product sum_e x[e] * y[e] over this thread's slots
-template <int T>
-__device__ __forceinline__ void haf_ip(const double (&xr)[T][2], const double (&xi)[T][2], const double (&yr)[2 * T],
-                                       const double (&yi)[2 * T], double& sr, double& si) {
-    double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;  // two chains for ILP
-#pragma unroll
-    for (int tau = 0; tau < T; ++tau) {
-        ar = fma(xr[tau][0], yr[2 * tau], ar);
-        ar = fma(-xi[tau][0], yi[2 * tau], ar);
-        ai = fma(xr[tau][0], yi[2 * tau], ai);
-        ai = fma(xi[tau][0], yr[2 * tau], ai);
-        br = fma(xr[tau][1], yr[2 * tau + 1], br);
-        br = fma(-xi[tau][1], yi[2 * tau + 1], br);
-        bi = fma(xr[tau][1], yi[2 * tau + 1], bi);
-        bi = fma(xi[tau][1], yr[2 * tau + 1], bi);
-    }
-    sr = ar + br;
-    si = ai + bi;
-}
-
-template <int T>
-__global__ void __launch_bounds__(HAF_THREADS, 1)
+template <int TF, bool TAIL, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1)
 haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A, const double* __restrict__ D, int n,
                 int m, uint64_t j0, uint64_t j1, double* __restrict__ partials) {
-    using L = HafSmem<T>;
+    using C = HafCfg<TF, TAIL, WARPS>;
     extern __shared__ __align__(16) double smem[];
     double2* sfrag = reinterpret_cast<double2*>(smem);
-    for (int i = threadIdx.x; i < L::FRAG_D / 2; i += HAF_THREADS) sfrag[i] = frag_g[i];
+    for (int i = threadIdx.x; i < C::FRAG_D / 2; i += 32 * WARPS) sfrag[i] = frag_g[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
-    double* wsm = smem + L::FRAG_D + warp * L::WARP_D;
-    double4* part = reinterpret_cast<double4*>(wsm);  // [slot][g] -> (odd.re, odd.im, even.re, even.im), written by t == 0
-    double* Pk = wsm + L::PART_D;                     // P[k][q] complex: Pk[(k*4+q)*2 + {0,1}]
-    double* Lk = Pk + L::P_D;                         // loop terms
-    double* Ck = Lk + L::P_D;                         // series coefficients
+    double* wsm = smem + C::FRAG_D + warp * C::WARP_D;
+    double2* part = reinterpret_cast<double2*>(wsm);  // part[j * 8 + g]: row-g share of tr(M^j)
+    double* Pk = wsm + C::PART_D;                     // P[k][q] complex: Pk[(k*4+q)*2 + {0,1}]
+    double* Lk = Pk + C::P_D;                         // loop terms
+    double* Ck = Lk + C::P_D;                         // series coefficients
     const bool loop = (D != nullptr);
-    const int nprod = (m - 1) >> 1;                   // products needed for p_1..p_m with pairing
-    const int nstepD = m >> 1;                        // products of the D row (l_1..l_m)
+    const int tp = TAIL ? m - 4 * TF : 0;             // vertex pairs in the tail tile (1 or 2)
+    const int nprod = (m - 1) >> 1;                   // products: B_2 .. B_K, K = nprod + 1
+    const int K = nprod + 1;                          // tr(M^j), j <= K, come from single elements
+    const int nstepD = m >> 1;                        // products of the loop row (l_1..l_m)
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
-    const uint64_t gstride = (uint64_t)gridDim.x * HAF_WARPS;
+    const uint64_t gstride = (uint64_t)gridDim.x * WARPS;
 
     cdd acc;
     acc.re = {0.0, 0.0};
     acc.im = {0.0, 0.0};
 
-    for (uint64_t G = (uint64_t)blockIdx.x * HAF_WARPS + warp; G < ngroups; G += gstride) {
+    for (uint64_t G = (uint64_t)blockIdx.x * WARPS + warp; G < ngroups; G += gstride) {
         const uint64_t jq = j0 + 4 * G + q;
         const bool valid = jq < j1;
-        unsigned sm[T];
+        unsigned sm[TF > 0 ? TF : 1];
 #pragma unroll
-        for (int tau = 0; tau < T; ++tau) {
+        for (int tau = 0; tau < TF; ++tau) {
             const int i = 4 * tau + t;
             const unsigned kept = (i < m) ? (unsigned)((jq >> (m - 1 - i)) & 1ull) : 1u;
             sm[tau] = kept ? 0u : 0x80000000u;
         }
-        for (int s = lane; s < (nprod + 1) * 8; s += 32) part[s] = make_double4(0.0, 0.0, 0.0, 0.0);
+        unsigned smt = 0u;
+        if (TAIL && (t >> 1) < tp) smt = ((jq >> (m - 1 - (4 * TF + (t >> 1)))) & 1ull) ? 0u : 0x80000000u;
+        for (int s = lane; s < (m + 2) * 8; s += 32) part[s] = make_double2(0.0, 0.0);
         __syncwarp();
 
         const int npanels = m + (loop ? 1 : 0);
         for (int i = 0; i < npanels; ++i) {
             const bool isD = (i == m);
-            double wr[T][2], wi[T][2], yr[2 * T], yi[2 * T];
+            HafRow<TF, TAIL> w;
+            HafY<TF, TAIL> y = {};
             // ---- first iterate: row v of A' (B_1 = A'), or D for the loop row
             {
                 const int v = i + half * m;
                 const double* src = isD ? D : (A + 2 * (size_t)v * n);
                 const bool rowok = isD ? (half == 0) : true;
 #pragma unroll
-                for (int tau = 0; tau < T; ++tau) {
+                for (int tau = 0; tau < TF; ++tau) {
 #pragma unroll
                     for (int r = 0; r < 2; ++r) {
                         const int iv = 4 * tau + t;
                         const bool ok = rowok && (iv < m);
                         const int e = iv + r * m;
-                        wr[tau][r] = ok ? __ldg(src + 2 * e) : 0.0;
-                        wi[tau][r] = ok ? __ldg(src + 2 * e + 1) : 0.0;
+                        w.wr[tau][r] = ok ? __ldg(src + 2 * e) : 0.0;
+                        w.wi[tau][r] = ok ? __ldg(src + 2 * e + 1) : 0.0;
                     }
+                }
+                w.wtr = w.wti = 0.0;
+                if (TAIL) {
+                    const bool ok = rowok && ((t >> 1) < tp);
+                    const int e = 4 * TF + (t >> 1) + (t & 1) * m;
+                    w.wtr = ok ? __ldg(src + 2 * e) : 0.0;
+                    w.wti = ok ? __ldg(src + 2 * e + 1) : 0.0;
                 }
             }
-            // sign of this row's vertex pair in subset jq (delta_i); unused for the D row
+            // delta of this row's vertex pair in subset jq
             const double rs = isD ? 1.0 : (((jq >> (m - 1 - (isD ? 0 : i))) & 1ull) ? 1.0 : -1.0);
-            haf_applyS<T>(wr, wi, sm, yr, yi);
-            {
-                // slot 0: odd = p_1 (D row: l_1), even = p_2
-                double xr[T][2], xi[T][2];
-                double er = 0.0, ei = 0.0, orr = 0.0, oi = 0.0;
-                if (!isD) {
-#pragma unroll
-                    for (int tau = 0; tau < T; ++tau)
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            xr[tau][r] = shfl_xor_d(wr[tau][r], 16);
-                            xi[tau][r] = shfl_xor_d(wi[tau][r], 16);
-                        }
-                    haf_ip<T>(xr, xi, yr, yi, er, ei);
-                    if (t == 0) {  // p_1 = sum_c delta_c A'[c, sigma(c)]
-                        const int v = i + half * m, sv = i + (1 - half) * m;
-                        orr = __ldg(A + 2 * ((size_t)v * n + sv));
-                        oi = __ldg(A + 2 * ((size_t)v * n + sv) + 1);
+            // which thread of the row holds element sigma(v) (the "diagonal" of B_k S), and where
+            const bool in_tail = TAIL && (i >= 4 * TF);
+            const int own_t = in_tail ? 2 * (i - 4 * TF) + (1 - half) : (i & 3);
+            const int own_tau = i >> 2;
+            double orr, oi, er, ei;
+            if (!isD) {
+                // tr(M) share: A'[v, sigma(v)]; tr(M^2) only by pairing when K < 2 (m <= 2)
+                if (K < 2) haf_advance<TF, TAIL, true, false>(w, y, sm, smt, orr, oi, er, ei);
+                else haf_advance<TF, TAIL, false, false>(w, y, sm, smt, orr, oi, er, ei);
+                if (t == 0) {
+                    const int v = i + half * m, sv = i + (1 - half) * m;
+                    double2 p = part[1 * 8 + g];
+                    p.x += rs * __ldg(A + 2 * ((size_t)v * n + sv));
+                    p.y += rs * __ldg(A + 2 * ((size_t)v * n + sv) + 1);
+                    part[1 * 8 + g] = p;
+                    if (K < 2 && m >= 2) {
+                        double2 p2 = part[2 * 8 + g];
+                        p2.x += rs * er; p2.y += rs * ei;
+                        part[2 * 8 + g] = p2;
                     }
-                    er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
-                    er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
-                    if (t == 0) {
-                        double4 p = part[g];
-                        p.x += rs * orr; p.y += rs * oi; p.z += rs * er; p.w += rs * ei;
-                        part[g] = p;
-                    }
-                } else {
-                    haf_ip<T>(wr, wi, yr, yi, orr, oi);  // l_1 = <Z_0, S Z_0>
-                    orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1);
-                    orr += shfl_xor_d(orr, 2); oi += shfl_xor_d(oi, 2);
-                    if (t == 0 && half == 0) { Lk[(1 * 4 + q) * 2] = orr; Lk[(1 * 4 + q) * 2 + 1] = oi; }
                 }
+            } else {
+                HafY<TF, TAIL> y0;  // l_1 = <Z_0, S Z_0>
+                haf_advance<TF, TAIL, false, true>(w, y0, sm, smt, orr, oi, er, ei);
+                y = y0;
+                haf_advance<TF, TAIL, true, true>(w, y, sm, smt, orr, oi, er, ei);
+                if (t == 0 && half == 0) { Lk[(1 * 4 + q) * 2] = orr; Lk[(1 * 4 + q) * 2 + 1] = oi; }
             }
             const int nsteps = isD ? nstepD : nprod;
             for (int k = 1; k <= nsteps; ++k) {
-                haf_step<T>(sfrag, lane, yr, yi, wr, wi);  // (wr, wi) <- Y * A'
-                double xr[T][2], xi[T][2];
+                haf_step<TF, TAIL>(sfrag, lane, y, w);  // w = row of B_{k+1} (Z_k for the loop row)
                 if (!isD) {
+                    // tr(M^(k+1)) share: element sigma(v) of this row
+                    if (t == own_t) {
+                        double dr, di;
+                        if (in_tail) { dr = w.wtr; di = w.wti; }
+                        else {
+                            dr = 0.0; di = 0.0;
 #pragma unroll
-                    for (int tau = 0; tau < T; ++tau)
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) {
-                            xr[tau][r] = shfl_xor_d(wr[tau][r], 16);
-                            xi[tau][r] = shfl_xor_d(wi[tau][r], 16);
+                            for (int tau = 0; tau < TF; ++tau)
+                                if (tau == own_tau) { dr = half ? w.wr[tau][0] : w.wr[tau][1]; di = half ? w.wi[tau][0] : w.wi[tau][1]; }
                         }
-                } else {
-#pragma unroll
-                    for (int tau = 0; tau < T; ++tau)
-#pragma unroll
-                        for (int r = 0; r < 2; ++r) { xr[tau][r] = wr[tau][r]; xi[tau][r] = wi[tau][r]; }
-                }
-                double orr, oi, er, ei;
-                haf_ip<T>(xr, xi, yr, yi, orr, oi);       // with Y_old
-                haf_applyS<T>(wr, wi, sm, yr, yi);        // Y_new
-                haf_ip<T>(xr, xi, yr, yi, er, ei);        // with Y_new
-                orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1); er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
-                orr += shfl_xor_d(orr, 2); oi += shfl_xor_d(oi, 2); er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
-                if (!isD) {
-                    if (t == 0) {
-                        double4 p = part[k * 8 + g];       // odd: p_{2k+1}, even: p_{2k+2}
-                        p.x += rs * orr; p.y += rs * oi; p.z += rs * er; p.w += rs * ei;
-                        part[k * 8 + g] = p;
+                        double2 p = part[(k + 1) * 8 + g];
+                        p.x += rs * dr; p.y += rs * di;
+                        part[(k + 1) * 8 + g] = p;
                     }
-                } else {                                   // l_{2k}, l_{2k+1}
+                    const bool needO = (2 * k + 1 > K) && (2 * k + 1 <= m);
+                    const bool needE = (2 * k + 2 > K) && (2 * k + 2 <= m);
+                    if (needO || needE) {
+                        haf_advance<TF, TAIL, true, false>(w, y, sm, smt, orr, oi, er, ei);
+                        if (t == 0) {
+                            if (needO) { double2 p = part[(2 * k + 1) * 8 + g]; p.x += rs * orr; p.y += rs * oi; part[(2 * k + 1) * 8 + g] = p; }
+                            if (needE) { double2 p = part[(2 * k + 2) * 8 + g]; p.x += rs * er; p.y += rs * ei; part[(2 * k + 2) * 8 + g] = p; }
+                        }
+                    } else {
+                        haf_advance<TF, TAIL, false, false>(w, y, sm, smt, orr, oi, er, ei);
+                    }
+                } else {  // l_{2k} = <Z_k, S Z_{k-1}>, l_{2k+1} = <Z_k, S Z_k>
+                    haf_advance<TF, TAIL, true, true>(w, y, sm, smt, orr, oi, er, ei);
                     if (t == 0 && half == 0) {
                         Lk[((2 * k) * 4 + q) * 2] = orr; Lk[((2 * k) * 4 + q) * 2 + 1] = oi;
                         Lk[((2 * k + 1) * 4 + q) * 2] = er; Lk[((2 * k + 1) * 4 + q) * 2 + 1] = ei;
                     }
                 }
             }
+            __syncwarp();  // part[] slots are updated by different lanes in the next panel
         }
-        __syncwarp();
         // ---- combine the two rows (vertex i and i + m) of each subset q
-        for (int s = lane; s < (nprod + 1) * 4; s += 32) {
-            const int slot = s >> 2, qq = s & 3;
-            const double4 a = part[slot * 8 + qq], b = part[slot * 8 + qq + 4];
-            Pk[((2 * slot + 1) * 4 + qq) * 2] = a.x + b.x; Pk[((2 * slot + 1) * 4 + qq) * 2 + 1] = a.y + b.y;
-            Pk[((2 * slot + 2) * 4 + qq) * 2] = a.z + b.z; Pk[((2 * slot + 2) * 4 + qq) * 2 + 1] = a.w + b.w;
+        for (int s = lane; s < (m + 1) * 4; s += 32) {
+            const int j = s >> 2, qq = s & 3;
+            const double2 a = part[j * 8 + qq], b = part[j * 8 + qq + 4];
+            Pk[(j * 4 + qq) * 2] = a.x + b.x; Pk[(j * 4 + qq) * 2 + 1] = a.y + b.y;
         }
         __syncwarp();
         // ---- coefficient [eta^m] of exp(sum_i a_i eta^i), a_i = p_i/(2i) (+ l_i/2): c_t = (1/t) sum_i i a_i c_{t-i}
@@ -288,21 +362,52 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
         }
         __syncwarp();
     }
-    __shared__ double red[HAF_WARPS * 4];
+    __shared__ double red[WARPS * 4];
     block_reduce_store(acc, red, partials);
 }
 
-template <int T>
-static int launch_haf(const double2* frag, const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
-                      double* partials, int grid, cudaStream_t st) {
-    using L = HafSmem<T>;
-    WB_CUDA(cudaFuncSetAttribute(haf_dmma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-    haf_dmma_kernel<T><<<grid, HAF_THREADS, L::BYTES, st>>>(frag, dA, dD, n, m, j0, j1, partials);
+// Warps per CTA (one CTA per SM): 8 (<= 255 registers) or 12 (<= 168 registers, 3 warps per scheduler).
+// Chosen per call: env WB200_HAF_WARPS overrides the default picked from measurements.
+static int haf_pick_warps(int TF, int tail) {
+    static int env = -1;
+    if (env < 0) {
+        const char* e = getenv("WB200_HAF_WARPS");
+        env = e ? atoi(e) : 0;
+    }
+    if (env == 8 || env == 12) return env;
+    (void)TF; (void)tail;
+    return 12;  // measured on B200: 12 warps beat 8 by 2-4 % at n = 40..64 (profiles/r01_hafnian_sweep.txt)
+}
+
+template <int TF, bool TAIL, int WARPS>
+static int launch_haf_w(const double2* frag, const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
+                        double* partials, uint64_t ngroups, int sms, int* grid_out, cudaStream_t st) {
+    using C = HafCfg<TF, TAIL, WARPS>;
+    auto kern = haf_dmma_kernel<TF, TAIL, WARPS>;
+    uint64_t want = (ngroups + WARPS - 1) / WARPS;
+    const int grid = (int)(want < (uint64_t)sms ? (want ? want : 1) : (uint64_t)sms);
+    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
+    kern<<<grid, 32 * WARPS, C::BYTES, st>>>(frag, dA, dD, n, m, j0, j1, partials);
     WB_CUDA(cudaGetLastError());
+    *grid_out = grid;
     return WB200_OK;
 }
 
+template <int TF, bool TAIL>
+static int launch_haf(const double2* frag, const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
+                      double* partials, uint64_t ngroups, int sms, int* grid_out, cudaStream_t st) {
+    if (haf_pick_warps(TF, TAIL) == 12)
+        return launch_haf_w<TF, TAIL, 12>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    return launch_haf_w<TF, TAIL, 8>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+}
+
 constexpr int HAF_MAX_GRID = 4096;
+
+static void haf_shape(int m, int* TF, int* tail) {
+    const int r = m & 3;
+    if (m >= 5 && (r == 1 || r == 2)) { *TF = m >> 2; *tail = 1; }
+    else { *TF = (m + 3) >> 2; *tail = 0; }
+}
 
 }  // namespace wb
 
@@ -310,8 +415,7 @@ using namespace wb;
 
 extern "C" size_t wb200_hafnian_workspace_bytes(int n) {
     if (n < 2 || n > 64 || (n & 1)) return 0;
-    const int m = n / 2, T = (m + 3) / 4;
-    return sizeof(double) * ((size_t)2 * T * T * 64 + (size_t)HAF_MAX_GRID * 4) + 256;
+    return sizeof(double) * ((size_t)17 * 9 * 64 + (size_t)HAF_MAX_GRID * 4) + 256;
 }
 
 extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint64_t j0, uint64_t j1, double* d_out4,
@@ -319,7 +423,9 @@ extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint
     if (!dA || !d_out4 || !d_workspace) { set_error("hafnian: null pointer"); return WB200_EINVAL; }
     if (n < 2 || (n & 1)) { set_error("hafnian: n must be even and >= 2 (got %d)", n); return WB200_EINVAL; }
     if (n > 64) { set_error("hafnian: n = %d exceeds the DMMA kernel limit of 64", n); return WB200_ENOSUP; }
-    const int m = n / 2, T = (m + 3) / 4;
+    const int m = n / 2;
+    int TF, tail;
+    haf_shape(m, &TF, &tail);
     const uint64_t steps = 1ull << (m - 1);
     if (j0 > j1 || j1 > steps) { set_error("hafnian: bad subset range"); return WB200_EINVAL; }
     if (workspace_bytes < wb200_hafnian_workspace_bytes(n)) { set_error("hafnian: workspace too small"); return WB200_EINVAL; }
@@ -329,23 +435,21 @@ extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
     double2* frag = reinterpret_cast<double2*>(d_workspace);
-    double* partials = reinterpret_cast<double*>(d_workspace) + (size_t)2 * T * T * 64;
-    haf_prep_kernel<<<8, 256, 0, st>>>(dA, n, m, T, frag);
+    double* partials = reinterpret_cast<double*>(d_workspace) + (size_t)17 * 9 * 64;
+    haf_prep_kernel<<<8, 256, 0, st>>>(dA, n, m, TF, tail, frag);
     WB_CUDA(cudaGetLastError());
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
-    uint64_t want = (ngroups + HAF_WARPS - 1) / HAF_WARPS;
-    int grid = (int)(want < (uint64_t)sms ? (want ? want : 1) : (uint64_t)sms);
+    int grid = 1;
     int rc = WB200_ENOSUP;
-    switch (T) {
-        case 1: rc = launch_haf<1>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 2: rc = launch_haf<2>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 3: rc = launch_haf<3>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 4: rc = launch_haf<4>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 5: rc = launch_haf<5>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 6: rc = launch_haf<6>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 7: rc = launch_haf<7>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
-        case 8: rc = launch_haf<8>(frag, dA, dD, n, m, j0, j1, partials, grid, st); break;
+#define WB_HAF_CASE(tf, tl) case (tf) * 2 + (tl): rc = launch_haf<tf, (tl) != 0>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, &grid, st); break;
+    switch (TF * 2 + tail) {
+        WB_HAF_CASE(1, 0) WB_HAF_CASE(2, 0) WB_HAF_CASE(3, 0) WB_HAF_CASE(4, 0)
+        WB_HAF_CASE(5, 0) WB_HAF_CASE(6, 0) WB_HAF_CASE(7, 0) WB_HAF_CASE(8, 0)
+        WB_HAF_CASE(1, 1) WB_HAF_CASE(2, 1) WB_HAF_CASE(3, 1) WB_HAF_CASE(4, 1)
+        WB_HAF_CASE(5, 1) WB_HAF_CASE(6, 1) WB_HAF_CASE(7, 1)
+        default: set_error("hafnian: unsupported tile shape TF=%d tail=%d", TF, tail);
     }
+#undef WB_HAF_CASE
     if (rc) return rc;
     final_reduce_kernel<<<1, 32, 0, st>>>(partials, grid, d_out4);
     WB_CUDA(cudaGetLastError());
