@@ -53,6 +53,27 @@ def make_input(workload):
     raise SystemExit(f"unknown workload {workload}")
 
 
+def make_gbs_state(M, B, seed, r=0.5, eta=0.8, hbar=2.0, mean_photons=0.45, max_total=10):
+    """BASELINE config 3: M-mode state  cov = eta (hbar/2) S S^T + (1 - eta)(hbar/2) I  with
+    S = interferometer(U_Haar) . squeezing(r), means 0.3 N(0,1), and B patterns drawn i.i.d. Poisson(0.45) per
+    mode, rejected if the total exceeds ``max_total``.  Returns (mu, cov, patterns[B, M])."""
+    rng = np.random.default_rng(seed)
+    Z = (rng.standard_normal((M, M)) + 1j * rng.standard_normal((M, M))) / np.sqrt(2)
+    Q, R = np.linalg.qr(Z)
+    U = Q * (np.diag(R) / np.abs(np.diag(R)))
+    X, Y = U.real, U.imag
+    Sint = np.block([[X, -Y], [Y, X]])                     # symplectic of a passive interferometer
+    Ssq = np.diag(np.concatenate([np.exp(-r) * np.ones(M), np.exp(r) * np.ones(M)]))
+    S = Sint @ Ssq
+    cov = eta * (hbar / 2) * S @ S.T + (1 - eta) * (hbar / 2) * np.identity(2 * M)
+    mu = 0.3 * rng.standard_normal(2 * M)
+    pats = np.zeros((0, M), dtype=np.int32)
+    while len(pats) < B:
+        cand = rng.poisson(mean_photons, size=(2 * (B - len(pats)) + 16, M)).astype(np.int32)
+        pats = np.concatenate([pats, cand[cand.sum(axis=1) <= max_total]])
+    return mu, cov, np.ascontiguousarray(pats[:B])
+
+
 def units_and_flops(kind, n):
     """(units per step, algorithmic flops per unit of THIS implementation, reference-algorithm flops per unit)."""
     if kind in ("hafnian", "lhaf"):

@@ -60,6 +60,28 @@ int wb200_lhaf_general_host(int device, const double* A, const double* D, const 
 /* total number of subset indices for these arguments (reference `steps`, _hafnian.py:432-435, 535-538) */
 int wb200_lhaf_general_steps(const int32_t* edge_reps, int n_edges, int glynn, int has_odd, uint64_t* steps);
 
+/* ---- batched front end: loop hafnians of many repetition patterns of ONE matrix ----------------------
+ * Replaces the per-pattern Python loop of probabilities() / density_matrix_element
+ * (thewalrus/quantum/fock_tensors.py:191-232, 412-421): for every row rpt[b] (nv repetition counts) this
+ * evaluates loop_hafnian(A, D = gamma, reps = rpt[b]) (thewalrus/_hafnian.py:581-631), or
+ * hafnian_repeated(A, rpt[b]) when gamma is NULL (:470-508), including the N = 0 / N = 1 / odd-N early exits
+ * and the final Glynn scale.  The vertex pairing (matched_reps, :80-159) is done on the device.
+ * A: nv x nv complex (NOT permuted), gamma: nv complex or NULL, rpt: B x nv int32, out: B complex (re, im).
+ * nv <= 64; per pattern at most 32 edges and series order <= 200. */
+int wb200_lhaf_patterns_host(int device, const double* A, const double* gamma, int nv, const int32_t* rpt,
+                             int64_t B, int glynn, double* out, double* kernel_ms);
+
+/* ---- loop_hafnian_batch sweep -------------------------------------------------------------------------
+ * Replaces _calc_loop_hafnian_batch_even / _odd (thewalrus/loop_hafnian_batch.py:51-208).  Ax (n x n, n = 2E),
+ * Dx: already edge-ordered by add_batch_edges_even/odd (:211-257); edge_reps = [batch_max, fixed...] (even
+ * variant) or [batch_max, 1, fixed...] (odd variant).  Subset index j in [0, prod(edge_reps + 1)) (:79, :155).
+ * out: length x {re_hi, re_lo, im_hi, im_lo}, length = 2 batch_max + cutoff_extra + 1 (+1 for the odd
+ * variant), WITHOUT the final 0.5^((N_fixed + j) / 2) scaling (:118-121), so shards can be added first. */
+int wb200_lhaf_batch_steps(const int32_t* edge_reps, int n_edges, uint64_t* steps);
+int wb200_lhaf_batch_host(int device, const double* Ax, const double* Dx, int n, const int32_t* edge_reps,
+                          int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* out,
+                          int length, double* kernel_ms);
+
 /* ---- permanent --------------------------------------------------------------------------------------
  * Replaces perm_bbfg (thewalrus/_permanent.py:130-168; method 0, steps k in [0, 2^(n-1)), final scale
  * 2^(1-n)) and perm_ryser (:86-127; method 1, steps k in [0, 2^n), no scale).  Step k evaluates the

@@ -123,6 +123,26 @@ def main():
     out["dme"] = {"M": M, "cov": cov.tolist(), "mu": mu.tolist(), "patterns": pats,
                   "displaced": [float(density_matrix_element(mu, cov, p, p).real) for p in pats],
                   "zero_mean": [float(density_matrix_element(0 * mu, cov, p, p).real) for p in pats]}
+    # host-side state preparation of the same state (pins thewalrus_b200.quantum.Qmat / Amat / prefactor)
+    from thewalrus.quantum.conversions import complex_to_real_displacements  # noqa: E402
+    from thewalrus.quantum.fock_tensors import _prefactor  # noqa: E402
+
+    out["conv"] = {"Q": enc(Qmat(cov, hbar=2)), "A": enc(Amat(cov, hbar=2)),
+                   "beta": enc(complex_to_real_displacements(mu, hbar=2)),
+                   "prefactor": enc(_prefactor(mu, cov, hbar=2))}
+    # BASELINE config 3 state (16 modes, bench.make_gbs_state): reference probabilities of a pattern sample
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import bench  # noqa: E402
+
+    mu16, cov16, pats16 = bench.make_gbs_state(16, 2000, seed=3016)
+    order = np.argsort(pats16.sum(axis=1), kind="stable")
+    pick = [int(order[i]) for i in (0, 5, 50, 300, 700, 1000, 1300, 1600, 1800, 1900, 1950, 1990, 1995, 1999)]
+    out["dme16"] = {"seed": 3016, "B": 2000, "index": pick, "patterns": [pats16[i].tolist() for i in pick],
+                    "mu": mu16.tolist(), "cov": cov16.tolist(),
+                    "displaced": [float(density_matrix_element(mu16, cov16, list(pats16[i]), list(pats16[i])).real)
+                                  for i in pick],
+                    "zero_mean": [float(density_matrix_element(0 * mu16, cov16, list(pats16[i]), list(pats16[i])).real)
+                                  for i in pick]}
     with open(os.path.join(HERE, "reference_outputs.json"), "w") as fh:
         json.dump(out, fh)
     print("wrote", os.path.join(HERE, "reference_outputs.json"), {k: len(v) for k, v in out.items()})

@@ -37,7 +37,18 @@ def _worker(rank, world, port, q):
     # integer (exact) path used by perm on int64 input
     part = np.array([float(rank + 1), float(7 * rank)])
     t2 = _engine.allreduce_partials(part, None)
-    q.put((rank, total, table.tolist(), t2.tolist()))
+    # batched front end: PATTERNS are sharded (ragged: 7 patterns over 2 ranks) and all-gathered
+    from oracle import walrus_oracle as wo
+
+    A5 = A[:5, :5]
+    g5 = np.diag(A)[:5].copy()
+    rpt = np.random.default_rng(5).integers(0, 3, (7, 5)).astype(np.int32)
+
+    def local(rows):
+        return np.array([wo.loop_hafnian(A5, g5, [int(x) for x in r]) for r in rows], dtype=np.complex128)
+
+    pats = _engine.run_sharded_patterns(A5, g5, rpt, True, True, None, local=local)
+    q.put((rank, total, table.tolist(), t2.tolist(), pats.tolist()))
     dist.destroy_process_group()
 
 
@@ -61,7 +72,12 @@ def test_two_rank_gloo_sharded_sum():
     G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     A = G + G.T
     want = co.hafnian(A)
-    (r0, v0, tab0, i0), (r1, v1, tab1, i1) = res
+    (r0, v0, tab0, i0, p0), (r1, v1, tab1, i1, p1) = res
+    from oracle import walrus_oracle as wo
+
+    rpt = np.random.default_rng(5).integers(0, 3, (7, 5)).astype(np.int32)
+    wantp = [wo.loop_hafnian(A[:5, :5], np.diag(A)[:5].copy(), [int(x) for x in r]) for r in rpt]
+    assert p0 == p1 and np.allclose(np.array(p0), np.array(wantp), rtol=1e-13, atol=0)
     assert v0 == v1, "ranks must agree bit-for-bit"
     assert tab0 == tab1 and len(tab0) == world
     assert abs(v0 - want) / abs(want) < 1e-12

@@ -302,3 +302,110 @@ def test_device_peak_probe():
     t = ctypes.c_double(0)
     assert lib.wb200_fp64_peak(0, 1, ctypes.byref(t)) == 0
     assert 10 < t.value < 60
+
+
+# ------------------------------------------------------------------------------ batched front ends (a8, a9)
+def test_loop_hafnian_batch_vs_reference_outputs(golden):
+    for c in golden["batch"]:
+        got = wb.loop_hafnian_batch(dec(c["A"]), dec(c["D"]), c["fixed"], c["cutoff"], glynn=c["glynn"])
+        want = dec(c["value"])
+        assert got.shape == want.shape and got.dtype == np.complex128
+        scale = max(np.max(np.abs(want)), 1e-300)
+        assert np.max(np.abs(got - want)) / scale < TOL, (c["fixed"], c["cutoff"], c["glynn"])
+
+
+def test_loop_hafnian_batch_identity_and_oracle():
+    """batch[k] == loop_hafnian(A, D, reps = fixed + [k]) (the pin for the unpinned boundary)."""
+    rng = np.random.default_rng(11)
+    for trial in range(10):
+        n = int(rng.integers(2, 7))
+        A = random_symmetric(rng, n) / np.sqrt(n)
+        D = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        fixed = [int(r) for r in rng.integers(0, 4, n - 1)]
+        cutoff = int(rng.integers(1, 9))
+        for glynn in (True, False):
+            got = wb.loop_hafnian_batch(A, D, fixed, cutoff, glynn=glynn)
+            want = np.array([wo.loop_hafnian(A, D, fixed + [k], glynn) for k in range(cutoff + 1)])
+            assert np.max(np.abs(got - want)) / max(np.max(np.abs(want)), 1e-300) < TOL, (fixed, cutoff, glynn)
+            orc = wo.loop_hafnian_batch(A, D, fixed, cutoff, glynn)
+            assert np.max(np.abs(got - orc)) / max(np.max(np.abs(orc)), 1e-300) < TOL
+
+
+def test_lhaf_patterns_vs_oracle_all_branches():
+    from thewalrus_b200 import quantum as q
+
+    rng = np.random.default_rng(12)
+    nv = 8
+    A = random_symmetric(rng, nv) / np.sqrt(nv)
+    g = rng.standard_normal(nv) + 1j * rng.standard_normal(nv)
+    rpt = rng.integers(0, 4, (200, nv)).astype(np.int32)
+    rpt[0] = 0                       # N = 0 -> 1
+    rpt[1] = 0; rpt[1, 3] = 1        # N = 1 -> gamma[3]
+    rpt[2] = 0; rpt[2, 5] = 7        # one vertex, self-paired + odd leftover
+    rpt[3] = 0; rpt[3, 2] = 6        # one vertex, self-paired
+    got = q.lhaf_patterns(A, g, rpt)
+    for b in range(len(rpt)):
+        want = wo.loop_hafnian(A, g, [int(r) for r in rpt[b]])
+        assert abs(got[b] - want) <= TOL * max(abs(want), 1e-12), (b, rpt[b])
+    got0 = q.lhaf_patterns(A, None, rpt)      # no loops: odd totals vanish
+    for b in range(len(rpt)):
+        want = wo.haf(A, [int(r) for r in rpt[b]])
+        assert abs(got0[b] - want) <= TOL * max(abs(want), 1e-12), (b, rpt[b])
+    got_ie = q.lhaf_patterns(A, g, rpt[:40], glynn=False)
+    for b in range(40):
+        want = wo.loop_hafnian(A, g, [int(r) for r in rpt[b]], False)
+        assert abs(got_ie[b] - want) <= TOL * max(abs(want), 1e-12), (b, rpt[b])
+    assert q.lhaf_patterns(A, g, np.zeros((0, nv), dtype=np.int32)).shape == (0,)
+
+
+def test_gbs_probabilities_vs_reference_outputs(golden):
+    d = golden["dme"]
+    mu, cov, pats = np.array(d["mu"]), np.array(d["cov"]), np.array(d["patterns"])
+    p = wb.probabilities_batch(mu, cov, pats)
+    assert np.max(np.abs(p - np.array(d["displaced"])) / np.maximum(np.array(d["displaced"]), 1e-30)) < 1e-9
+    p0 = wb.probabilities_batch(0 * mu, cov, pats)
+    want0 = np.array(d["zero_mean"])
+    assert np.max(np.abs(p0 - want0)) < 1e-12 + 1e-9 * np.max(want0)
+    one = wb.density_matrix_element(mu, cov, list(pats[3]), list(pats[3]))
+    assert rel(one.real, d["displaced"][3]) < 1e-9
+
+
+def test_gbs_probabilities_16_modes_sample_and_normalisation():
+    """BASELINE config 3 state (16 modes, eta = 0.8, displaced): a pattern sample against the general kernel and
+    the NumPy oracle, and sum_n p(n) -> 1 over a 2-mode marginal-free small state."""
+    from thewalrus_b200 import quantum as q
+
+    sys_path_bench = __import__("bench")
+    mu, cov, pats = sys_path_bench.make_gbs_state(16, 2000, seed=3016)
+    A, gamma = q._state(mu, cov, 2, 1e-10)
+    rpt = np.concatenate([pats, pats], axis=1)
+    got = q.lhaf_patterns(A, gamma, rpt)
+    idx = np.argsort(pats.sum(axis=1))[[0, 10, 500, 1000, 1500, 1990, 1999]]
+    for b in idx:
+        r = [int(x) for x in rpt[b]]
+        want = wb.hafnian_repeated(A, r, mu=gamma, loop=True)
+        assert abs(got[b] - want) <= 1e-9 * max(abs(want), 1e-300), (b, pats[b])
+        if sum(r) <= 8:
+            assert abs(got[b] - wo.loop_hafnian(A, gamma, r)) <= 1e-9 * max(abs(want), 1e-300)
+    # normalisation on a small lossy displaced state: probabilities over a generous cutoff sum to ~1
+    mu2, cov2, _ = sys_path_bench.make_gbs_state(2, 1, seed=7, r=0.4)
+    P = wb.probabilities(mu2, cov2, 14)
+    assert abs(P.sum() - 1.0) < 1e-6 and P.min() >= 0.0
+
+
+def test_gbs_probabilities_config3_state_vs_reference_outputs(golden):
+    """16-mode BASELINE config 3 state: the reference's own density_matrix_element on a pattern sample
+    (0..10 photons), regenerated inputs checked against the stored ones."""
+    import bench
+
+    d = golden["dme16"]
+    mu, cov, pats = bench.make_gbs_state(16, d["B"], seed=d["seed"])
+    assert np.allclose(mu, np.array(d["mu"])) and np.allclose(cov, np.array(d["cov"]))
+    sel = pats[d["index"]]
+    assert sel.tolist() == d["patterns"]
+    p = wb.probabilities_batch(mu, cov, pats)[d["index"]]
+    want = np.array(d["displaced"])
+    assert np.max(np.abs(p - want) / want) < 1e-9
+    p0 = wb.probabilities_batch(0 * mu, cov, sel)
+    want0 = np.array(d["zero_mean"])
+    assert np.max(np.abs(p0 - want0)) < 1e-9 * np.max(want0) + 1e-18

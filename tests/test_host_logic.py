@@ -163,3 +163,51 @@ def test_no_cpu_fallback_without_gpu():
         wb.perm(np.ones((5, 5)))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         wb.tor(np.eye(4) * 0.1)
+
+
+def test_batch_edge_bookkeeping_matches_oracle():
+    from thewalrus_b200.loop_hafnian_batch import add_batch_edges_even, add_batch_edges_odd
+
+    assert add_batch_edges_even(np.array([], dtype=int)).tolist() == [0, 0]
+    assert add_batch_edges_odd(np.array([], dtype=int), 0).tolist() == [1, 0, 1, 1]
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        ne = 2 * int(rng.integers(1, 5))
+        fe = rng.permutation(ne + 2)[:ne]
+        assert add_batch_edges_even(fe).tolist() == wo._batch_edges_even(fe).tolist()
+        odd = int(rng.integers(0, ne + 3))
+        assert add_batch_edges_odd(fe, odd).tolist() == wo._batch_edges_odd(fe, odd).tolist()
+
+
+def test_loop_hafnian_batch_assertions():
+    A = np.ones((3, 3), dtype=complex)
+    with pytest.raises(AssertionError):
+        wb.loop_hafnian_batch(A, np.ones(2, dtype=complex), [1, 1], 2)
+    with pytest.raises(AssertionError):
+        wb.loop_hafnian_batch(A, np.ones(3, dtype=complex), [1], 2)
+
+
+def test_gaussian_state_preparation_matches_reference(golden):
+    """Qmat / Amat / displacement vector / prefactor against the reference's own outputs
+    (thewalrus/quantum/conversions.py:70-169, fock_tensors.py:566-581)."""
+    from conftest import dec
+    from thewalrus_b200 import quantum as q
+
+    d, c = golden["dme"], golden["conv"]
+    mu, cov = np.array(d["mu"]), np.array(d["cov"])
+    assert np.allclose(q.Qmat(cov), dec(c["Q"]), rtol=1e-13, atol=1e-14)
+    assert np.allclose(q.Amat(cov), dec(c["A"]), rtol=1e-12, atol=1e-14)
+    assert np.allclose(q.complex_to_real_displacements(mu), dec(c["beta"]), rtol=1e-14)
+    assert np.isclose(q._prefactor(mu, cov), dec(c["prefactor"]), rtol=1e-12)
+    with pytest.raises(ValueError, match="shape"):
+        q.probabilities_batch(mu, cov, np.zeros((3, 5), dtype=int))
+
+
+def test_gbs_state_generator_is_a_valid_covariance():
+    import bench
+
+    mu, cov, pats = bench.make_gbs_state(16, 500, seed=3016)
+    assert cov.shape == (32, 32) and np.allclose(cov, cov.T)
+    Om = np.block([[np.zeros((16, 16)), np.identity(16)], [-np.identity(16), np.zeros((16, 16))]])
+    assert np.min(np.linalg.eigvalsh(cov + 1j * Om)) > -1e-12          # uncertainty relation (hbar = 2)
+    assert pats.shape == (500, 16) and pats.sum(axis=1).max() <= 10 and pats.min() >= 0

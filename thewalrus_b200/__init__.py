@@ -14,7 +14,10 @@ from ._hafnian import (  # noqa: F401
     matched_reps,
     reduction,
 )
+from .loop_hafnian_batch import loop_hafnian_batch  # noqa: F401
 from ._permanent import perm, perm_bbfg, perm_ryser  # noqa: F401
 from ._torontonian import tor, tor_input_checks  # noqa: F401
+from . import quantum  # noqa: F401
+from .quantum import density_matrix_element, probabilities, probabilities_batch  # noqa: F401
 
 __version__ = "0.1.0"

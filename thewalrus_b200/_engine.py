@@ -207,3 +207,67 @@ def tor_num_prefixes(n_modes):
     c = ctypes.c_uint64(0)
     _lib.check(lib.wb200_tor_num_prefixes(n_modes, ctypes.byref(c)), "wb200_tor_num_prefixes")
     return int(c.value)
+
+
+def lhaf_batch_range(Ax, Dx, edge_reps, odd_variant, cutoff_extra, glynn, j0, j1, length, device=None):
+    """Partial loop_hafnian_batch sweep over subset indices [j0, j1) -> 4 * length doubles (no final scale)."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    Ax, pA = _lib.as_c128(Ax)
+    Dx, pD = _lib.as_c128(Dx)
+    er = np.ascontiguousarray(edge_reps, dtype=np.int32)
+    out = np.zeros(4 * length)
+    rc = lib.wb200_lhaf_batch_host(idx, pA, pD, Ax.shape[0], er.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                   int(odd_variant), int(cutoff_extra), 1 if glynn else 0, j0, j1, _lib.dptr(out),
+                                   int(length), None)
+    _lib.check(rc, "wb200_lhaf_batch_host")
+    return out
+
+
+def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False):
+    """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    A, pA = _lib.as_c128(A)
+    pG = None
+    if gamma is not None:
+        gamma, pG = _lib.as_c128(gamma)
+    rpt = np.ascontiguousarray(rpt, dtype=np.int32)
+    B, nv = rpt.shape
+    out = np.zeros(B, dtype=np.complex128)
+    ms = ctypes.c_double(0.0)
+    rc = lib.wb200_lhaf_patterns_host(idx, pA, pG, nv, rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B,
+                                      1 if glynn else 0, _lib.dptr(out.view(np.float64)), ctypes.byref(ms))
+    _lib.check(rc, "wb200_lhaf_patterns_host")
+    return (out, ms.value) if want_ms else out
+
+
+def run_sharded_patterns(A, gamma, rpt, glynn, group, device, local=None):
+    """Shard the PATTERNS in contiguous blocks over the ranks of ``group`` and all-gather the results
+    (the batched front end shards the batch, not the subset index).  ``local`` overrides the
+    per-rank evaluator (tests use the oracle there)."""
+    local = local or (lambda r: lhaf_patterns_local(A, gamma, r, glynn, device))
+    rank, world = _rank_world(group, None)
+    B = rpt.shape[0]
+    if world == 1:
+        return local(rpt)
+    torch = _torch()
+    import torch.distributed as dist
+
+    lo, hi = shard_range(B, rank, world)
+    mine = local(rpt[lo:hi]) if hi > lo else np.zeros(0, dtype=np.complex128)
+    g = None if group is True else group
+    backend = dist.get_backend(g)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    # equal-sized slots so a single all_gather works for ragged shards
+    slot = (B + world - 1) // world
+    buf = torch.zeros(2 * slot, dtype=torch.float64, device=dev)
+    buf[: 2 * (hi - lo)] = torch.from_numpy(np.ascontiguousarray(mine).view(np.float64)).to(dev)
+    gathered = torch.empty(world * 2 * slot, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(gathered, buf, group=g)
+    table = gathered.cpu().numpy().reshape(world, 2 * slot)
+    out = np.empty(B, dtype=np.complex128)
+    for r in range(world):
+        a, b = shard_range(B, r, world)
+        out[a:b] = table[r, : 2 * (b - a)].view(np.complex128)
+    return out

@@ -1,0 +1,726 @@
+// Batched loop-hafnian front ends (one warp per subset, repeated edges, Glynn or inclusion/exclusion):
+//
+//  * lhaf_patterns: (A, gamma, rpt[B][nv]) -> loop hafnian of every repetition pattern.  Replaces the
+//    Python loop of probabilities() over density_matrix_element (thewalrus/quantum/fock_tensors.py:191-232,
+//    412-421), i.e. per pattern matched_reps (thewalrus/_hafnian.py:80-159) + _calc_loop_hafnian (:512-577).
+//    (pattern, subset) pairs are flattened into one index space: a prep kernel pairs the vertices of every
+//    pattern and counts its subsets, a scan turns the per-pattern chunk counts into offsets, persistent
+//    warps pull fixed-size chunks from an atomic counter and write one compensated partial per chunk, and a
+//    final kernel adds each pattern's chunks in index order (deterministic: no floating-point atomics).
+//  * lhaf_batch: _calc_loop_hafnian_batch_even / _odd (thewalrus/loop_hafnian_batch.py:51-208): one sweep
+//    over the subsets of (batch edge + fixed edges); every subset contributes to all photon numbers
+//    N_det >= 2 kept_0 of the batch mode.
+//
+// Per subset (all in the warp's slice of shared memory): reduced matrix M = AX_S (get_submatrices,
+// _hafnian.py:315-356), power traces by a product chain with the pairing
+// tr(M^(a+b)) = sum_rc (M^a)[r,c] (M^b)[c,r] — continued past the matrix size, where the reference switches
+// to La Budde + Newton (thewalrus/charpoly.py:319-326; same numbers) — loop terms XD M^(t-1) D and
+// oddVX M^(t-1) D from one mat-vec chain, and the series c_t = (1/t) sum_i i a_i c_(t-i) of f_loop /
+// f_loop_odd (_hafnian.py:212-285).
+#include "common.cuh"
+
+namespace wb {
+
+constexpr int BW_EMAX = 32;      // max edges per problem
+constexpr int BW_NVMAX = 64;     // max vertices of the big matrix
+constexpr int BW_WARPS = 8;      // warps per CTA
+constexpr int BW_CHUNK = 16;     // subsets per work item (patterns kernel)
+constexpr int BW_MAX_ORDER = 200;
+
+__device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
+    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);
+    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);
+}
+__device__ __forceinline__ double2 warp_sum2(double2 v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { v.x += shfl_xor_d(v.x, off); v.y += shfl_xor_d(v.y, off); }
+    return v;
+}
+__device__ __forceinline__ double binom_d(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    if (k > n - k) k = n - k;
+    double b = 1.0;
+    for (int q = 0; q < k; ++q) b = b * (double)(n - q) / (double)(q + 1);
+    return rint(b);
+}
+
+// per-warp shared-memory workspace
+struct WarpWs {
+    double2 *M, *P, *Pn;              // smax * smax each
+    double2 *vXD, *vD, *vD2, *vOV, *vOV0;  // smax each
+    double2 *ptr, *lv, *ov, *ov0;     // T + 2 each
+    double2 *fac, *cs0, *cs1, *cs2;   // O + 2 each
+    int* rows;                        // 2 * BW_EMAX
+    double* delta;                    // 2 * BW_EMAX
+    int* kept;                        // BW_EMAX
+    unsigned char* eu; unsigned char* ev; unsigned short* er;  // edge lists (BW_EMAX each)
+};
+__host__ __device__ inline size_t warp_ws_bytes(int smax, int T, int O) {
+    size_t b = sizeof(double2) * ((size_t)3 * smax * smax + 5 * (size_t)smax + 4 * (size_t)(T + 2) + 4 * (size_t)(O + 2));
+    b += sizeof(int) * 2 * BW_EMAX + sizeof(double) * 2 * BW_EMAX + sizeof(int) * BW_EMAX + 2 * BW_EMAX + 2 * BW_EMAX;
+    return (b + 15) & ~(size_t)15;
+}
+__device__ inline WarpWs carve(unsigned char* base, int smax, int T, int O) {
+    WarpWs w;
+    double2* p = reinterpret_cast<double2*>(base);
+    w.M = p; p += smax * smax; w.P = p; p += smax * smax; w.Pn = p; p += smax * smax;
+    w.vXD = p; p += smax; w.vD = p; p += smax; w.vD2 = p; p += smax; w.vOV = p; p += smax; w.vOV0 = p; p += smax;
+    w.ptr = p; p += T + 2; w.lv = p; p += T + 2; w.ov = p; p += T + 2; w.ov0 = p; p += T + 2;
+    w.fac = p; p += O + 2; w.cs0 = p; p += O + 2; w.cs1 = p; p += O + 2; w.cs2 = p; p += O + 2;
+    double* d = reinterpret_cast<double*>(p);
+    w.delta = d; d += 2 * BW_EMAX;
+    int* ip = reinterpret_cast<int*>(d);
+    w.rows = ip; ip += 2 * BW_EMAX; w.kept = ip; ip += BW_EMAX;
+    unsigned short* sp = reinterpret_cast<unsigned short*>(ip);
+    w.er = sp; sp += BW_EMAX;
+    unsigned char* cp = reinterpret_cast<unsigned char*>(sp);
+    w.eu = cp; cp += BW_EMAX; w.ev = cp;
+    return w;
+}
+
+// Decode subset j (mixed radix, most significant digit first: find_kept_edges, _hafnian.py:162-180), build the
+// list of kept rows.  Returns k (edges with delta != 0); *esum = sum kept, *weight = prod_{i >= wstart} C(r_i, kept_i),
+// *d0zero = (delta_0 == 0).  Executed by lane 0; results broadcast by the caller through shared memory.
+__device__ inline int decode_subset(const WarpWs& w, int E, int glynn, unsigned long long j, int wstart, int* esum,
+                                    double* weight, int* d0zero) {
+    unsigned long long num = j;
+    for (int i = E - 1; i >= 0; --i) {
+        const unsigned long long base = (unsigned long long)w.er[i] + 1ull;
+        w.kept[i] = (int)(num % base);
+        num /= base;
+    }
+    int k = 0, es = 0;
+    double wt = 1.0;
+    *d0zero = 0;
+    for (int i = 0; i < E; ++i) {
+        const int r = w.er[i], kp = w.kept[i];
+        es += kp;
+        if (i >= wstart) wt *= binom_d(r, kp);
+        const int d = glynn ? 2 * kp - r : kp;
+        if (i == 0) *d0zero = (d == 0);
+        if (d != 0) { w.rows[k] = i; w.delta[k] = (double)d; ++k; }
+    }
+    for (int a = 0; a < k; ++a) {
+        const int e = w.rows[a];
+        w.rows[a] = w.eu[e];
+        w.rows[k + a] = w.ev[e];
+        w.delta[k + a] = w.delta[a];
+    }
+    *esum = es; *weight = wt;
+    return k;
+}
+
+// Reduced matrix, vectors, power traces ptr[1..T], loop terms lv[t] = XD M^(t-1) D, ov[t] = oddVX M^(t-1) D,
+// ov0[t] likewise for a second odd row (t = 1..T).  A: nv x nv (row stride lda); D: nv or null; odd rows are
+// rows of A (index or -1).
+__device__ inline void subset_traces(const WarpWs& w, const double2* __restrict__ A, int lda, const double2* __restrict__ D,
+                                     int odd_row, int odd0_row, int k, int T, int lane) {
+    const int s = 2 * k;
+    const bool loops = D != nullptr;
+    for (int idx = lane; idx < s * s; idx += 32) {
+        const int r = idx / s, c = idx - r * s;
+        const int sc = c < k ? c + k : c - k;
+        const double2 a = __ldg(A + (size_t)w.rows[r] * lda + w.rows[sc]);
+        const double d = w.delta[c];
+        const double2 v = make_double2(a.x * d, a.y * d);
+        w.M[idx] = v;
+        w.P[idx] = v;
+    }
+    for (int c = lane; c < s; c += 32) {
+        const int sc = c < k ? c + k : c - k;
+        const double d = w.delta[c];
+        if (loops) {
+            const double2 dv = __ldg(D + w.rows[sc]);
+            w.vXD[c] = make_double2(dv.x * d, dv.y * d);
+            w.vD[c] = __ldg(D + w.rows[c]);
+        }
+        if (odd_row >= 0) {
+            const double2 ov = __ldg(A + (size_t)odd_row * lda + w.rows[sc]);
+            w.vOV[c] = make_double2(ov.x * d, ov.y * d);
+        }
+        if (odd0_row >= 0) {
+            const double2 ov = __ldg(A + (size_t)odd0_row * lda + w.rows[sc]);
+            w.vOV0[c] = make_double2(ov.x * d, ov.y * d);
+        }
+    }
+    __syncwarp();
+    // ---- power traces
+    {
+        double2 t1 = make_double2(0.0, 0.0);
+        for (int r = lane; r < s; r += 32) { t1.x += w.M[r * s + r].x; t1.y += w.M[r * s + r].y; }
+        t1 = warp_sum2(t1);
+        if (lane == 0) { w.ptr[0] = make_double2((double)s, 0.0); if (T >= 1) w.ptr[1] = t1; }
+        double2* Pc = w.P;
+        double2* Pnx = w.Pn;
+        for (int t = 1; 2 * t <= T; ++t) {
+            double2 e = make_double2(0.0, 0.0);
+            for (int idx = lane; idx < s * s; idx += 32) {
+                const int r = idx / s, c = idx - r * s;
+                cfma(e, Pc[idx], Pc[c * s + r]);
+            }
+            e = warp_sum2(e);
+            if (lane == 0) w.ptr[2 * t] = e;
+            if (2 * t + 1 > T) break;
+            for (int idx = lane; idx < s * s; idx += 32) {
+                const int r = idx / s, c = idx - r * s;
+                double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+                int q = 0;
+                for (; q + 1 < s; q += 2) {
+                    cfma(a0, Pc[r * s + q], w.M[q * s + c]);
+                    cfma(a1, Pc[r * s + q + 1], w.M[(q + 1) * s + c]);
+                }
+                if (q < s) cfma(a0, Pc[r * s + q], w.M[q * s + c]);
+                Pnx[idx] = make_double2(a0.x + a1.x, a0.y + a1.y);
+            }
+            __syncwarp();
+            double2 o = make_double2(0.0, 0.0);
+            for (int idx = lane; idx < s * s; idx += 32) {
+                const int r = idx / s, c = idx - r * s;
+                cfma(o, Pnx[idx], Pc[c * s + r]);
+            }
+            o = warp_sum2(o);
+            if (lane == 0) w.ptr[2 * t + 1] = o;
+            double2* tmp = Pc; Pc = Pnx; Pnx = tmp;
+            __syncwarp();
+        }
+    }
+    // ---- loop terms
+    if (loops) {
+        double2* v = w.vD;
+        double2* v2 = w.vD2;
+        for (int t = 1; t <= T; ++t) {
+            double2 l = make_double2(0.0, 0.0), o = make_double2(0.0, 0.0), o0 = make_double2(0.0, 0.0);
+            for (int c = lane; c < s; c += 32) {
+                const double2 dv = v[c];
+                cfma(l, w.vXD[c], dv);
+                if (odd_row >= 0) cfma(o, w.vOV[c], dv);
+                if (odd0_row >= 0) cfma(o0, w.vOV0[c], dv);
+            }
+            l = warp_sum2(l);
+            if (odd_row >= 0) o = warp_sum2(o);
+            if (odd0_row >= 0) o0 = warp_sum2(o0);
+            if (lane == 0) { w.lv[t] = l; w.ov[t] = o; w.ov0[t] = o0; }
+            if (t < T) {
+                for (int r = lane; r < s; r += 32) {
+                    double2 a = make_double2(0.0, 0.0);
+                    for (int q = 0; q < s; ++q) cfma(a, w.M[r * s + q], v[q]);
+                    v2[r] = a;
+                }
+                __syncwarp();
+                double2* tmp = v; v = v2; v2 = tmp;
+            }
+        }
+    } else {
+        for (int t = lane + 1; t <= T; t += 32) { w.lv[t] = make_double2(0.0, 0.0); w.ov[t] = w.lv[t]; w.ov0[t] = w.lv[t]; }
+    }
+    __syncwarp();
+}
+
+// fac[i] = i * a_i for the even series (f / f_loop): a_i = p_i/(2i) + l_i/2, i = 1..order
+__device__ inline void fac_even(const WarpWs& w, int order, int lane) {
+    for (int i = lane + 1; i <= order; i += 32)
+        w.fac[i] = make_double2(0.5 * w.ptr[i].x + 0.5 * i * w.lv[i].x, 0.5 * w.ptr[i].y + 0.5 * i * w.lv[i].y);
+    __syncwarp();
+}
+// odd series (f_loop_odd): a_1 = oddloop, a_2t = p_t/(2t) + l_t/2, a_(2t+1) = o_t
+__device__ inline void fac_odd(const WarpWs& w, int order, double2 oddloop, const double2* ov, int lane) {
+    for (int i = lane + 1; i <= order; i += 32) {
+        double2 f;
+        if (i == 1) f = oddloop;
+        else if ((i & 1) == 0) { const int t = i >> 1; f = make_double2(w.ptr[t].x + 0.5 * i * w.lv[t].x, w.ptr[t].y + 0.5 * i * w.lv[t].y); }
+        else { const int t = i >> 1; f = make_double2(i * ov[t].x, i * ov[t].y); }
+        w.fac[i] = f;
+    }
+    __syncwarp();
+}
+// cs[t] = (1/t) sum_{i=1..t} fac[i] cs[t-i]
+__device__ inline void exp_series(const WarpWs& w, double2* cs, int order, int lane) {
+    if (lane == 0) cs[0] = make_double2(1.0, 0.0);
+    __syncwarp();
+    for (int t = 1; t <= order; ++t) {
+        double2 a = make_double2(0.0, 0.0);
+        for (int i = 1 + lane; i <= t; i += 32) cfma(a, w.fac[i], cs[t - i]);
+        a = warp_sum2(a);
+        if (lane == 0) cs[t] = make_double2(a.x / t, a.y / t);
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// patterns
+// =================================================================================================
+struct __align__(16) PatDesc {
+    unsigned long long steps;
+    unsigned int nchunks;
+    short E, N, odd, kind;  // kind: 0 subset sum, 1 -> 1.0, 2 -> 0.0, 3 -> D[odd]
+    unsigned short r[BW_EMAX];
+    unsigned char u[BW_EMAX], v[BW_EMAX];
+};
+
+struct PatMeta {  // maxima over the batch + error flag, filled by the prep kernel
+    int maxE, maxN, anyOdd, err;
+};
+
+__global__ void pat_prep_kernel(const int32_t* __restrict__ rpt, long long B, int nv, int loops, int glynn,
+                                PatDesc* __restrict__ desc, unsigned int* __restrict__ nchunks, PatMeta* meta) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    int cnt[BW_NVMAX];
+    int N = 0, npool = 0;
+    bool bad = false;
+    for (int i = 0; i < nv; ++i) {
+        const int r = rpt[p * nv + i];
+        if (r < 0 || r > 65535) bad = true;
+        cnt[i] = r < 0 ? 0 : r;
+        N += cnt[i];
+        npool += cnt[i] > 0;
+    }
+    PatDesc d;
+    d.steps = 0; d.nchunks = 0; d.E = 0; d.N = (short)N; d.odd = -1; d.kind = 0;
+    if (bad || N > 32000) { atomicExch(&meta->err, 1); d.kind = 2; desc[p] = d; nchunks[p] = 0; return; }
+    if (N == 0) d.kind = 1;
+    else if (!loops && (N & 1)) d.kind = 2;
+    else if (loops && N == 1) {
+        d.kind = 3;
+        for (int i = 0; i < nv; ++i) if (cnt[i] == 1) d.odd = (short)i;
+    }
+    if (d.kind != 0) { desc[p] = d; nchunks[p] = 0; return; }
+    // greedy pairing (matched_reps, _hafnian.py:97-159): largest (count, index) first
+    int E = 0;
+    while (npool >= 1) {
+        int i0 = -1, i1 = -1;
+        for (int i = nv - 1; i >= 0; --i) {  // descending index so ties pick the larger index first
+            if (cnt[i] <= 0) continue;
+            if (i0 < 0 || cnt[i] > cnt[i0]) { i1 = i0; i0 = i; }
+            else if (i1 < 0 || cnt[i] > cnt[i1]) i1 = i;
+        }
+        const int r0 = cnt[i0];
+        if (npool == 1 && r0 <= 1) break;
+        if (E >= BW_EMAX) { bad = true; break; }
+        if (npool == 1 || r0 > 2 * cnt[i1]) {
+            d.u[E] = (unsigned char)i0; d.v[E] = (unsigned char)i0; d.r[E] = (unsigned short)(r0 / 2);
+            if (r0 & 1) cnt[i0] = 1; else { cnt[i0] = 0; --npool; }
+        } else {
+            const int r1 = cnt[i1];
+            d.u[E] = (unsigned char)i0; d.v[E] = (unsigned char)i1; d.r[E] = (unsigned short)r1;
+            cnt[i1] = 0; --npool;
+            if (r0 > r1) cnt[i0] = r0 - r1; else { cnt[i0] = 0; --npool; }
+        }
+        ++E;
+    }
+    if (npool > 1) bad = true;
+    if (npool == 1) for (int i = 0; i < nv; ++i) if (cnt[i] > 0) d.odd = (short)i;
+    for (int e = E; e < BW_EMAX; ++e) { d.u[e] = 0; d.v[e] = 0; d.r[e] = 0; }
+    // steps (_hafnian.py:432-435, 535-538)
+    double stepsd = 1.0;
+    unsigned long long steps = 1;
+    for (int e = 0; e < E; ++e) {
+        unsigned long long f = (unsigned long long)d.r[e] + 1ull;
+        if (e == 0 && glynn && d.odd < 0) f = ((unsigned long long)d.r[0] + 2ull) / 2ull;
+        steps *= f; stepsd *= (double)f;
+    }
+    const int order = d.odd >= 0 ? N : N / 2;
+    if (bad || stepsd > 1e12 || order > BW_MAX_ORDER || (d.odd >= 0 && !loops)) {
+        atomicExch(&meta->err, 2); d.kind = 2; desc[p] = d; nchunks[p] = 0; return;
+    }
+    d.E = (short)E; d.steps = steps;
+    d.nchunks = (unsigned int)((steps + BW_CHUNK - 1) / BW_CHUNK);
+    desc[p] = d;
+    nchunks[p] = d.nchunks;
+    atomicMax(&meta->maxE, E);
+    atomicMax(&meta->maxN, N);
+    if (d.odd >= 0) atomicMax(&meta->anyOdd, 1);
+}
+
+// exclusive scan of n unsigned ints into 64-bit offsets (off[n] = total); one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restrict__ in, long long n,
+                                                    unsigned long long* __restrict__ off) {
+    __shared__ unsigned long long part[1024];
+    const int tid = threadIdx.x;
+    const long long per = (n + 1023) / 1024;
+    const long long lo = tid * per, hi = lo + per < n ? lo + per : n;
+    unsigned long long s = 0;
+    for (long long i = lo; i < hi; ++i) s += in[i];
+    part[tid] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        unsigned long long v = tid >= d ? part[tid - d] : 0ull;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    unsigned long long run = tid ? part[tid - 1] : 0ull;
+    for (long long i = lo; i < hi; ++i) { off[i] = run; run += in[i]; }
+    if (tid == 1023) off[n] = part[1023];
+}
+
+struct PatParams {
+    const double2* A;
+    const double2* D;  // gamma or null
+    int nv, glynn, smax, T, O;
+    long long B;
+    const PatDesc* desc;
+    const unsigned long long* coff;  // B + 1 chunk offsets
+    unsigned long long nchunks;
+    unsigned long long* counter;
+    double* partial;  // nchunks * 4
+};
+
+__global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
+    extern __shared__ __align__(16) unsigned char smem_bw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t wsb = warp_ws_bytes(p.smax, p.T, p.O);
+    WarpWs w = carve(smem_bw + warp * wsb, p.smax, p.T, p.O);
+    __shared__ int s_k[BW_WARPS], s_esum[BW_WARPS], s_d0[BW_WARPS];
+    __shared__ double s_wt[BW_WARPS];
+    const bool loops = p.D != nullptr;
+
+    for (;;) {
+        unsigned long long chunk = 0;
+        if (lane == 0) chunk = atomicAdd(p.counter, 1ull);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= p.nchunks) break;
+        // pattern owning this chunk: largest pat with coff[pat] <= chunk
+        long long lo = 0, hi = p.B;
+        while (hi - lo > 1) {
+            const long long mid = (lo + hi) >> 1;
+            if (__ldg(p.coff + mid) <= chunk) lo = mid; else hi = mid;
+        }
+        const long long pat = lo;
+        const PatDesc* d = p.desc + pat;
+        const int E = d->E, N = d->N, odd = d->odd;
+        const unsigned long long steps = d->steps;
+        __syncwarp();
+        if (lane < BW_EMAX) { w.eu[lane] = d->u[lane]; w.ev[lane] = d->v[lane]; w.er[lane] = d->r[lane]; }
+        __syncwarp();
+        const unsigned long long jb = (chunk - __ldg(p.coff + pat)) * BW_CHUNK;
+        const unsigned long long je = jb + BW_CHUNK < steps ? jb + BW_CHUNK : steps;
+        const int T = N / 2, order = odd >= 0 ? N : N / 2;
+        cdd acc;
+        acc.re = {0.0, 0.0};
+        acc.im = {0.0, 0.0};
+        for (unsigned long long j = jb; j < je; ++j) {
+            if (lane == 0) {
+                int es, d0;
+                double wt;
+                s_k[warp] = decode_subset(w, E, p.glynn, j, 0, &es, &wt, &d0);
+                s_esum[warp] = es; s_wt[warp] = wt; s_d0[warp] = d0;
+            }
+            __syncwarp();
+            const int k = s_k[warp];
+            subset_traces(w, p.A, p.nv, p.D, odd, -1, k, T, lane);
+            if (odd >= 0) fac_odd(w, order, __ldg(p.D + odd), w.ov, lane);
+            else fac_even(w, order, lane);
+            exp_series(w, w.cs0, order, lane);
+            if (lane == 0) {
+                double pre = (((N / 2 - s_esum[warp]) & 1) ? -1.0 : 1.0) * s_wt[warp];
+                if (p.glynn && odd < 0 && s_d0[warp]) pre *= 0.5;
+                dd_add(acc.re, pre * w.cs0[order].x);
+                dd_add(acc.im, pre * w.cs0[order].y);
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            double* o = p.partial + chunk * 4;
+            o[0] = acc.re.hi; o[1] = acc.re.lo; o[2] = acc.im.hi; o[3] = acc.im.lo;
+        }
+        (void)loops;
+    }
+}
+
+__global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigned long long* __restrict__ coff,
+                                 const double* __restrict__ partial, const double2* __restrict__ D, int glynn,
+                                 long long B, double2* __restrict__ out) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    const PatDesc* d = desc + p;
+    if (d->kind == 1) { out[p] = make_double2(1.0, 0.0); return; }
+    if (d->kind == 2) { out[p] = make_double2(0.0, 0.0); return; }
+    if (d->kind == 3) { out[p] = D[d->odd]; return; }
+    dd re = {0.0, 0.0}, im = {0.0, 0.0};
+    for (unsigned long long c = coff[p]; c < coff[p + 1]; ++c) {
+        dd_add_dd(re, dd{partial[c * 4 + 0], partial[c * 4 + 1]});
+        dd_add_dd(im, dd{partial[c * 4 + 2], partial[c * 4 + 3]});
+    }
+    double scale = 1.0;
+    if (glynn) scale = ldexp(1.0, -(d->odd >= 0 ? d->N / 2 : d->N / 2 - 1));  // _hafnian.py:571-575
+    out[p] = make_double2((re.hi + re.lo) * scale, (im.hi + im.lo) * scale);
+}
+
+// =================================================================================================
+// loop_hafnian_batch sweep
+// =================================================================================================
+struct BatchParams {
+    const double2* A;   // n x n, edge ordered (vertex e paired with e + E)
+    const double2* D;   // n
+    int n, E, glynn, odd_variant, N_fixed, N_max, length, smax, T, O;
+    int reps[BW_EMAX];
+    unsigned long long j0, j1;
+    double* partials;   // (gridDim.x * BW_WARPS) * length * 4
+};
+
+__global__ void __launch_bounds__(32 * BW_WARPS) batch_kernel(BatchParams p) {
+    extern __shared__ __align__(16) unsigned char smem_bw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t wsb = warp_ws_bytes(p.smax, p.T, p.O) + sizeof(double) * 4 * (size_t)p.length;
+    unsigned char* base = smem_bw + warp * wsb;
+    WarpWs w = carve(base, p.smax, p.T, p.O);
+    double* acc = reinterpret_cast<double*>(base + warp_ws_bytes(p.smax, p.T, p.O));  // [length][4]
+    __shared__ int s_k[BW_WARPS], s_esum[BW_WARPS], s_d0[BW_WARPS];
+    __shared__ double s_wt[BW_WARPS];
+    const int E = p.E;
+    for (int i = lane; i < 4 * p.length; i += 32) acc[i] = 0.0;
+    if (lane < BW_EMAX) {
+        w.eu[lane] = (unsigned char)lane; w.ev[lane] = (unsigned char)(lane + E);
+        w.er[lane] = (unsigned short)(lane < E ? p.reps[lane] : 0);
+    }
+    __syncwarp();
+    const int T = p.N_max / 2;
+    const double2 oddloop = __ldg(p.D + 0), oddloop0 = p.odd_variant ? __ldg(p.D + 1) : make_double2(0.0, 0.0);
+    const int wpc = blockDim.x >> 5;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * wpc + warp, nw = (unsigned long long)gridDim.x * wpc;
+    for (unsigned long long j = p.j0 + gw; j < p.j1; j += nw) {
+        if (lane == 0) {
+            int es, d0;
+            double wt;
+            s_k[warp] = decode_subset(w, E, p.glynn, j, 1, &es, &wt, &d0);
+            s_esum[warp] = es; s_wt[warp] = wt; s_d0[warp] = d0;
+        }
+        __syncwarp();
+        const int k = s_k[warp], esum = s_esum[warp];
+        const double wt = s_wt[warp];
+        const int kept0 = w.kept[0];
+        const bool extra = p.odd_variant && kept0 == 0 && w.kept[1] == 0;
+        subset_traces(w, p.A, p.n, p.D, 0, extra ? 1 : -1, k, T, lane);
+        fac_even(w, p.N_max / 2, lane);
+        exp_series(w, w.cs0, p.N_max / 2, lane);           // f_loop
+        fac_odd(w, p.N_max, oddloop, w.ov, lane);
+        exp_series(w, w.cs1, p.N_max, lane);               // f_loop_odd
+        if (extra) {                                        // loop_hafnian_batch.py:181-185
+            fac_odd(w, p.N_fixed, oddloop0, w.ov0, lane);
+            exp_series(w, w.cs2, p.N_fixed, lane);
+            if (lane == 0) {
+                const double pm = ((p.N_fixed / 2 - esum) & 1) ? -1.0 : 1.0;
+                dd a = {acc[0], acc[1]}, b = {acc[2], acc[3]};
+                dd_add(a, wt * pm * w.cs2[p.N_fixed].x);
+                dd_add(b, wt * pm * w.cs2[p.N_fixed].y);
+                acc[0] = a.hi; acc[1] = a.lo; acc[2] = b.hi; acc[3] = b.lo;
+            }
+            __syncwarp();
+        }
+        const int first = 2 * kept0 + (p.odd_variant ? 1 : 0);
+        for (int nd = first + lane; nd < p.length; nd += 32) {   // loop_hafnian_batch.py:105-114, 188-200
+            const int N = p.N_fixed + nd;
+            const double pm = ((N / 2 - esum) & 1) ? -1.0 : 1.0;
+            const int half = p.odd_variant ? (nd - 1) / 2 : nd / 2;
+            const double wgt = binom_d(half, kept0) * wt * pm;
+            const double2 v = (N & 1) ? w.cs1[N] : w.cs0[N / 2];
+            dd a = {acc[nd * 4 + 0], acc[nd * 4 + 1]}, b = {acc[nd * 4 + 2], acc[nd * 4 + 3]};
+            dd_add(a, wgt * v.x);
+            dd_add(b, wgt * v.y);
+            acc[nd * 4 + 0] = a.hi; acc[nd * 4 + 1] = a.lo; acc[nd * 4 + 2] = b.hi; acc[nd * 4 + 3] = b.lo;
+        }
+        __syncwarp();
+    }
+    double* o = p.partials + gw * 4 * (size_t)p.length;
+    for (int i = lane; i < 4 * p.length; i += 32) o[i] = acc[i];
+}
+
+// out[nd][4] = fixed-order sum over warps
+__global__ void batch_final_kernel(const double* __restrict__ partials, int nwarps, int length, double* __restrict__ out) {
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= length) return;
+    dd re = {0.0, 0.0}, im = {0.0, 0.0};
+    for (int wv = 0; wv < nwarps; ++wv) {
+        const double* q = partials + ((size_t)wv * length + nd) * 4;
+        dd_add_dd(re, dd{q[0], q[1]});
+        dd_add_dd(im, dd{q[2], q[3]});
+    }
+    out[nd * 4 + 0] = re.hi; out[nd * 4 + 1] = re.lo; out[nd * 4 + 2] = im.hi; out[nd * 4 + 3] = im.lo;
+}
+
+struct DevBufB {
+    void* p = nullptr;
+    ~DevBufB() { if (p) cudaFree(p); }
+};
+struct EvPair {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~EvPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+
+// Warps per CTA (1..BW_WARPS) maximising resident warps per SM for a per-warp shared-memory footprint;
+// returns 0 if even one warp does not fit.  *ctas = CTAs per SM at that choice.
+static int bw_pick_warps(size_t per_warp, int* ctas) {
+    const size_t budget = 227 * 1024, per_cta_overhead = 1024 + 256;
+    int best_w = 0, best_total = 0, best_c = 0;
+    for (int wv = 1; wv <= BW_WARPS; ++wv) {
+        const size_t cta = per_warp * wv + per_cta_overhead;
+        if (cta > budget) break;
+        int c = (int)(budget / cta);
+        if (c > 32 / wv) c = 32 / wv;   // keep <= 32 warps per SM (register budget of these kernels)
+        if (c < 1) c = 1;
+        if (c * wv >= best_total) { best_total = c * wv; best_w = wv; best_c = c; }
+    }
+    *ctas = best_c;
+    return best_w;
+}
+
+}  // namespace wb
+
+using namespace wb;
+
+extern "C" int wb200_lhaf_patterns_host(int device, const double* A, const double* gamma, int nv, const int32_t* rpt,
+                                        int64_t B, int glynn, double* out, double* kernel_ms) {
+    if (!A || !rpt || !out) { set_error("lhaf_patterns: null pointer"); return WB200_EINVAL; }
+    if (nv < 1 || nv > BW_NVMAX) { set_error("lhaf_patterns: %d vertices outside [1, %d]", nv, BW_NVMAX); return nv > BW_NVMAX ? WB200_ENOSUP : WB200_EINVAL; }
+    if (B < 0) { set_error("lhaf_patterns: negative batch"); return WB200_EINVAL; }
+    if (B == 0) { if (kernel_ms) *kernel_ms = 0.0; return WB200_OK; }
+    WB_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    if (device_sm_count(device, &sms)) return WB200_ECUDA;
+    DevBufB dA, dD, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
+    WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * nv * nv));
+    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * nv * nv, cudaMemcpyHostToDevice));
+    if (gamma) {
+        WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * nv));
+        WB_CUDA(cudaMemcpy(dD.p, gamma, sizeof(double2) * nv, cudaMemcpyHostToDevice));
+    }
+    WB_CUDA(cudaMalloc(&drpt.p, sizeof(int32_t) * (size_t)B * nv));
+    WB_CUDA(cudaMemcpy(drpt.p, rpt, sizeof(int32_t) * (size_t)B * nv, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMalloc(&ddesc.p, sizeof(PatDesc) * (size_t)B));
+    WB_CUDA(cudaMalloc(&dnch.p, sizeof(unsigned int) * (size_t)B));
+    WB_CUDA(cudaMalloc(&dcoff.p, sizeof(unsigned long long) * ((size_t)B + 1)));
+    WB_CUDA(cudaMalloc(&dmeta.p, sizeof(PatMeta)));
+    WB_CUDA(cudaMalloc(&dcounter.p, sizeof(unsigned long long)));
+    WB_CUDA(cudaMalloc(&dout.p, sizeof(double2) * (size_t)B));
+    WB_CUDA(cudaMemset(dmeta.p, 0, sizeof(PatMeta)));
+    WB_CUDA(cudaMemset(dcounter.p, 0, sizeof(unsigned long long)));
+    EvPair ev;
+    WB_CUDA(cudaEventCreate(&ev.e0));
+    WB_CUDA(cudaEventCreate(&ev.e1));
+    WB_CUDA(cudaEventRecord(ev.e0, 0));
+    pat_prep_kernel<<<(unsigned)((B + 127) / 128), 128>>>((const int32_t*)drpt.p, B, nv, gamma != nullptr, glynn,
+                                                          (PatDesc*)ddesc.p, (unsigned int*)dnch.p, (PatMeta*)dmeta.p);
+    scan_kernel<<<1, 1024>>>((const unsigned int*)dnch.p, B, (unsigned long long*)dcoff.p);
+    WB_CUDA(cudaGetLastError());
+    PatMeta meta;
+    unsigned long long nchunks = 0;
+    WB_CUDA(cudaMemcpy(&meta, dmeta.p, sizeof(meta), cudaMemcpyDeviceToHost));
+    WB_CUDA(cudaMemcpy(&nchunks, (unsigned long long*)dcoff.p + B, sizeof(nchunks), cudaMemcpyDeviceToHost));
+    if (meta.err) {
+        set_error(meta.err == 1 ? "lhaf_patterns: repetition counts must be in [0, 65535] with total <= 32000"
+                                : "lhaf_patterns: a pattern exceeds the kernel limits (edges <= %d, series order <= %d, steps <= 1e12) or has an odd total without loops", BW_EMAX, BW_MAX_ORDER);
+        return meta.err == 1 ? WB200_EINVAL : WB200_ENOSUP;
+    }
+    if (nchunks > 0) {
+        PatParams p;
+        p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.nv = nv; p.glynn = glynn;
+        p.smax = 2 * meta.maxE; p.T = meta.maxN / 2; p.O = meta.anyOdd ? meta.maxN : meta.maxN / 2;
+        p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p;
+        p.nchunks = nchunks; p.counter = (unsigned long long*)dcounter.p;
+        WB_CUDA(cudaMalloc(&dpartial.p, sizeof(double) * 4 * (size_t)nchunks));
+        p.partial = (double*)dpartial.p;
+        const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
+        int ctas = 1;
+        const int wpc = bw_pick_warps(per_warp, &ctas);
+        if (wpc < 1) { set_error("lhaf_patterns: pattern too large for shared memory (%zu bytes per warp)", per_warp); return WB200_ENOSUP; }
+        const size_t shm = per_warp * wpc;
+        WB_CUDA(cudaFuncSetAttribute(pat_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        int grid = sms * ctas;
+        const unsigned long long want = (nchunks + wpc - 1) / wpc;
+        if ((unsigned long long)grid > want) grid = (int)want;
+        pat_main_kernel<<<grid, 32 * wpc, shm>>>(p);
+        WB_CUDA(cudaGetLastError());
+    }
+    pat_final_kernel<<<(unsigned)((B + 127) / 128), 128>>>((const PatDesc*)ddesc.p, (const unsigned long long*)dcoff.p,
+                                                           (const double*)dpartial.p, (const double2*)dD.p, glynn, B,
+                                                           (double2*)dout.p);
+    WB_CUDA(cudaEventRecord(ev.e1, 0));
+    WB_CUDA(cudaEventSynchronize(ev.e1));
+    WB_CUDA(cudaGetLastError());
+    float ms = 0;
+    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    if (kernel_ms) *kernel_ms = ms;
+    WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double2) * (size_t)B, cudaMemcpyDeviceToHost));
+    return WB200_OK;
+}
+
+extern "C" int wb200_lhaf_batch_steps(const int32_t* edge_reps, int n_edges, uint64_t* steps) {
+    if (!edge_reps || !steps || n_edges < 1) { set_error("lhaf_batch_steps: bad arguments"); return WB200_EINVAL; }
+    unsigned __int128 s = 1;
+    for (int i = 0; i < n_edges; ++i) {
+        if (edge_reps[i] < 0) { set_error("negative edge repetition"); return WB200_EINVAL; }
+        s *= (uint64_t)edge_reps[i] + 1;
+        if (s > (((unsigned __int128)1) << 62)) { set_error("subset index space exceeds 2^62"); return WB200_ENOSUP; }
+    }
+    *steps = (uint64_t)s;
+    return WB200_OK;
+}
+
+extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double* Dx, int n, const int32_t* edge_reps,
+                                     int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* out,
+                                     int length, double* kernel_ms) {
+    if (!Ax || !Dx || !edge_reps || !out) { set_error("lhaf_batch: null pointer"); return WB200_EINVAL; }
+    if (n < 2 || (n & 1)) { set_error("lhaf_batch: n must be even and >= 2 (got %d)", n); return WB200_EINVAL; }
+    const int E = n / 2;
+    if (E > BW_EMAX) { set_error("lhaf_batch: %d edges exceed the limit of %d", E, BW_EMAX); return WB200_ENOSUP; }
+    if (odd_variant && (E < 2 || edge_reps[1] != 1)) { set_error("lhaf_batch: odd variant needs edge_reps[1] == 1"); return WB200_EINVAL; }
+    uint64_t steps = 0;
+    int rc = wb200_lhaf_batch_steps(edge_reps, E, &steps);
+    if (rc) return rc;
+    if (j0 > j1 || j1 > steps) { set_error("lhaf_batch: bad subset range"); return WB200_EINVAL; }
+    BatchParams p;
+    memset(&p, 0, sizeof(p));
+    const int batch_max = edge_reps[0];
+    int fixed_sum = 0;
+    for (int i = 0; i < E; ++i) { p.reps[i] = edge_reps[i]; if (i >= (odd_variant ? 2 : 1)) fixed_sum += edge_reps[i]; }
+    if (odd_variant) {
+        p.N_fixed = 2 * fixed_sum + 1;
+        p.N_max = p.N_fixed + 2 * batch_max + cutoff_extra + 1;
+        p.length = 2 * batch_max + cutoff_extra + 2;
+    } else {
+        p.N_fixed = 2 * fixed_sum;
+        p.N_max = p.N_fixed + 2 * batch_max + cutoff_extra;
+        p.length = 2 * batch_max + cutoff_extra + 1;
+    }
+    if (length != p.length) { set_error("lhaf_batch: output length must be %d (got %d)", p.length, length); return WB200_EINVAL; }
+    if (p.N_max > BW_MAX_ORDER) { set_error("lhaf_batch: photon number %d too large", p.N_max); return WB200_ENOSUP; }
+    p.n = n; p.E = E; p.glynn = glynn; p.odd_variant = odd_variant; p.j0 = j0; p.j1 = j1;
+    p.smax = n; p.T = p.N_max / 2; p.O = p.N_max;
+    WB_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    if (device_sm_count(device, &sms)) return WB200_ECUDA;
+    DevBufB dA, dD, dpart, dout;
+    WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * n * n));
+    WB_CUDA(cudaMemcpy(dA.p, Ax, sizeof(double2) * n * n, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * n));
+    WB_CUDA(cudaMemcpy(dD.p, Dx, sizeof(double2) * n, cudaMemcpyHostToDevice));
+    p.A = (const double2*)dA.p; p.D = (const double2*)dD.p;
+    const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O) + sizeof(double) * 4 * (size_t)p.length;
+    int ctas = 1;
+    const int wpc = bw_pick_warps(per_warp, &ctas);
+    if (wpc < 1) { set_error("lhaf_batch: problem too large for shared memory (%zu bytes per warp)", per_warp); return WB200_ENOSUP; }
+    const size_t shm = per_warp * wpc;
+    WB_CUDA(cudaFuncSetAttribute(batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    int grid = sms * ctas;
+    const uint64_t total = j1 - j0, want = (total + wpc - 1) / wpc;
+    if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
+    const int nwarps = grid * wpc;
+    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * (size_t)p.length * nwarps));
+    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4 * (size_t)p.length));
+    p.partials = (double*)dpart.p;
+    EvPair ev;
+    WB_CUDA(cudaEventCreate(&ev.e0));
+    WB_CUDA(cudaEventCreate(&ev.e1));
+    WB_CUDA(cudaEventRecord(ev.e0, 0));
+    batch_kernel<<<grid, 32 * wpc, shm>>>(p);
+    batch_final_kernel<<<(p.length + 63) / 64, 64>>>((const double*)dpart.p, nwarps, p.length, (double*)dout.p);
+    WB_CUDA(cudaEventRecord(ev.e1, 0));
+    WB_CUDA(cudaEventSynchronize(ev.e1));
+    WB_CUDA(cudaGetLastError());
+    float ms = 0;
+    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    if (kernel_ms) *kernel_ms = ms;
+    WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * 4 * (size_t)p.length, cudaMemcpyDeviceToHost));
+    return WB200_OK;
+}
