@@ -9,7 +9,8 @@ scaling: total work fixed) and the partial sums are combined by one all-reduce i
   python bench.py --gpus N --steps K --warmup W                 # GPU arm (torchrun for N > 1)
   python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the oracle port on host cores
 
-Other workloads for development: --workload hafnian56|hafnian40|perm32|perm36|tor48|lhaf50
+Other workloads (the remaining BASELINE configs and the north-star targets):
+--workload hafnian24|hafnian56|lhaf50|perm32|perm40|tor48|gbs16
 """
 import argparse
 import ctypes
@@ -74,17 +75,48 @@ def make_gbs_state(M, B, seed, r=0.5, eta=0.8, hbar=2.0, mean_photons=0.45, max_
     return mu, cov, np.ascontiguousarray(pats[:B])
 
 
+def tor_tree_flops(N, DC=9):
+    """Executed flops of the Schur-complement tree kernel (torontonian.cu) per torontonian, counted from its
+    loops: an included child of a breadth-first node of dimension d updates (d-2)^2 complex entries with four
+    a*conj(b) products (6 flops) and four real-scaled subtractions (4 flops) = 40 flops; a 2-mode leaf node
+    costs ~70 flops for its 4 subsets; the shared leading-mode eliminations are lower order and included."""
+    DC = min(DC, N)
+    per_prefix = 0.0
+    for lvl in range(max(0, DC - 2)):
+        d = 2 * (DC - lvl)
+        per_prefix += (1 << lvl) * (d - 2) ** 2 * 40.0
+    per_prefix += (1 << max(0, DC - 2)) * 70.0
+    lead = 0.0
+    for i in range(N - DC):  # on average half of the leading modes are eliminated, on the full trailing block
+        d = 2 * (N - i)
+        lead += 0.5 * ((d - 1) ** 2 + (d - 2) ** 2) * 10.0
+    prefixes = 1 << (N - DC)
+    return prefixes * per_prefix + (prefixes / 32.0) * lead
+
+
 def units_and_flops(kind, n):
-    """(units per step, algorithmic flops per unit of THIS implementation, reference-algorithm flops per unit)."""
+    """(units per step, executed-algorithm flops per unit of THIS implementation, reference-algorithm flops per
+    unit, text of the model, FP64 pipe the kernel issues to)."""
     if kind in ("hafnian", "lhaf"):
         m = n // 2
         nprod = (m - 1) // 2
-        return 1 << (m - 1), 8.0 * n**3 * nprod, 8.0 * n**3 * (m - 1)
+        return (1 << (m - 1), 8.0 * n**3 * nprod, 8.0 * n**3 * (m - 1),
+                "8 n^3 floor((n/2-1)/2) per subset: trace pairing halves the reference's 8 n^3 (n/2-1) product chain",
+                "FP64 DMMA.8x8x4 (tensor pipe; same flop rate as the FP64 FMA pipe)")
     if kind == "perm":
-        return 1 << (n - 1), 8.0 * n - 4, 8.0 * n - 4
+        return (1 << (n - 1), 8.0 * n - 4, 8.0 * n - 4,
+                "8n-4 per Gray-code step (n complex adds + n-1 complex multiplies + accumulate); these occupy 6n-2 "
+                "FP64 issue slots, so the flop fraction cannot exceed (8n-4)/(2(6n-2)) ~ 67 % of the DFMA peak",
+                "FP64 DFMA/DMUL/DADD (vector pipe)")
     if kind == "tor":
         N = n // 2
-        return 1 << N, float("nan"), float("nan")
+        f = tor_tree_flops(N) / float(1 << N)
+        # direct method of the reference: complex Cholesky (4/3)(2k)^3 averaged over subsets, E[k^3] over Binomial(N, 1/2)
+        ek3 = N * (N - 1) * (N - 2) / 8.0 + 3 * N * (N - 1) / 4.0 + N / 2.0
+        return (1 << N, f, (4.0 / 3.0) * 8.0 * ek3,
+                "Schur-complement tree: 40 flops per updated entry of every included child node (torontonian.cu), "
+                "averaged per subset; the kernel is shared-memory bound, the FP64 fraction is reported for scale only",
+                "FP64 DFMA (vector pipe), operands in shared memory")
     raise ValueError(kind)
 
 
@@ -123,6 +155,14 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+def gbs_reference_flops(pats):
+    """Reference-algorithm flops for the GBS patterns workload: a pattern with N_p photons is a loop hafnian of
+    the reduction-expanded 2N_p x 2N_p matrix: 2^(N_p-1) Glynn subsets x 8 (2N_p)^3 (N_p - 1)."""
+    Np = pats.sum(axis=1).astype(np.float64)
+    Np = Np[Np >= 2]
+    return float(np.sum(2.0 ** (Np - 1) * 8.0 * (2 * Np) ** 3 * (Np - 1)))
+
+
 def cpu_baseline(kind, n, X, seconds=15.0):
     """Time the oracle's C port (reference algorithm) on the host cores over a bounded sample."""
     from oracle import c_oracle as co
@@ -132,22 +172,23 @@ def cpu_baseline(kind, n, X, seconds=15.0):
         x = co.matched_order(X)
         Ax = np.ascontiguousarray(X[np.ix_(x, x)])
         Dx = np.ascontiguousarray(np.diag(X)[x]) if kind == "lhaf" else None
-        co.hafnian_range(Ax, 0, 64 * threads, Dx)  # warm-up (thread pool, page faults)
+        total = 1 << (n // 2 - 1)
+        co.hafnian_range(Ax, 0, min(total, 64 * threads), Dx)  # warm-up (thread pool, page faults)
         t0 = time.perf_counter()
-        co.hafnian_range(Ax, 0, 256 * threads, Dx)
-        rate = 256 * threads / (time.perf_counter() - t0)
-        sample = int(min(1 << (n // 2 - 1), max(1024, rate * seconds)))
+        co.hafnian_range(Ax, 0, min(total, 256 * threads), Dx)
+        rate = min(total, 256 * threads) / (time.perf_counter() - t0)
+        sample = int(min(total, max(1024, rate * seconds)))
         t0 = time.perf_counter()
         co.hafnian_range(Ax, 0, sample, Dx)
         dt = time.perf_counter() - t0
-        what = f"first {sample} of {1 << (n // 2 - 1)} Glynn subsets of the same {n}x{n} matrix, full product-chain algorithm"
+        what = f"first {sample} of {total} Glynn subsets of the same {n}x{n} matrix, full product-chain algorithm"
     elif kind == "perm":
-        sample = int(min(1 << (n - 1), 4e7 * threads))
+        sample = int(min(1 << (n - 1), 4e7 * threads * seconds / 15.0))
         t0 = time.perf_counter()
         co.perm_range(X, 0, 0, sample)
         dt = time.perf_counter() - t0
         what = f"first {sample} of {1 << (n - 1)} Gray-code steps (the reference itself is single-threaded; the port splits the range over threads)"
-    else:
+    elif kind == "tor":
         N = n // 2
         sample = 1 << N
         t0 = time.perf_counter()
@@ -155,36 +196,75 @@ def cpu_baseline(kind, n, X, seconds=15.0):
         dt = time.perf_counter() - t0
         threads = 1
         what = "full recursive torontonian (single thread, as the reference)"
+    else:  # gbs: X = (A, gamma, rpt); one loop hafnian per pattern through the NumPy oracle, single thread as the reference
+        from oracle import walrus_oracle as wo
+
+        A, gamma, rpt = X
+        t0 = time.perf_counter()
+        sample = 0
+        for r in rpt:
+            wo.loop_hafnian(A, gamma, [int(v) for v in r])
+            sample += 1
+            if time.perf_counter() - t0 > seconds:
+                break
+        dt = time.perf_counter() - t0
+        threads = 1
+        what = f"first {sample} of {len(rpt)} patterns, one loop hafnian per pattern (NumPy restatement, single thread; the reference makes one Python call per pattern)"
+        return {"value": sample / dt, "unit": "patterns/s", "cores": threads, "kind": "port", "sample": what, "seconds": dt}
     return {"value": sample / dt, "unit": "subsets/s", "cores": threads, "kind": "port", "sample": what,
             "seconds": dt}
+
+
+def metric_name(workload):
+    if workload == "hafnian50":
+        return METRIC
+    if workload.startswith("gbs"):
+        return f"{workload} GBS pattern probabilities/s"
+    return f"{workload} subsets/s"
+
+
+def gbs_inputs(workload, batch):
+    import thewalrus_b200 as wb
+
+    M = int(workload[3:])
+    mu, cov, pats = make_gbs_state(M, batch, seed=1000 * 3 + M)
+    A, gamma = wb.quantum._state(mu, cov, 2, 1e-10)
+    rpt = np.ascontiguousarray(np.concatenate([pats, pats], axis=1))
+    return M, mu, cov, pats, A, gamma, rpt
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as ge  # builds the oracle if needed (CPU only)
+    import __graft_entry__ as ge  # noqa: F401  (builds the oracle if needed; CPU only)
 
     from oracle import build as obuild
 
     obuild.ensure()
-    kind, n, X = make_input(args.workload)
-    units, _, ref_flops = units_and_flops(kind, n)
+    per = max(2.0, 60.0 / max(1, args.warmup + args.steps))
+    if args.workload.startswith("gbs"):
+        M, mu, cov, pats, A, gamma, rpt = gbs_inputs(args.workload, args.batch)
+        kind, n, X, units, ref_flops, unit = "gbs", 2 * M, (A, gamma, rpt), len(rpt), gbs_reference_flops(pats) / len(rpt), "patterns/s"
+    else:
+        kind, n, X = make_input(args.workload)
+        units, _, ref_flops, _, _ = units_and_flops(kind, n)
+        unit = "subsets/s"
     vals = []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(kind, n, X, seconds=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        cb = cpu_baseline(kind, n, X, seconds=per)
         if i >= args.warmup:
             vals.append(cb)
     v = statistics.mean(c["value"] for c in vals)
-    line = {"impl": "reference", "metric": METRIC if args.workload == "hafnian50" else f"{args.workload} subsets/s",
-            "value": v, "unit": "subsets/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": metric_name(args.workload),
+            "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": units / v * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": n, "units_per_step": units,
                        "note": "each step is a bounded sample of the workload; ms_per_step is extrapolated to the full step"},
-            "cpu_baseline": {"value": v, "unit": "subsets/s", "cores": vals[-1]["cores"], "kind": "port",
+            "cpu_baseline": {"value": v, "unit": unit, "cores": vals[-1]["cores"], "kind": "port",
                              "sample": vals[-1]["sample"], "gflops_reference_algorithm": v * ref_flops * 1e-9},
-            "e2e": {"value": v, "unit": "subsets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -195,6 +275,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hafnian50")
+    ap.add_argument("--batch", type=int, default=100000, help="patterns per step of the gbs workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -215,29 +296,48 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
-    kind, n, X = make_input(args.workload)
-    units, my_flops, ref_flops = units_and_flops(kind, n)
-    lo, hi = shard_range(units if kind != "tor" else _engine.tor_num_prefixes(n // 2), rank, world)
+    is_gbs = args.workload.startswith("gbs")
+    if is_gbs:
+        M, mu, cov, pats, A, gamma, rpt = gbs_inputs(args.workload, args.batch)
+        kind, n, X = "gbs", 2 * M, (A, gamma, rpt)
+        units = len(rpt)
+        ref_flops = gbs_reference_flops(pats) / units
+        my_flops = ref_flops
+        model = ("reference-algorithm flops of the reduction-expanded Glynn loop hafnians, sum_p 2^(N_p-1) 8 (2N_p)^3 (N_p-1); "
+                 "the kernel works on the un-expanded matrices with mixed-radix subsets, so this is an equivalent, not an executed count")
+        pipe = "FP64 DFMA (vector pipe), warp per subset, operands in shared memory"
+        unit = "patterns/s"
+        lo, hi = shard_range(units, rank, world)
+    else:
+        kind, n, X = make_input(args.workload)
+        units, my_flops, ref_flops, model, pipe = units_and_flops(kind, n)
+        unit = "subsets/s"
+        lo, hi = shard_range(units if kind != "tor" else _engine.tor_num_prefixes(n // 2), rank, world)
 
     # ---- device-resident inputs for the kernel-only number
+    dA = dD = None
+    wsb = 8
     if kind in ("hafnian", "lhaf"):
         x, er, _ = wb.matched_reps([1] * n)
         Ax = np.ascontiguousarray(X[np.ix_(x, x)].astype(np.complex128))
         dA = torch.from_numpy(Ax.view(np.float64).reshape(-1)).to(dev)
         dD = torch.from_numpy(np.ascontiguousarray(np.diag(X)[x]).view(np.float64).reshape(-1)).to(dev) if kind == "lhaf" else None
         wsb = lib.wb200_hafnian_workspace_bytes(n)
-        launches_per_step = 3
+        launches_per_step = 3      # haf_prep, haf_dmma, final_reduce
     elif kind == "perm":
         dA = torch.from_numpy(np.ascontiguousarray(X).view(np.float64).reshape(-1)).to(dev)
         wsb = lib.wb200_perm_workspace_bytes(n)
-        launches_per_step = 2
+        launches_per_step = 2      # perm_kernel, final_reduce
+    elif kind == "tor":
+        launches_per_step = 3      # tor_prep, tor_kernel, final_reduce
     else:
-        dA, wsb, launches_per_step = None, 8, 3
+        launches_per_step = 4      # pat_prep, scan, pat_main, pat_final
     ws = torch.empty((wsb + 7) // 8, dtype=torch.float64, device=dev)
     out = torch.zeros(4, dtype=torch.float64, device=dev)
     table = torch.zeros((world, 4), dtype=torch.float64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
+    inner_ms = []   # kernel time reported by the *_host entry points (CUDA events around the launches only)
 
     def kernel_step():
         if kind in ("hafnian", "lhaf"):
@@ -246,12 +346,19 @@ def main():
         elif kind == "perm":
             rc = lib.wb200_perm_dev(dA.data_ptr(), n, 0, lo, hi, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
                                     stream.cuda_stream)
-        else:
-            o2 = _engine.tor_range(X, lo, hi, dev)
+        elif kind == "tor":
+            o2 = np.zeros(2)
+            ms = ctypes.c_double(0)
+            Oc, pO = _lib.as_c128(X)
+            rc = lib.wb200_tor_host(local, pO, n // 2, lo, hi, _lib.dptr(o2), ctypes.byref(ms))
+            inner_ms.append(ms.value)
             out[:2] = torch.from_numpy(o2).to(dev)
+        else:
+            _, ms = _engine.lhaf_patterns_local(A, gamma, rpt[lo:hi], True, dev, want_ms=True)
+            inner_ms.append(ms)
             rc = 0
         _lib.check(rc, "kernel step")
-        if world > 1:  # the one collective of the path: all-reduce of the (hi, lo) partials
+        if world > 1 and not is_gbs:  # the one collective of the path: all-reduce of the (hi, lo) partials
             table.zero_()
             table[rank] = out
             dist.all_reduce(table)
@@ -270,14 +377,15 @@ def main():
     total_ms = 0.0
     kern_ms = []
     for _ in range(args.steps):
-        flush.fill_(1.0)  # L2 flush between timed iterations (inputs are 40 KB, far below L2)
+        flush.fill_(1.0)  # L2 flush between timed iterations (inputs are KB-sized, far below L2)
         sync_all()
+        inner_ms.clear()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         kernel_step()
         e1.record(stream)
         sync_all()
-        ms = e0.elapsed_time(e1)
+        ms = inner_ms[-1] if inner_ms else e0.elapsed_time(e1)   # host-buffer entry points time their own launches
         kern_ms.append(ms)
         total_ms += ms
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -285,20 +393,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = units * args.steps / (total_ms * 1e-3)
-    if world > 1:
+    if is_gbs:
+        res = 0j
+    elif world > 1:
         res = _engine.combine4(table.cpu().numpy())
     else:
         res = _engine.combine4([out.cpu().numpy()])
 
     # ---- end to end through the public API with host buffers
+    grp = True if world > 1 else None
+
     def e2e_step():
         if kind == "hafnian":
-            return wb.hafnian(X, group=(True if world > 1 else None))
+            return wb.hafnian(X, group=grp)
         if kind == "lhaf":
-            return wb.hafnian(X, loop=True, group=(True if world > 1 else None))
+            return wb.hafnian(X, loop=True, group=grp)
         if kind == "perm":
-            return wb.perm(X, method="glynn", group=(True if world > 1 else None))
-        return wb.tor(X, group=(True if world > 1 else None))
+            return wb.perm(X, method="glynn", group=grp)
+        if kind == "tor":
+            return wb.tor(X, group=grp)
+        return float(np.sum(wb.probabilities_batch(mu, cov, pats, group=grp)))
 
     e2e_step()
     sync_all()
@@ -315,30 +429,45 @@ def main():
 
     if rank == 0:
         peak = ctypes.c_double(0)
-        lib.wb200_fp64_peak(local, 1, ctypes.byref(peak))
-        per_gpu_units = (hi - lo)
+        lib.wb200_fp64_peak(local, 1 if kind in ("hafnian", "lhaf") else 0, ctypes.byref(peak))
+        per_gpu_units = (hi - lo) if kind != "tor" else units / world
         kms = statistics.mean(kern_ms)
         achieved = per_gpu_units * my_flops / (kms * 1e-3) * 1e-12
+        if is_gbs:
+            h2d, d2h = int(mu.nbytes + cov.nbytes + pats.nbytes), int(8 * len(pats))
+            cfg_in = (f"{M}-mode Gaussian state (Haar interferometer, r=0.5, eta=0.8, displaced), {units} Poisson(0.45) "
+                      "patterns with <= 10 photons")
+            api = "thewalrus_b200.probabilities_batch(mu, cov, patterns) with host NumPy arrays"
+        else:
+            h2d, d2h = int(X.nbytes), 32
+            cfg_in = {"hafnian": "random complex symmetric G+G^T, seed 1000*config+n", "lhaf": "random complex symmetric G+G^T, loops = diagonal",
+                      "perm": "n x n block of a 2n Haar unitary", "tor": "random Hermitian O = 0.9 H/||H||, 2N x 2N"}[kind]
+            api = {"hafnian": "thewalrus_b200.hafnian(A)", "lhaf": "thewalrus_b200.hafnian(A, loop=True)",
+                   "perm": "thewalrus_b200.perm(A, method='glynn')", "tor": "thewalrus_b200.tor(O)"}[kind] + " with a host NumPy array"
         line = {
-            "metric": METRIC if args.workload == "hafnian50" else f"{args.workload} subsets/s",
-            "value": value, "unit": "subsets/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": metric_name(args.workload),
+            "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "n": n, "units_per_step": units, "units": "Glynn subsets (reference `steps`)",
-                       "input": "random complex symmetric G+G^T, seed 1000*config+n" if kind != "perm" else "n x n block of a 2n Haar unitary",
-                       "parallelism": f"subset-index shards x{world}, one all-reduce", "l2_flush": True,
+            "config": {"workload": args.workload, "n": n, "units_per_step": units,
+                       "units": "photon-number patterns" if is_gbs else "subsets (reference `steps`)",
+                       "input": cfg_in,
+                       "parallelism": (f"pattern shards x{world}, one all-gather" if is_gbs else f"subset-index shards x{world}, one all-reduce"),
+                       "l2_flush": True,
                        "l2_note": "256 MiB fill between timed iterations; inputs are KB-sized, the path is FP64-pipe bound"},
-            "e2e": {"value": units * args.steps / e2e_s, "unit": "subsets/s", "h2d_bytes_per_step": int(X.nbytes),
-                    "d2h_bytes_per_step": 32, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "thewalrus_b200.hafnian(A) with a host NumPy array" if kind == "hafnian" else "public API"},
+            "e2e": {"value": units * args.steps / e2e_s, "unit": unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3, "api": api},
             "gpu_launches": launches_per_step * args.steps * world,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "pipe": "FP64 DMMA.8x8x4 (same issue rate as the FP64 FMA pipe)",
+            "roofline": {"bound": "tensor", "pipe": pipe,
                          "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-                         "peak_source": "measured live by wb200_fp64_peak (DMMA chain micro-benchmark); MEASURED_PEAKS.json has no FP64 entry; nominal 37.2 at 1965 MHz",
-                         "flops_per_unit": my_flops, "flops_model": "8 n^3 floor((n/2-1)/2): pairing halves the reference's 8 n^3 (n/2-1)",
+                         "peak_source": "measured live by wb200_fp64_peak (dependent-chain micro-benchmark on the same pipe: "
+                                        "DMMA for the hafnian kernels, DFMA otherwise); MEASURED_PEAKS.json has no FP64 entry; "
+                                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+                         "flops_per_unit": my_flops, "flops_model": model,
                          "reference_algorithm_equivalent_tflops": per_gpu_units * ref_flops / (kms * 1e-3) * 1e-12,
-                         "kernel_ms": kms, "traffic": None},
+                         "kernel_ms": kms, "traffic": None,
+                         "traffic_note": "DRAM traffic is KB per launch (matrix in, 4 doubles per CTA out); see profiles/ for the ncu capture"},
             "result": {"re": res.real, "im": res.imag, "e2e_re": complex(r_e2e).real},
         }
         if not args.no_cpu_baseline and world == 1:

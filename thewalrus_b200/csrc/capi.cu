@@ -39,6 +39,7 @@ int device_sm_count(int device, int* sms) {
     return WB200_OK;
 }
 
+int check_perm_args(int n, int method, uint64_t k0, uint64_t k1);
 int perm_f64_dev(const double*, int, int, uint64_t, uint64_t, double*, void*, cudaStream_t);
 int perm_i64_dev(const int64_t*, int, int, uint64_t, uint64_t, unsigned long long*, cudaStream_t);
 
@@ -157,7 +158,7 @@ extern "C" int wb200_hafnian_host(int device, const double* A, const double* D, 
 extern "C" int wb200_perm_host(int device, const double* M, int n, int method, uint64_t k0, uint64_t k1,
                                double out4[4], double* kernel_ms) {
     if (!M || !out4) { set_error("perm: null pointer"); return WB200_EINVAL; }
-    if (n < 1 || n > 40) { set_error("perm: n = %d outside [1, 40]", n); return n > 40 ? WB200_ENOSUP : WB200_EINVAL; }
+    { int rc0 = check_perm_args(n, method, k0, k1); if (rc0) return rc0; }
     WB_CUDA(cudaSetDevice(device));
     DevBuf dM, dout, ws;
     const size_t wsb = wb200_perm_workspace_bytes(n);
@@ -175,7 +176,7 @@ extern "C" int wb200_perm_host(int device, const double* M, int n, int method, u
 extern "C" int wb200_perm_f64_host(int device, const double* M, int n, int method, uint64_t k0, uint64_t k1,
                                    double out2[2], double* kernel_ms) {
     if (!M || !out2) { set_error("perm: null pointer"); return WB200_EINVAL; }
-    if (n < 1 || n > 40) { set_error("perm: n = %d outside [1, 40]", n); return n > 40 ? WB200_ENOSUP : WB200_EINVAL; }
+    { int rc0 = check_perm_args(n, method, k0, k1); if (rc0) return rc0; }
     WB_CUDA(cudaSetDevice(device));
     DevBuf dM, dout, ws;
     if (dM.alloc(sizeof(double) * n * n) || dout.alloc(4 * sizeof(double)) || ws.alloc(wb200_perm_workspace_bytes(n))) return WB200_ECUDA;
@@ -194,7 +195,7 @@ extern "C" int wb200_perm_f64_host(int device, const double* M, int n, int metho
 extern "C" int wb200_perm_int64_host(int device, const int64_t* M, int n, int method, uint64_t k0, uint64_t k1,
                                      int64_t* out, double* kernel_ms) {
     if (!M || !out) { set_error("perm: null pointer"); return WB200_EINVAL; }
-    if (n < 1 || n > 40) { set_error("perm: n = %d outside [1, 40]", n); return n > 40 ? WB200_ENOSUP : WB200_EINVAL; }
+    { int rc0 = check_perm_args(n, method, k0, k1); if (rc0) return rc0; }
     WB_CUDA(cudaSetDevice(device));
     DevBuf dM, dout;
     if (dM.alloc(sizeof(int64_t) * n * n) || dout.alloc(sizeof(int64_t))) return WB200_ECUDA;

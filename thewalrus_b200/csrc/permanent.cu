@@ -4,30 +4,45 @@
 // column sums r_c = sum_rows delta_row M[row, c]:
 //   bbfg : delta = +1 / -1 for bit clear / set, k in [0, 2^(n-1)), result total / 2^(n-1)
 //   ryser: r_c = -sum_{rows in g(k)} M[row, c],  k in [0, 2^n), result total (the sign absorbs (-1)^n)
-// B200 mapping: every thread owns whole power-of-two aligned segments of the step index, keeps all n
-// column sums in registers, seeds them from the Gray code of its first step (O(n^2)) and then applies the
-// +-2*row (bbfg) / +-1*row (ryser) update per step.  Because segments are aligned and equally long, the
-// flipped row ctz(k+1) is warp-uniform, so the row is one broadcast read from shared memory.  Products use
-// four independent chains for FP64 ILP; per-thread Kahan sums feed a double-double block/grid reduction.
+//
+// B200 mapping.  The step index is cut in power-of-two aligned, equally long segments ("streams").  A stream
+// is owned by SL adjacent lanes of a warp; lane `sub` keeps the column sums of the interleaved columns
+// c * SL + sub (CPL of them) in registers.  SL = 1 (one thread holds all n sums) is the fastest shape up to
+// n = 40 and is what runs there; SL = 4 with two streams per lane carries n = 41..64, where the sums no longer
+// fit one thread (measured shapes: profiles/r01_perm_shapes.txt).
+// Streams are seeded from the Gray code of their first step (O(n CPL) per lane) and then advance by the
+// +-2*row (bbfg) / +-row (ryser) update; all streams of a warp are at the same offset of their segment, so
+// the flipped row ctz(k) is warp-uniform and a lane's piece of the row is one LDS.128 shared by 32/SL lanes.
+// Steps are taken in groups of G = max(SL, 2): every lane forms its partial product of each step of the group,
+// then a transpose-reduce over the SL lanes (shuffle + one complex multiply per halving) leaves lane `sub`
+// with the complete product of step k + sub, whose sign (-1)^sub is static.  There is no branch inside a
+// group: steps outside [k0, k1) (ragged shard edges) are masked by a zero weight.  Terms are added in plain
+// FP64 over 16 groups and then folded into a per-thread Kahan sum (the per-term rounding of the n-factor
+// product dominates that block sum by an order of magnitude); per-thread sums feed a double-double
+// warp -> block -> grid reduction in fixed order.
+#include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
 
 namespace wb {
 
-constexpr int PERM_THREADS = 256;
+constexpr int PERM_THREADS = 128;
+constexpr int PERM_MIN_CTAS = 2;        // <= 255 registers; the tile shapes below land at 8-16 warps per SM
+constexpr int PERM_BLOCK_GROUPS = 16;   // groups added in plain FP64 before the compensated fold
 
 struct C128 {
     double re, im;
-    __device__ __forceinline__ static C128 zero() { return {0.0, 0.0}; }
-    __device__ __forceinline__ static C128 one() { return {1.0, 0.0}; }
 };
 __device__ __forceinline__ C128 cmul(C128 a, C128 b) {
     return {fma(a.re, b.re, -a.im * b.im), fma(a.re, b.im, a.im * b.re)};
 }
 __device__ __forceinline__ double cmul(double a, double b) { return a * b; }
 __device__ __forceinline__ unsigned long long cmul(unsigned long long a, unsigned long long b) { return a * b; }
+__device__ __forceinline__ C128 cadd(C128 a, C128 b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ double cadd(double a, double b) { return a + b; }
+__device__ __forceinline__ unsigned long long cadd(unsigned long long a, unsigned long long b) { return a + b; }
 
-// x += s * y with s in {+-1, +-2}
+// x += s * y with s in {0, +-1, +-2}
 __device__ __forceinline__ void axpy(C128& x, double s, C128 y) {
     x.re = fma(s, y.re, x.re);
     x.im = fma(s, y.im, x.im);
@@ -35,6 +50,15 @@ __device__ __forceinline__ void axpy(C128& x, double s, C128 y) {
 __device__ __forceinline__ void axpy(double& x, double s, double y) { x = fma(s, y, x); }
 __device__ __forceinline__ void axpy(unsigned long long& x, long long s, unsigned long long y) {
     x += (unsigned long long)s * y;
+}
+
+// shuffles among the lanes of one stream only (streams of a warp may run different numbers of groups)
+__device__ __forceinline__ double shfl_xor_s(unsigned mask, double v, int m) { return __shfl_xor_sync(mask, v, m); }
+__device__ __forceinline__ C128 shfl_xor_s(unsigned mask, C128 v, int m) {
+    return {__shfl_xor_sync(mask, v.re, m), __shfl_xor_sync(mask, v.im, m)};
+}
+__device__ __forceinline__ unsigned long long shfl_xor_s(unsigned mask, unsigned long long v, int m) {
+    return __shfl_xor_sync(mask, v, m);
 }
 
 template <typename S> struct Traits;
@@ -54,54 +78,74 @@ template <> struct Traits<unsigned long long> {
     __device__ static unsigned long long one() { return 1ull; }
 };
 
-// Kahan accumulators
+// Kahan accumulators (fed with block sums)
 struct KahanC {
     double sr = 0, cr = 0, si = 0, ci = 0;
-    __device__ __forceinline__ void add(C128 x, bool neg) {
-        double xr = neg ? -x.re : x.re, xi = neg ? -x.im : x.im;
-        double y = xr - cr, t = sr + y;
+    __device__ __forceinline__ void add(C128 x) {
+        double y = x.re - cr, t = sr + y;
         cr = (t - sr) - y; sr = t;
-        y = xi - ci; t = si + y;
+        y = x.im - ci; t = si + y;
         ci = (t - si) - y; si = t;
     }
     __device__ __forceinline__ cdd get() const { cdd o; o.re = {sr, -cr}; o.im = {si, -ci}; return o; }
 };
 struct KahanR {
     double s = 0, c = 0;
-    __device__ __forceinline__ void add(double x, bool neg) {
-        double y = (neg ? -x : x) - c, t = s + y;
+    __device__ __forceinline__ void add(double x) {
+        double y = x - c, t = s + y;
         c = (t - s) - y; s = t;
     }
     __device__ __forceinline__ cdd get() const { cdd o; o.re = {s, -c}; o.im = {0.0, 0.0}; return o; }
 };
 struct AccI {
     unsigned long long s = 0;
-    __device__ __forceinline__ void add(unsigned long long x, bool neg) { s += neg ? (0ull - x) : x; }
+    __device__ __forceinline__ void add(unsigned long long x) { s += x; }
 };
 template <typename S> struct AccOf;
 template <> struct AccOf<C128> { using type = KahanC; };
 template <> struct AccOf<double> { using type = KahanR; };
 template <> struct AccOf<unsigned long long> { using type = AccI; };
 
-template <int NP, typename S>
-__device__ __forceinline__ S product(const S (&r)[NP]) {
-    S p0 = r[0], p1 = r[1], p2 = r[2], p3 = r[3];
+// product of CPL values with up to four independent chains
+template <int CPL, typename S>
+__device__ __forceinline__ S product(const S (&r)[CPL]) {
+    constexpr int NC = CPL < 4 ? CPL : 4;
+    S p[NC];
 #pragma unroll
-    for (int c = 4; c < NP; c += 4) {
-        p0 = cmul(p0, r[c]);
-        p1 = cmul(p1, r[c + 1]);
-        p2 = cmul(p2, r[c + 2]);
-        p3 = cmul(p3, r[c + 3]);
-    }
-    return cmul(cmul(p0, p1), cmul(p2, p3));
+    for (int j = 0; j < NC; ++j) p[j] = r[j];
+#pragma unroll
+    for (int c = NC; c < CPL; ++c) p[c % NC] = cmul(p[c % NC], r[c]);
+    if constexpr (NC == 4) return cmul(cmul(p[0], p[1]), cmul(p[2], p[3]));
+    else if constexpr (NC == 3) return cmul(cmul(p[0], p[1]), p[2]);
+    else if constexpr (NC == 2) return cmul(p[0], p[1]);
+    else return p[0];
 }
 
-// M in shared memory: smem[row * NP + col]; padded columns hold 0 and their sums are pinned to 1.
-template <int NP, typename S>
-__global__ void __launch_bounds__(PERM_THREADS)
+// x, -x or 0 by selects (no FP64 issue slots)
+__device__ __forceinline__ C128 weigh(C128 x, bool on, bool neg) {
+    C128 y = {neg ? -x.re : x.re, neg ? -x.im : x.im};
+    return {on ? y.re : 0.0, on ? y.im : 0.0};
+}
+__device__ __forceinline__ double weigh(double x, bool on, bool neg) { return on ? (neg ? -x : x) : 0.0; }
+__device__ __forceinline__ unsigned long long weigh(unsigned long long x, bool on, bool neg) {
+    return on ? (neg ? (0ull - x) : x) : 0ull;
+}
+
+// M in shared memory: sM[row * NP + col], NP = CPL * SL >= n, padded columns hold 0 and their sums are pinned
+// to 1.  Lane `sub` of a lane group owns columns c * SL + sub (interleaved, so the SL pieces of one LDS.128 sit
+// in adjacent 16-byte slots: no bank conflicts) of NS independent streams: a register tile r[NS][CPL].  Every
+// row element fetched from shared memory feeds NS updates, which is what lifts the kernel off the shared-memory
+// return path (one LDS.128 per 6 FP64 instructions saturates the 128 B/clk LSU before the FP64 pipe:
+// tools/fp64_mix.cu, profiles/r01_fp64_mix.txt) and gives NS-fold instruction-level parallelism.
+// All streams of the grid sit at the same offset t of their 2^logL-aligned segment, so the flipped row
+// ctz(t) and the loop trip counts are uniform; steps outside [k0, k1) are masked by a zero weight.
+template <int CPL, int SL, int NS, int MINB, typename S>
+__global__ void __launch_bounds__(PERM_THREADS, MINB)
 perm_kernel(const S* __restrict__ Mg, int n, int ryser, uint64_t k0, uint64_t k1, int logL,
             double* __restrict__ partials, unsigned long long* __restrict__ iout) {
     using Coef = typename Traits<S>::Coef;
+    constexpr int NP = CPL * SL;
+    constexpr int G = SL < 2 ? 2 : SL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* sM = reinterpret_cast<S*>(smem_raw);
     for (int i = threadIdx.x; i < n * NP; i += PERM_THREADS) {
@@ -111,44 +155,116 @@ perm_kernel(const S* __restrict__ Mg, int n, int ryser, uint64_t k0, uint64_t k1
     __syncthreads();
 
     typename AccOf<S>::type acc;
-    const uint64_t L = 1ull << logL;
+    const int sub = threadIdx.x & (SL - 1);
+    const uint32_t L = 1u << logL;
     const uint64_t c_first = k0 >> logL, c_last = (k1 + L - 1) >> logL;  // chunk ids [c_first, c_last)
-    const uint64_t nthreads = (uint64_t)gridDim.x * PERM_THREADS;
+    const uint64_t ngroups = (uint64_t)gridDim.x * (PERM_THREADS / SL);
+    const uint64_t group = ((uint64_t)blockIdx.x * PERM_THREADS + threadIdx.x) / SL;
     const Coef step = ryser ? (Coef)1 : (Coef)2;
-    for (uint64_t c = c_first + (uint64_t)blockIdx.x * PERM_THREADS + threadIdx.x; c < c_last; c += nthreads) {
-        uint64_t kb = c << logL, ke = kb + L;
-        if (kb < k0) kb = k0;
-        if (ke > k1) ke = k1;
-        if (kb >= ke) continue;
-        // ---- seed column sums from g(kb)
-        uint64_t gray = kb ^ (kb >> 1);
-        S r[NP];
+    const S* mcol = sM + sub;
+    const uint64_t per_round = ngroups * NS;
+    const uint64_t rounds = (c_last - c_first + per_round - 1) / per_round;
+    for (uint64_t it = 0; it < rounds; ++it) {
+        uint64_t kbase[NS];
+        uint32_t tlo[NS], thi[NS];          // steps t in [tlo, thi) of the segment lie in [k0, k1)
+        S r[NS][CPL];
 #pragma unroll
-        for (int col = 0; col < NP; ++col) r[col] = Traits<S>::zero();
+        for (int s = 0; s < NS; ++s) {
+            const uint64_t c = c_first + (it * ngroups + group) * NS + s;
+            kbase[s] = c << logL;
+            const uint64_t lo = kbase[s] < k0 ? k0 : kbase[s];
+            uint64_t hi = kbase[s] + L;
+            if (hi > k1) hi = k1;
+            const bool live = c < c_last && lo < hi;
+            tlo[s] = live ? (uint32_t)(lo - kbase[s]) : 0u;
+            thi[s] = live ? (uint32_t)(hi - kbase[s]) : 0u;
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) r[s][q] = Traits<S>::zero();
+        }
+        // ---- seed the column sums from g(kbase)
         for (int row = 0; row < n; ++row) {
-            const bool set = (gray >> row) & 1ull;
-            const Coef d = ryser ? (set ? (Coef)-1 : (Coef)0) : (set ? (Coef)-1 : (Coef)1);
-            if (d != (Coef)0) {
+            Coef d[NS];
 #pragma unroll
-                for (int col = 0; col < NP; ++col) axpy(r[col], d, sM[row * NP + col]);
+            for (int s = 0; s < NS; ++s) {
+                const bool set = ((kbase[s] ^ (kbase[s] >> 1)) >> row) & 1ull;
+                d[s] = ryser ? (set ? (Coef)-1 : (Coef)0) : (set ? (Coef)-1 : (Coef)1);
+            }
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) {
+                const S mv = mcol[row * NP + q * SL];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) axpy(r[s][q], d[s], mv);
             }
         }
 #pragma unroll
-        for (int col = 0; col < NP; ++col)
-            if (col >= n) r[col] = Traits<S>::one();
-        // ---- sweep
-        for (uint64_t k = kb; k < ke; ++k) {
-            acc.add(product<NP, S>(r), (k & 1ull) != 0);
-            const uint64_t k1n = k + 1;
-            const int row = __ffsll((long long)k1n) - 1;         // bit flipped between g(k) and g(k+1)
-            if (row < n) {
-                const bool set = ((k1n ^ (k1n >> 1)) >> row) & 1ull;  // new value of that bit
-                const Coef d = set ? -step : step;
-                const S* mrow = sM + row * NP;
+        for (int q = 0; q < CPL; ++q)
+            if (q * SL + sub >= n) {
 #pragma unroll
-                for (int col = 0; col < NP; ++col) axpy(r[col], d, mrow[col]);  // padded columns add 0
+                for (int s = 0; s < NS; ++s) r[s][q] = Traits<S>::one();
+            }
+        // ---- sweep in groups of G steps
+        S blk[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) blk[s] = Traits<S>::zero();
+        int inblk = 0;
+        for (uint32_t t = 0; t < L; t += G) {
+            S P[NS][G];
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                const uint32_t tt = t + i;
+                // flip the row that turns g(k - 1) into g(k), k = kbase + tt; nothing to do for the seeded step
+                int row = tt ? (__ffs((int)tt) - 1) : 0;
+                if (row >= n) row = n - 1;        // only in masked steps of a one-segment problem
+                Coef d[NS];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    const uint32_t two = (uint32_t)((kbase[s] + tt) >> row) & 3u;   // bits row, row + 1 of k
+                    const bool set = ((two ^ (two >> 1)) & 1u) != 0;                 // new value of Gray bit `row`
+                    d[s] = tt ? (set ? -step : step) : (Coef)0;
+                }
+                const S* mrow = mcol + row * NP;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const S mv = mrow[q * SL];
+#pragma unroll
+                    for (int s = 0; s < NS; ++s) axpy(r[s][q], d[s], mv);          // padded columns add 0
+                }
+#pragma unroll
+                for (int s = 0; s < NS; ++s) P[s][i] = product<CPL, S>(r[s]);
+            }
+            // ---- transpose-reduce over the SL lanes: lane `sub` ends with the full product of step t + sub
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                S T;
+                if constexpr (SL == 1) {
+                    const bool on0 = t >= tlo[s] && t < thi[s], on1 = t + 1 >= tlo[s] && t + 1 < thi[s];
+                    T = cadd(weigh(P[s][0], on0, false), weigh(P[s][1], on1, true));     // t is even: + then -
+                } else if constexpr (SL == 2) {
+                    const S mine = sub ? P[s][1] : P[s][0], give = sub ? P[s][0] : P[s][1];
+                    const S got = shfl_xor_s(0xffffffffu, give, 1);
+                    const uint32_t tt = t + sub;
+                    T = weigh(cmul(mine, got), tt >= tlo[s] && tt < thi[s], sub & 1);
+                } else {
+                    const bool hi = sub & 2;
+                    const S keep0 = hi ? P[s][2] : P[s][0], keep1 = hi ? P[s][3] : P[s][1];
+                    const S give0 = hi ? P[s][0] : P[s][2], give1 = hi ? P[s][1] : P[s][3];
+                    const S q0 = cmul(keep0, shfl_xor_s(0xffffffffu, give0, 2));
+                    const S q1 = cmul(keep1, shfl_xor_s(0xffffffffu, give1, 2));
+                    const bool odd = sub & 1;
+                    const S mine = odd ? q1 : q0, give = odd ? q0 : q1;
+                    const uint32_t tt = t + sub;
+                    T = weigh(cmul(mine, shfl_xor_s(0xffffffffu, give, 1)), tt >= tlo[s] && tt < thi[s], odd);
+                }
+                blk[s] = cadd(blk[s], T);
+            }
+            if (++inblk == PERM_BLOCK_GROUPS) {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) { acc.add(blk[s]); blk[s] = Traits<S>::zero(); }
+                inblk = 0;
             }
         }
+#pragma unroll
+        for (int s = 0; s < NS; ++s) acc.add(blk[s]);
     }
     if constexpr (std::is_same<S, unsigned long long>::value) {
         unsigned long long v = acc.s;
@@ -161,59 +277,83 @@ perm_kernel(const S* __restrict__ Mg, int n, int ryser, uint64_t k0, uint64_t k1
     }
 }
 
-static int pick_logL(uint64_t total, uint64_t nthreads) {
+constexpr int PERM_MAX_GRID = 4096;
+constexpr int PERM_MAX_N = 64;
+
+// segment length 2^logL: long enough to amortise seeding (n / 6 steps' worth), short enough to fill the grid
+static int pick_logL(uint64_t total, uint64_t nstreams) {
     int logL = 6;
-    while (logL < 20 && (total >> (logL + 1)) >= nthreads * 64) ++logL;
+    while (logL < 20 && (total >> (logL + 1)) >= nstreams * 32) ++logL;   // >= 32 segments per stream slot: <= 3 % tail
     return logL;
 }
 
-template <int NP, typename S>
+template <int CPL, int SL, int NS, int MINB, typename S>
 static int launch_perm(const S* dM, int n, int method, uint64_t k0, uint64_t k1, double* partials,
                        unsigned long long* iout, int* grid_out, cudaStream_t st) {
     int dev = 0, sms = 0, occ = 1;
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
+    constexpr int NP = CPL * SL;
     const size_t shm = sizeof(S) * (size_t)n * NP;
-    WB_CUDA(cudaFuncSetAttribute(perm_kernel<NP, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, perm_kernel<NP, S>, PERM_THREADS, shm));
+    WB_CUDA(cudaFuncSetAttribute(perm_kernel<CPL, SL, NS, MINB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, perm_kernel<CPL, SL, NS, MINB, S>, PERM_THREADS, shm));
     if (occ < 1) occ = 1;
     const uint64_t total = k1 - k0;
+    const uint64_t spb = (PERM_THREADS / SL) * NS;                // streams per block
     uint64_t maxgrid = (uint64_t)sms * occ;
-    uint64_t want = (total + (uint64_t)PERM_THREADS * 64 - 1) / ((uint64_t)PERM_THREADS * 64);
+    if (maxgrid > PERM_MAX_GRID) maxgrid = PERM_MAX_GRID;
+    uint64_t want = (total + spb * 64 - 1) / (spb * 64);
     int grid = (int)(want < maxgrid ? (want ? want : 1) : maxgrid);
-    const int logL = pick_logL(total, (uint64_t)grid * PERM_THREADS);
-    perm_kernel<NP, S><<<grid, PERM_THREADS, shm, st>>>(dM, n, method, k0, k1, logL, partials, iout);
+    int logL = pick_logL(total, (uint64_t)grid * spb);
+    const int bits = method ? n : n - 1;          // the step index has `bits` bits: rows ctz(t) stay below n
+    if (logL > bits) logL = bits;
+    if (logL < 1) logL = 1;
+    perm_kernel<CPL, SL, NS, MINB, S><<<grid, PERM_THREADS, shm, st>>>(dM, n, method, k0, k1, logL, partials, iout);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
 }
 
+// Tile shape per matrix size (measured on B200, profiles/r01_perm_shapes.txt): one lane per stream with all n
+// column sums in registers is fastest up to n = 40 (6.7e10 steps/s at n = 32, 5.5e10 at n = 40); beyond that the
+// sums no longer fit one thread and four lanes share two streams.  WB200_PERM_SL / WB200_PERM_NS override.
+static int env_int(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
 template <typename S>
 static int dispatch_perm(const S* dM, int n, int method, uint64_t k0, uint64_t k1, double* partials,
                          unsigned long long* iout, int* grid, cudaStream_t st) {
-    const int np = (n + 3) / 4;
-    switch (np) {
-        case 1: return launch_perm<4, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 2: return launch_perm<8, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 3: return launch_perm<12, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 4: return launch_perm<16, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 5: return launch_perm<20, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 6: return launch_perm<24, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 7: return launch_perm<28, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 8: return launch_perm<32, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 9: return launch_perm<36, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-        case 10: return launch_perm<40, S>(dM, n, method, k0, k1, partials, iout, grid, st);
-    }
-    set_error("perm: n = %d exceeds the register-resident kernel limit of 40", n);
+    static const int f_sl = env_int("WB200_PERM_SL"), f_ns = env_int("WB200_PERM_NS");
+    int sl = n <= 40 ? 1 : 4, ns = n <= 40 ? 1 : 2;
+    if (f_sl == 2 && n > 8 && n <= 32) { sl = 2; ns = 2; }
+    if (f_sl == 4 && n > 8) { sl = 4; ns = 2; }
+    if ((f_ns == 1 || f_ns == 2) && sl > 1) ns = f_ns;
+    const int cpl = (n + sl - 1) / sl;
+#define WB_PERM_CASE(C, L, N) \
+    if (sl == L && ns == N && cpl <= C) return launch_perm<C, L, N, PERM_MIN_CTAS, S>(dM, n, method, k0, k1, partials, iout, grid, st);
+    WB_PERM_CASE(4, 1, 1) WB_PERM_CASE(8, 1, 1) WB_PERM_CASE(12, 1, 1) WB_PERM_CASE(16, 1, 1) WB_PERM_CASE(20, 1, 1)
+    WB_PERM_CASE(24, 1, 1) WB_PERM_CASE(28, 1, 1) WB_PERM_CASE(30, 1, 1) WB_PERM_CASE(32, 1, 1) WB_PERM_CASE(34, 1, 1)
+    WB_PERM_CASE(36, 1, 1) WB_PERM_CASE(38, 1, 1) WB_PERM_CASE(40, 1, 1)
+    WB_PERM_CASE(8, 2, 1) WB_PERM_CASE(16, 2, 1) WB_PERM_CASE(8, 2, 2) WB_PERM_CASE(12, 2, 2) WB_PERM_CASE(16, 2, 2)
+    WB_PERM_CASE(8, 4, 1) WB_PERM_CASE(12, 4, 1) WB_PERM_CASE(16, 4, 1)
+    WB_PERM_CASE(4, 4, 2) WB_PERM_CASE(8, 4, 2) WB_PERM_CASE(10, 4, 2) WB_PERM_CASE(11, 4, 2) WB_PERM_CASE(12, 4, 2)
+    WB_PERM_CASE(14, 4, 2) WB_PERM_CASE(16, 4, 2)
+#undef WB_PERM_CASE
+    set_error("perm: no kernel for n = %d with SL = %d, NS = %d (limit n <= %d)", n, sl, ns, PERM_MAX_N);
     return WB200_ENOSUP;
 }
 
-constexpr int PERM_MAX_GRID = 4096;
-
-static int check_perm_args(int n, int method, uint64_t k0, uint64_t k1) {
-    if (n < 1 || n > 40) { set_error("perm: n = %d outside [1, 40]", n); return n > 40 ? WB200_ENOSUP : WB200_EINVAL; }
+int check_perm_args(int n, int method, uint64_t k0, uint64_t k1) {
+    if (n < 1 || n > PERM_MAX_N) {
+        set_error("perm: n = %d outside [1, %d]", n, PERM_MAX_N);
+        return n > PERM_MAX_N ? WB200_ENOSUP : WB200_EINVAL;
+    }
     if (method != 0 && method != 1) { set_error("perm: method must be 0 (bbfg) or 1 (ryser)"); return WB200_EINVAL; }
-    const uint64_t steps = 1ull << (method ? n : n - 1);
+    const int bits = method ? n : n - 1;
+    if (bits > 62) { set_error("perm: 2^%d steps exceed the 64-bit step index", bits); return WB200_ENOSUP; }
+    const uint64_t steps = 1ull << bits;
     if (k0 > k1 || k1 > steps) { set_error("perm: bad step range"); return WB200_EINVAL; }
     return WB200_OK;
 }
