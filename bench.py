@@ -329,6 +329,8 @@ def main():
         wsb = lib.wb200_perm_workspace_bytes(n)
         launches_per_step = 2      # perm_kernel, final_reduce
     elif kind == "tor":
+        dA = torch.from_numpy(np.ascontiguousarray(X, dtype=np.complex128).view(np.float64).reshape(-1)).to(dev)
+        wsb = lib.wb200_tor_workspace_bytes(n // 2)
         launches_per_step = 3      # tor_prep, tor_kernel, final_reduce
     else:
         launches_per_step = 4      # pat_prep, scan, pat_main, pat_final
@@ -347,12 +349,8 @@ def main():
             rc = lib.wb200_perm_dev(dA.data_ptr(), n, 0, lo, hi, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
                                     stream.cuda_stream)
         elif kind == "tor":
-            o2 = np.zeros(2)
-            ms = ctypes.c_double(0)
-            Oc, pO = _lib.as_c128(X)
-            rc = lib.wb200_tor_host(local, pO, n // 2, lo, hi, _lib.dptr(o2), ctypes.byref(ms))
-            inner_ms.append(ms.value)
-            out[:2] = torch.from_numpy(o2).to(dev)
+            rc = lib.wb200_tor_dev(dA.data_ptr(), n // 2, lo, hi, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                                   stream.cuda_stream)
         else:
             _, ms = _engine.lhaf_patterns_local(A, gamma, rpt[lo:hi], True, dev, want_ms=True)
             inner_ms.append(ms)

@@ -86,7 +86,7 @@ int wb200_lhaf_batch_host(int device, const double* Ax, const double* Dx, int n,
  * Replaces perm_bbfg (thewalrus/_permanent.py:130-168; method 0, steps k in [0, 2^(n-1)), final scale
  * 2^(1-n)) and perm_ryser (:86-127; method 1, steps k in [0, 2^n), no scale).  Step k evaluates the
  * Gray code g(k) = k ^ (k >> 1) with sign (-1)^k, as the reference's loop does.  M: n x n complex,
- * 2 <= n <= 40. */
+ * 1 <= n <= 64 (one thread holds all column sums up to n = 40; four lanes share them above). */
 int wb200_perm_dev(const double* dM, int n, int method, uint64_t k0, uint64_t k1, double* d_out4,
                    void* d_workspace, size_t workspace_bytes, void* stream);
 size_t wb200_perm_workspace_bytes(int n);
@@ -107,6 +107,10 @@ int wb200_perm_int64_host(int device, const int64_t* M, int n, int method, uint6
  * 2^P "prefixes" (choices for the first P modes); this call evaluates prefixes [p0, p1).
  * wb200_tor_num_prefixes gives 2^P for N.  out2 = {hi, lo} (the sum is real). */
 int wb200_tor_num_prefixes(int n_modes, uint64_t* count);
+size_t wb200_tor_workspace_bytes(int n_modes);
+/* device pointers, no synchronisation; d_out4 = {hi, lo, 0, 0} */
+int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                  void* d_workspace, size_t workspace_bytes, void* stream);
 int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
                    double* kernel_ms);
 

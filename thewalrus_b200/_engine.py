@@ -193,13 +193,21 @@ def lhaf_general_range(Ax, Dx, oddV, oddloop, edge_reps, glynn, j0, j1, device=N
 
 def tor_range(O, p0, p1, device=None):
     """Partial torontonian sum over prefixes [p0, p1) -> (hi, lo)."""
+    torch = _torch()
+    dev = require_cuda(device)
     lib = _lib.load()
-    idx = _dev_index(device)
-    O, pO = _lib.as_c128(O)
-    out = np.zeros(2)
-    rc = lib.wb200_tor_host(idx, pO, O.shape[0] // 2, p0, p1, _lib.dptr(out), None)
-    _lib.check(rc, "wb200_tor_host")
-    return out
+    N = O.shape[0] // 2
+    nbytes = lib.wb200_tor_workspace_bytes(N)
+    if nbytes == 0:
+        raise NotImplementedError(f"torontonian kernel supports 2..32 modes, got {N}")
+    with torch.cuda.device(dev):
+        dO = _to_dev(O, dev)
+        ws = _workspace(dev, nbytes)
+        out = torch.empty(4, dtype=torch.float64, device=dev)
+        rc = lib.wb200_tor_dev(dO.data_ptr(), N, p0, p1, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
+                               torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "wb200_tor_dev")
+        return out.cpu().numpy()[:2]
 
 
 def tor_num_prefixes(n_modes):

@@ -235,42 +235,71 @@ extern "C" int wb200_tor_num_prefixes(int n_modes, uint64_t* count) {
     return WB200_OK;
 }
 
+// workspace: interleaved I - O (2N x 2N complex) followed by 4 doubles per CTA
+static size_t tor_ws_partials_offset(int N) {
+    return (sizeof(double2) * (size_t)(2 * N) * (2 * N) + 255) & ~(size_t)255;
+}
+constexpr int TOR_MAX_GRID = 1024;
+
+extern "C" size_t wb200_tor_workspace_bytes(int n_modes) {
+    if (n_modes < 2 || n_modes > TOR_MAX_MODES) return 0;
+    return tor_ws_partials_offset(n_modes) + sizeof(double) * 4 * TOR_MAX_GRID;
+}
+
+extern "C" int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!dO || !d_out4 || !d_workspace) { set_error("tor: null pointer"); return WB200_EINVAL; }
+    uint64_t total = 0;
+    int rc = wb200_tor_num_prefixes(n_modes, &total);
+    if (rc) return rc;
+    if (p0 > p1 || p1 > total) { set_error("tor: bad prefix range"); return WB200_EINVAL; }
+    if (workspace_bytes < wb200_tor_workspace_bytes(n_modes)) { set_error("tor: workspace too small"); return WB200_EINVAL; }
+    const int N = n_modes, n2 = 2 * N;
+    cudaStream_t st = (cudaStream_t)stream;
+    TorParams p;
+    tor_shape(N, &p.P, &p.g, &p.DC);
+    p.N = N; p.p0 = p0; p.p1 = p1;
+    double2* dB = reinterpret_cast<double2*>(d_workspace);
+    double* dpart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_workspace) + tor_ws_partials_offset(N));
+    p.B = dB;
+    int dev = 0, sms = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (device_sm_count(dev, &sms)) return WB200_ECUDA;
+    const int dg = 2 * (p.DC + p.g);
+    const size_t shm = sizeof(double2) * ((size_t)n2 * n2 + 2 * (size_t)dg * dg + 2 * 2304) + sizeof(double) * 6 * 256;
+    WB_CUDA(cudaFuncSetAttribute(tor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
+    int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
+    if (grid > TOR_MAX_GRID) grid = TOR_MAX_GRID;
+    tor_prep_kernel<<<8, 256, 0, st>>>(reinterpret_cast<const double2*>(dO), N, dB);
+    tor_kernel<<<grid, TOR_THREADS, shm, st>>>(p, dpart);
+    final_reduce_kernel<<<1, 32, 0, st>>>(dpart, grid, d_out4);
+    WB_CUDA(cudaGetLastError());
+    return WB200_OK;
+}
+
 extern "C" int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
                               double* kernel_ms) {
     if (!O || !out2) { set_error("tor: null pointer"); return WB200_EINVAL; }
     uint64_t total = 0;
     int rc = wb200_tor_num_prefixes(n_modes, &total);
     if (rc) return rc;
-    if (p0 > p1 || p1 > total) { set_error("tor: bad prefix range"); return WB200_EINVAL; }
-    const int N = n_modes, n2 = 2 * N;
-    TorParams p;
-    tor_shape(N, &p.P, &p.g, &p.DC);
-    p.N = N; p.p0 = p0; p.p1 = p1;
+    const int n2 = 2 * n_modes;
     WB_CUDA(cudaSetDevice(device));
-    DevBufT dO, dB, dpart, dout;
+    DevBufT dO, dws, dout;
+    const size_t wsb = wb200_tor_workspace_bytes(n_modes);
     WB_CUDA(cudaMalloc(&dO.p, sizeof(double) * 2 * n2 * n2));
-    WB_CUDA(cudaMalloc(&dB.p, sizeof(double) * 2 * n2 * n2));
-    WB_CUDA(cudaMemcpy(dO.p, O, sizeof(double) * 2 * n2 * n2, cudaMemcpyHostToDevice));
-    p.B = (const double2*)dB.p;
-    int sms = 0;
-    if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    const int dg = 2 * (p.DC + p.g);
-    const size_t shm = sizeof(double2) * ((size_t)n2 * n2 + 2 * (size_t)dg * dg + 2 * 2304) + sizeof(double) * 6 * 256;
-    WB_CUDA(cudaFuncSetAttribute(tor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
-    int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
-    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * grid));
+    WB_CUDA(cudaMalloc(&dws.p, wsb));
     WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4));
+    WB_CUDA(cudaMemcpy(dO.p, O, sizeof(double) * 2 * n2 * n2, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1;
     WB_CUDA(cudaEventCreate(&e0));
     WB_CUDA(cudaEventCreate(&e1));
     WB_CUDA(cudaEventRecord(e0, 0));
-    tor_prep_kernel<<<8, 256>>>((const double2*)dO.p, N, (double2*)dB.p);
-    tor_kernel<<<grid, TOR_THREADS, shm>>>(p, (double*)dpart.p);
-    final_reduce_kernel<<<1, 32>>>((const double*)dpart.p, grid, (double*)dout.p);
+    rc = wb200_tor_dev((const double*)dO.p, n_modes, p0, p1, (double*)dout.p, dws.p, wsb, nullptr);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     WB_CUDA(cudaEventRecord(e1, 0));
     WB_CUDA(cudaEventSynchronize(e1));
-    WB_CUDA(cudaGetLastError());
     float ms = 0;
     WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0);
