@@ -82,6 +82,14 @@ int wb200_lhaf_batch_host(int device, const double* Ax, const double* Dx, int n,
                           int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* out,
                           int length, double* kernel_ms);
 
+/* Same sweep for n_D loop vectors at once: replaces _calc_loop_hafnian_batch_gamma_even / _odd
+ * (thewalrus/loop_hafnian_batch_gamma.py:52-220).  Dx: n_D x n (row k = the edge-ordered loop vector of
+ * displacement k); out: n_D x length x {re_hi, re_lo, im_hi, im_lo}, unscaled as above.  The reduced matrix and
+ * its power traces are computed once per subset and shared by all n_D vectors. */
+int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, int n, int n_D,
+                                const int32_t* edge_reps, int odd_variant, int cutoff_extra, int glynn,
+                                uint64_t j0, uint64_t j1, double* out, int length, double* kernel_ms);
+
 /* ---- permanent --------------------------------------------------------------------------------------
  * Replaces perm_bbfg (thewalrus/_permanent.py:130-168; method 0, steps k in [0, 2^(n-1)), final scale
  * 2^(1-n)) and perm_ryser (:86-127; method 1, steps k in [0, 2^n), no scale).  Step k evaluates the

@@ -385,6 +385,15 @@ def loop_hafnian_batch(A, D, fixed_reps, N_cutoff, glynn=True):
     return _batch_core(Ax, Dx, fixed_m_reps, (N_cutoff - 1) // 2, 1 - (N_cutoff % 2), glynn, True)
 
 
+def loop_hafnian_batch_gamma(A, D, fixed_reps, N_cutoff, glynn=True):
+    """thewalrus/loop_hafnian_batch_gamma.py:222-269.  The reference's two sweeps (:52-125, :129-220) differ from
+    loop_hafnian_batch only by the loop over the rows of D (XD_S, D_S, oddloop[k], oddloop0[k] per row; AX_S,
+    oddVX_S shared), so row k is the batch sweep with loop vector D[k]."""
+    n = A.shape[0]
+    assert A.shape[1] == n and D.shape[1] == n and len(fixed_reps) == n - 1
+    return np.array([loop_hafnian_batch(A, D[k], fixed_reps, N_cutoff, glynn) for k in range(D.shape[0])])
+
+
 # --------------------------------------------------------------------------------------------------
 # permanent (thewalrus/_permanent.py)
 # --------------------------------------------------------------------------------------------------
@@ -503,6 +512,138 @@ def tor(O, recursive=True):
     if O.shape[0] == 0:
         return 1.0
     return tor_recursive(O) if recursive else np.real(tor_direct(O))
+
+
+# --------------------------------------------------------------------------------------------------
+# SURVEY 8(f) "next" components: Bristolian, loop torontonian, montrealer
+# --------------------------------------------------------------------------------------------------
+
+
+def _subset_rows(j, m):
+    """Indices of the set bits of the MSB-first m-bit index j (find_kept_edges(j, ones), _hafnian.py:162-180)."""
+    return [i for i in range(m) if (j >> (m - 1 - i)) & 1]
+
+
+def brs(A, E, j0=0, j1=None):
+    """Bristolian, thewalrus/_permanent.py:198-223: sum over row subsets Y of (-1)^(m-|Y|) perm(A_Y^H A_Y + E)
+    over subset indices [j0, j1)."""
+    A = np.asarray(A, dtype=np.complex128)
+    m = A.shape[0]
+    j1 = 2**m if j1 is None else j1
+    total = 0j
+    for j in range(j0, j1):
+        rows = _subset_rows(j, m)
+        Ay = A[rows, :]
+        total += (-1) ** ((m - len(rows)) % 2) * perm_bbfg(Ay.conj().T @ Ay + E)
+    return total
+
+
+def ubrs(A):
+    """Unitary Bristolian, thewalrus/_permanent.py:226-249: the same sum without E and without the empty set."""
+    A = np.asarray(A, dtype=np.complex128)
+    n = A.shape[1]
+    return brs(A, np.zeros((n, n)), j0=1)
+
+
+def fock_threshold_prob(n, d, T):
+    """thewalrus/_permanent.py:282-321."""
+    n, d = np.array(n), np.array(d)
+    fac = float(np.prod([math.factorial(int(x)) for x in n]))
+    in_modes = np.array([i for i, c in enumerate(n) for _ in range(int(c))], dtype=int)
+    C = np.where(d > 0)[0]
+    A = T[np.ix_(C, in_modes)]
+    E = np.eye(T.shape[1]) - T.conj().T @ T
+    if np.allclose(E, 0):
+        return ubrs(A).real / fac
+    return brs(A, E[np.ix_(in_modes, in_modes)]).real / fac
+
+
+def ltor_direct(O, gamma, j0=0, j1=None):
+    """Loop torontonian, thewalrus/_torontonian.py:369-412 (numba_ltor) over subset indices [j0, j1):
+    sum_S (-1)^(N-|S|) exp(gamma_S (I - O_S)^-1 gamma_S^* / 2) / sqrt(Re det(I - O_S))."""
+    O = np.asarray(O, dtype=np.complex128)
+    gamma = np.asarray(gamma, dtype=np.complex128)
+    N = O.shape[0] // 2
+    j1 = 2**N if j1 is None else j1
+    total = 0j
+    for j in range(j0, j1):
+        modes = _subset_rows(j, N)
+        k = len(modes)
+        rows = modes + [i + N for i in modes]
+        sub = np.eye(2 * k) - O[np.ix_(rows, rows)]
+        g = gamma[rows]
+        top = np.exp(0.5 * g @ np.linalg.solve(sub, g.conj())) if k else 1.0
+        det = np.linalg.det(sub).real if k else 1.0
+        total += (-1.0) ** ((N - k) % 2) * top / np.sqrt(det)
+    return total
+
+
+def _qmat(cov, hbar=2):
+    """thewalrus/quantum/conversions.py:70-96."""
+    N = len(cov) // 2
+    I = np.identity(N)
+    x, xp, p = cov[:N, :N] * 2 / hbar, cov[:N, N:] * 2 / hbar, cov[N:, N:] * 2 / hbar
+    aidaj = (x + p + 1j * (xp - xp.T) - 2 * I) / 4
+    aiaj = (x - p + 1j * (xp + xp.T)) / 4
+    return np.block([[aidaj, aiaj.conj()], [aiaj, aidaj.conj()]]) + np.identity(2 * N)
+
+
+def threshold_detection_prob(mu, cov, det_pattern, hbar=2, atol=1e-10, rtol=1e-10):
+    """thewalrus/_torontonian.py:77-120."""
+    mu, cov, det = np.asarray(mu, dtype=float), np.asarray(cov, dtype=float), np.asarray(det_pattern)
+    n = cov.shape[0] // 2
+    clicked = [i for i in range(n) if det[i] == 1]
+    rows = clicked + [i + n for i in clicked]
+    if np.allclose(mu, 0, atol=atol, rtol=rtol):
+        Q = _qmat(cov, hbar)
+        O = np.eye(2 * n) - np.linalg.inv(Q)
+        Os = O[np.ix_(rows, rows)]
+        t = tor_direct(Os) if len(clicked) else 1.0
+        return (t / np.sqrt(np.linalg.det(Q))).real
+    alpha = np.concatenate((mu[:n] + 1j * mu[n:], mu[:n] - 1j * mu[n:])) / np.sqrt(2 * hbar)
+    sigma = _qmat(cov, hbar).conj()
+    inv_sigma = np.linalg.inv(sigma)
+    O = np.eye(2 * n) - inv_sigma
+    gamma = (inv_sigma @ alpha).conj()
+    vac = (np.exp(-0.5 * alpha.conj() @ inv_sigma @ alpha).real / np.sqrt(np.linalg.det(sigma))).real
+    lt = ltor_direct(O[np.ix_(rows, rows)], gamma[rows]) if len(clicked) else 1.0
+    return float(vac * np.real(lt))
+
+
+def montrealer(Sigma, zeta=None, j0=1, j1=None):
+    """thewalrus/_montrealer.py:37-57 (and :78-102 with zeta): over subset labels p in [j0, j1) of 2^n,
+    (-1)^(n+1) [ sum_p (-1)^(|p|+1) tr(Sigma_p^n) / (2n) + sum_p (-1)^(|p|+1) conj(zeta_p) Sigma_p^(n-1) zeta_p / 2 ].
+    dec2bin (:17-34) selects mode i when bit i of the MSB-first n-bit label is set."""
+    Sigma = np.asarray(Sigma, dtype=np.complex128)
+    n = len(Sigma) // 2
+    j1 = 2**n if j1 is None else j1
+    val, val_loops = 0j, 0j
+    for p in range(max(j0, 1), j1):
+        modes = _subset_rows(p, n)
+        pos = modes + [i + n for i in modes]
+        sub = Sigma[np.ix_(pos, pos)]
+        sign = (-1) ** (len(modes) + 1)
+        val += sign * np.trace(np.linalg.matrix_power(sub, n))
+        if zeta is not None:
+            z = np.asarray(zeta, dtype=np.complex128)[pos]
+            val_loops += sign * (z.conj() @ np.linalg.matrix_power(sub, n - 1) @ z)
+    return (-1) ** (n + 1) * (val / (2 * n) + val_loops / 2)
+
+
+def mtl(A):
+    """thewalrus/_montrealer.py:121-135: montrealer of Xmat(n) @ A."""
+    A = np.asarray(A)
+    n = len(A) // 2
+    X = np.block([[np.zeros((n, n)), np.eye(n)], [np.eye(n), np.zeros((n, n))]])
+    return montrealer(X @ A)
+
+
+def lmtl(A, zeta):
+    """thewalrus/_montrealer.py:105-118."""
+    A = np.asarray(A)
+    n = len(A) // 2
+    X = np.block([[np.zeros((n, n)), np.eye(n)], [np.eye(n), np.zeros((n, n))]])
+    return montrealer(X @ A, zeta)
 
 
 # --------------------------------------------------------------------------------------------------

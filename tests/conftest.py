@@ -20,6 +20,13 @@ def golden():
         return json.load(fh)
 
 
+@pytest.fixture(scope="session")
+def golden_next():
+    """Reference outputs for the SURVEY 8(f) components (tests/golden/make_golden_next.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_outputs_next.json")) as fh:
+        return json.load(fh)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Make sure the CUDA library and the oracle are built (nvcc cross-compiles without a GPU)."""

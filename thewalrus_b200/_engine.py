@@ -232,6 +232,23 @@ def lhaf_batch_range(Ax, Dx, edge_reps, odd_variant, cutoff_extra, glynn, j0, j1
     return out
 
 
+def lhaf_batch_gamma_range(Ax, Dx, edge_reps, odd_variant, cutoff_extra, glynn, j0, j1, length, device=None):
+    """Partial loop_hafnian_batch_gamma sweep over subset indices [j0, j1) for the n_D rows of ``Dx`` ->
+    4 * n_D * length doubles (no final scale)."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    Ax, pA = _lib.as_c128(Ax)
+    Dx, pD = _lib.as_c128(Dx)
+    n_D = Dx.shape[0]
+    er = np.ascontiguousarray(edge_reps, dtype=np.int32)
+    out = np.zeros(4 * length * n_D)
+    rc = lib.wb200_lhaf_batch_gamma_host(idx, pA, pD, Ax.shape[0], n_D, er.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                         int(odd_variant), int(cutoff_extra), 1 if glynn else 0, j0, j1,
+                                         _lib.dptr(out), int(length), None)
+    _lib.check(rc, "wb200_lhaf_batch_gamma_host")
+    return out
+
+
 def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False):
     """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU."""
     lib = _lib.load()

@@ -110,13 +110,11 @@ __device__ inline int decode_subset(const WarpWs& w, int E, int glynn, unsigned 
     return k;
 }
 
-// Reduced matrix, vectors, power traces ptr[1..T], loop terms lv[t] = XD M^(t-1) D, ov[t] = oddVX M^(t-1) D,
-// ov0[t] likewise for a second odd row (t = 1..T).  A: nv x nv (row stride lda); D: nv or null; odd rows are
-// rows of A (index or -1).
-__device__ inline void subset_traces(const WarpWs& w, const double2* __restrict__ A, int lda, const double2* __restrict__ D,
-                                     int odd_row, int odd0_row, int k, int T, int lane) {
+// Reduced matrix M = AX_S, odd-row vectors and power traces ptr[1..T] of subset (rows, delta) — everything that
+// does not depend on the loop vector D.  A: nv x nv (row stride lda); odd rows are rows of A (index or -1).
+__device__ inline void subset_setup(const WarpWs& w, const double2* __restrict__ A, int lda, int odd_row, int odd0_row,
+                                    int k, int T, int lane) {
     const int s = 2 * k;
-    const bool loops = D != nullptr;
     for (int idx = lane; idx < s * s; idx += 32) {
         const int r = idx / s, c = idx - r * s;
         const int sc = c < k ? c + k : c - k;
@@ -129,11 +127,6 @@ __device__ inline void subset_traces(const WarpWs& w, const double2* __restrict_
     for (int c = lane; c < s; c += 32) {
         const int sc = c < k ? c + k : c - k;
         const double d = w.delta[c];
-        if (loops) {
-            const double2 dv = __ldg(D + w.rows[sc]);
-            w.vXD[c] = make_double2(dv.x * d, dv.y * d);
-            w.vD[c] = __ldg(D + w.rows[c]);
-        }
         if (odd_row >= 0) {
             const double2 ov = __ldg(A + (size_t)odd_row * lda + w.rows[sc]);
             w.vOV[c] = make_double2(ov.x * d, ov.y * d);
@@ -145,75 +138,96 @@ __device__ inline void subset_traces(const WarpWs& w, const double2* __restrict_
     }
     __syncwarp();
     // ---- power traces
-    {
-        double2 t1 = make_double2(0.0, 0.0);
-        for (int r = lane; r < s; r += 32) { t1.x += w.M[r * s + r].x; t1.y += w.M[r * s + r].y; }
-        t1 = warp_sum2(t1);
-        if (lane == 0) { w.ptr[0] = make_double2((double)s, 0.0); if (T >= 1) w.ptr[1] = t1; }
-        double2* Pc = w.P;
-        double2* Pnx = w.Pn;
-        for (int t = 1; 2 * t <= T; ++t) {
-            double2 e = make_double2(0.0, 0.0);
-            for (int idx = lane; idx < s * s; idx += 32) {
-                const int r = idx / s, c = idx - r * s;
-                cfma(e, Pc[idx], Pc[c * s + r]);
-            }
-            e = warp_sum2(e);
-            if (lane == 0) w.ptr[2 * t] = e;
-            if (2 * t + 1 > T) break;
-            for (int idx = lane; idx < s * s; idx += 32) {
-                const int r = idx / s, c = idx - r * s;
-                double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
-                int q = 0;
-                for (; q + 1 < s; q += 2) {
-                    cfma(a0, Pc[r * s + q], w.M[q * s + c]);
-                    cfma(a1, Pc[r * s + q + 1], w.M[(q + 1) * s + c]);
-                }
-                if (q < s) cfma(a0, Pc[r * s + q], w.M[q * s + c]);
-                Pnx[idx] = make_double2(a0.x + a1.x, a0.y + a1.y);
-            }
-            __syncwarp();
-            double2 o = make_double2(0.0, 0.0);
-            for (int idx = lane; idx < s * s; idx += 32) {
-                const int r = idx / s, c = idx - r * s;
-                cfma(o, Pnx[idx], Pc[c * s + r]);
-            }
-            o = warp_sum2(o);
-            if (lane == 0) w.ptr[2 * t + 1] = o;
-            double2* tmp = Pc; Pc = Pnx; Pnx = tmp;
-            __syncwarp();
+    double2 t1 = make_double2(0.0, 0.0);
+    for (int r = lane; r < s; r += 32) { t1.x += w.M[r * s + r].x; t1.y += w.M[r * s + r].y; }
+    t1 = warp_sum2(t1);
+    if (lane == 0) { w.ptr[0] = make_double2((double)s, 0.0); if (T >= 1) w.ptr[1] = t1; }
+    double2* Pc = w.P;
+    double2* Pnx = w.Pn;
+    for (int t = 1; 2 * t <= T; ++t) {
+        double2 e = make_double2(0.0, 0.0);
+        for (int idx = lane; idx < s * s; idx += 32) {
+            const int r = idx / s, c = idx - r * s;
+            cfma(e, Pc[idx], Pc[c * s + r]);
         }
-    }
-    // ---- loop terms
-    if (loops) {
-        double2* v = w.vD;
-        double2* v2 = w.vD2;
-        for (int t = 1; t <= T; ++t) {
-            double2 l = make_double2(0.0, 0.0), o = make_double2(0.0, 0.0), o0 = make_double2(0.0, 0.0);
-            for (int c = lane; c < s; c += 32) {
-                const double2 dv = v[c];
-                cfma(l, w.vXD[c], dv);
-                if (odd_row >= 0) cfma(o, w.vOV[c], dv);
-                if (odd0_row >= 0) cfma(o0, w.vOV0[c], dv);
+        e = warp_sum2(e);
+        if (lane == 0) w.ptr[2 * t] = e;
+        if (2 * t + 1 > T) break;
+        for (int idx = lane; idx < s * s; idx += 32) {
+            const int r = idx / s, c = idx - r * s;
+            double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
+            int q = 0;
+            for (; q + 1 < s; q += 2) {
+                cfma(a0, Pc[r * s + q], w.M[q * s + c]);
+                cfma(a1, Pc[r * s + q + 1], w.M[(q + 1) * s + c]);
             }
-            l = warp_sum2(l);
-            if (odd_row >= 0) o = warp_sum2(o);
-            if (odd0_row >= 0) o0 = warp_sum2(o0);
-            if (lane == 0) { w.lv[t] = l; w.ov[t] = o; w.ov0[t] = o0; }
-            if (t < T) {
-                for (int r = lane; r < s; r += 32) {
-                    double2 a = make_double2(0.0, 0.0);
-                    for (int q = 0; q < s; ++q) cfma(a, w.M[r * s + q], v[q]);
-                    v2[r] = a;
-                }
-                __syncwarp();
-                double2* tmp = v; v = v2; v2 = tmp;
-            }
+            if (q < s) cfma(a0, Pc[r * s + q], w.M[q * s + c]);
+            Pnx[idx] = make_double2(a0.x + a1.x, a0.y + a1.y);
         }
-    } else {
-        for (int t = lane + 1; t <= T; t += 32) { w.lv[t] = make_double2(0.0, 0.0); w.ov[t] = w.lv[t]; w.ov0[t] = w.lv[t]; }
+        __syncwarp();
+        double2 o = make_double2(0.0, 0.0);
+        for (int idx = lane; idx < s * s; idx += 32) {
+            const int r = idx / s, c = idx - r * s;
+            cfma(o, Pnx[idx], Pc[c * s + r]);
+        }
+        o = warp_sum2(o);
+        if (lane == 0) w.ptr[2 * t + 1] = o;
+        double2* tmp = Pc; Pc = Pnx; Pnx = tmp;
+        __syncwarp();
     }
     __syncwarp();
+}
+
+// Loop terms of one loop vector D (nv complex, or null): lv[t] = XD M^(t-1) D, ov[t] = oddVX M^(t-1) D and
+// ov0[t] for the second odd row, t = 1..T, from one mat-vec chain on the M left by subset_setup.
+__device__ inline void subset_loops(const WarpWs& w, const double2* __restrict__ D, bool has_odd, bool has_odd0, int k,
+                                    int T, int lane) {
+    const int s = 2 * k;
+    if (D == nullptr) {
+        for (int t = lane + 1; t <= T; t += 32) { w.lv[t] = make_double2(0.0, 0.0); w.ov[t] = w.lv[t]; w.ov0[t] = w.lv[t]; }
+        __syncwarp();
+        return;
+    }
+    for (int c = lane; c < s; c += 32) {
+        const int sc = c < k ? c + k : c - k;
+        const double d = w.delta[c];
+        const double2 dv = __ldg(D + w.rows[sc]);
+        w.vXD[c] = make_double2(dv.x * d, dv.y * d);
+        w.vD[c] = __ldg(D + w.rows[c]);
+    }
+    __syncwarp();
+    double2* v = w.vD;
+    double2* v2 = w.vD2;
+    for (int t = 1; t <= T; ++t) {
+        double2 l = make_double2(0.0, 0.0), o = make_double2(0.0, 0.0), o0 = make_double2(0.0, 0.0);
+        for (int c = lane; c < s; c += 32) {
+            const double2 dv = v[c];
+            cfma(l, w.vXD[c], dv);
+            if (has_odd) cfma(o, w.vOV[c], dv);
+            if (has_odd0) cfma(o0, w.vOV0[c], dv);
+        }
+        l = warp_sum2(l);
+        if (has_odd) o = warp_sum2(o);
+        if (has_odd0) o0 = warp_sum2(o0);
+        if (lane == 0) { w.lv[t] = l; w.ov[t] = o; w.ov0[t] = o0; }
+        if (t < T) {
+            for (int r = lane; r < s; r += 32) {
+                double2 a = make_double2(0.0, 0.0);
+                for (int q = 0; q < s; ++q) cfma(a, w.M[r * s + q], v[q]);
+                v2[r] = a;
+            }
+            __syncwarp();
+            double2* tmp = v; v = v2; v2 = tmp;
+        }
+    }
+    // leave the chain buffers where subset_loops expects them next time (vD is rewritten from D on entry)
+    __syncwarp();
+}
+
+__device__ inline void subset_traces(const WarpWs& w, const double2* __restrict__ A, int lda, const double2* __restrict__ D,
+                                     int odd_row, int odd0_row, int k, int T, int lane) {
+    subset_setup(w, A, lda, odd_row, odd0_row, k, T, lane);
+    subset_loops(w, D, odd_row >= 0, odd0_row >= 0, k, T, lane);
 }
 
 // fac[i] = i * a_i for the even series (f / f_loop): a_i = p_i/(2i) + l_i/2, i = 1..order
@@ -452,33 +466,33 @@ __global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigne
 // =================================================================================================
 struct BatchParams {
     const double2* A;   // n x n, edge ordered (vertex e paired with e + E)
-    const double2* D;   // n
-    int n, E, glynn, odd_variant, N_fixed, N_max, length, smax, T, O;
+    const double2* D;   // n_D x n loop vectors (loop_hafnian_batch: n_D = 1; ..._gamma: one row per displacement)
+    int n, n_D, E, glynn, odd_variant, N_fixed, N_max, length, smax, T, O;
     int reps[BW_EMAX];
     unsigned long long j0, j1;
-    double* partials;   // (gridDim.x * BW_WARPS) * length * 4
+    double* partials;   // (gridDim.x * warps per CTA) x n_D x length x 4, zero-initialised
 };
 
+// One warp per subset.  The reduced matrix and its power traces are built once per subset and shared by all
+// n_D loop vectors (the reference recomputes only XD_S, D_S per vector too: loop_hafnian_batch_gamma.py:107-111);
+// the warp's accumulators live in its own slice of global memory (L2 resident), double-double, no atomics.
 __global__ void __launch_bounds__(32 * BW_WARPS) batch_kernel(BatchParams p) {
     extern __shared__ __align__(16) unsigned char smem_bw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t wsb = warp_ws_bytes(p.smax, p.T, p.O) + sizeof(double) * 4 * (size_t)p.length;
-    unsigned char* base = smem_bw + warp * wsb;
-    WarpWs w = carve(base, p.smax, p.T, p.O);
-    double* acc = reinterpret_cast<double*>(base + warp_ws_bytes(p.smax, p.T, p.O));  // [length][4]
+    const size_t wsb = warp_ws_bytes(p.smax, p.T, p.O);
+    WarpWs w = carve(smem_bw + warp * wsb, p.smax, p.T, p.O);
     __shared__ int s_k[BW_WARPS], s_esum[BW_WARPS], s_d0[BW_WARPS];
     __shared__ double s_wt[BW_WARPS];
     const int E = p.E;
-    for (int i = lane; i < 4 * p.length; i += 32) acc[i] = 0.0;
     if (lane < BW_EMAX) {
         w.eu[lane] = (unsigned char)lane; w.ev[lane] = (unsigned char)(lane + E);
         w.er[lane] = (unsigned short)(lane < E ? p.reps[lane] : 0);
     }
     __syncwarp();
     const int T = p.N_max / 2;
-    const double2 oddloop = __ldg(p.D + 0), oddloop0 = p.odd_variant ? __ldg(p.D + 1) : make_double2(0.0, 0.0);
     const int wpc = blockDim.x >> 5;
     const unsigned long long gw = (unsigned long long)blockIdx.x * wpc + warp, nw = (unsigned long long)gridDim.x * wpc;
+    double* acc_all = p.partials + gw * 4 * (size_t)p.length * p.n_D;
     for (unsigned long long j = p.j0 + gw; j < p.j1; j += nw) {
         if (lane == 0) {
             int es, d0;
@@ -491,39 +505,43 @@ __global__ void __launch_bounds__(32 * BW_WARPS) batch_kernel(BatchParams p) {
         const double wt = s_wt[warp];
         const int kept0 = w.kept[0];
         const bool extra = p.odd_variant && kept0 == 0 && w.kept[1] == 0;
-        subset_traces(w, p.A, p.n, p.D, 0, extra ? 1 : -1, k, T, lane);
-        fac_even(w, p.N_max / 2, lane);
-        exp_series(w, w.cs0, p.N_max / 2, lane);           // f_loop
-        fac_odd(w, p.N_max, oddloop, w.ov, lane);
-        exp_series(w, w.cs1, p.N_max, lane);               // f_loop_odd
-        if (extra) {                                        // loop_hafnian_batch.py:181-185
-            fac_odd(w, p.N_fixed, oddloop0, w.ov0, lane);
-            exp_series(w, w.cs2, p.N_fixed, lane);
-            if (lane == 0) {
-                const double pm = ((p.N_fixed / 2 - esum) & 1) ? -1.0 : 1.0;
-                dd a = {acc[0], acc[1]}, b = {acc[2], acc[3]};
-                dd_add(a, wt * pm * w.cs2[p.N_fixed].x);
-                dd_add(b, wt * pm * w.cs2[p.N_fixed].y);
-                acc[0] = a.hi; acc[1] = a.lo; acc[2] = b.hi; acc[3] = b.lo;
+        subset_setup(w, p.A, p.n, 0, extra ? 1 : -1, k, T, lane);
+        for (int dk = 0; dk < p.n_D; ++dk) {
+            const double2* Dk = p.D + (size_t)dk * p.n;
+            double* acc = acc_all + (size_t)dk * 4 * p.length;      // [length][4]
+            const double2 oddloop = __ldg(Dk + 0), oddloop0 = p.odd_variant ? __ldg(Dk + 1) : make_double2(0.0, 0.0);
+            subset_loops(w, Dk, true, extra, k, T, lane);
+            fac_even(w, p.N_max / 2, lane);
+            exp_series(w, w.cs0, p.N_max / 2, lane);           // f_loop
+            fac_odd(w, p.N_max, oddloop, w.ov, lane);
+            exp_series(w, w.cs1, p.N_max, lane);               // f_loop_odd
+            if (extra) {                                        // loop_hafnian_batch.py:181-185
+                fac_odd(w, p.N_fixed, oddloop0, w.ov0, lane);
+                exp_series(w, w.cs2, p.N_fixed, lane);
+                if (lane == 0) {
+                    const double pm = ((p.N_fixed / 2 - esum) & 1) ? -1.0 : 1.0;
+                    dd a = {acc[0], acc[1]}, b = {acc[2], acc[3]};
+                    dd_add(a, wt * pm * w.cs2[p.N_fixed].x);
+                    dd_add(b, wt * pm * w.cs2[p.N_fixed].y);
+                    acc[0] = a.hi; acc[1] = a.lo; acc[2] = b.hi; acc[3] = b.lo;
+                }
+                __syncwarp();
+            }
+            const int first = 2 * kept0 + (p.odd_variant ? 1 : 0);
+            for (int nd = first + lane; nd < p.length; nd += 32) {   // loop_hafnian_batch.py:105-114, 188-200
+                const int N = p.N_fixed + nd;
+                const double pm = ((N / 2 - esum) & 1) ? -1.0 : 1.0;
+                const int half = p.odd_variant ? (nd - 1) / 2 : nd / 2;
+                const double wgt = binom_d(half, kept0) * wt * pm;
+                const double2 v = (N & 1) ? w.cs1[N] : w.cs0[N / 2];
+                dd a = {acc[nd * 4 + 0], acc[nd * 4 + 1]}, b = {acc[nd * 4 + 2], acc[nd * 4 + 3]};
+                dd_add(a, wgt * v.x);
+                dd_add(b, wgt * v.y);
+                acc[nd * 4 + 0] = a.hi; acc[nd * 4 + 1] = a.lo; acc[nd * 4 + 2] = b.hi; acc[nd * 4 + 3] = b.lo;
             }
             __syncwarp();
         }
-        const int first = 2 * kept0 + (p.odd_variant ? 1 : 0);
-        for (int nd = first + lane; nd < p.length; nd += 32) {   // loop_hafnian_batch.py:105-114, 188-200
-            const int N = p.N_fixed + nd;
-            const double pm = ((N / 2 - esum) & 1) ? -1.0 : 1.0;
-            const int half = p.odd_variant ? (nd - 1) / 2 : nd / 2;
-            const double wgt = binom_d(half, kept0) * wt * pm;
-            const double2 v = (N & 1) ? w.cs1[N] : w.cs0[N / 2];
-            dd a = {acc[nd * 4 + 0], acc[nd * 4 + 1]}, b = {acc[nd * 4 + 2], acc[nd * 4 + 3]};
-            dd_add(a, wgt * v.x);
-            dd_add(b, wgt * v.y);
-            acc[nd * 4 + 0] = a.hi; acc[nd * 4 + 1] = a.lo; acc[nd * 4 + 2] = b.hi; acc[nd * 4 + 3] = b.lo;
-        }
-        __syncwarp();
     }
-    double* o = p.partials + gw * 4 * (size_t)p.length;
-    for (int i = lane; i < 4 * p.length; i += 32) o[i] = acc[i];
 }
 
 // out[nd][4] = fixed-order sum over warps
@@ -657,11 +675,12 @@ extern "C" int wb200_lhaf_batch_steps(const int32_t* edge_reps, int n_edges, uin
     return WB200_OK;
 }
 
-extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double* Dx, int n, const int32_t* edge_reps,
-                                     int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* out,
-                                     int length, double* kernel_ms) {
+extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, int n, int n_D,
+                                           const int32_t* edge_reps, int odd_variant, int cutoff_extra, int glynn,
+                                           uint64_t j0, uint64_t j1, double* out, int length, double* kernel_ms) {
     if (!Ax || !Dx || !edge_reps || !out) { set_error("lhaf_batch: null pointer"); return WB200_EINVAL; }
     if (n < 2 || (n & 1)) { set_error("lhaf_batch: n must be even and >= 2 (got %d)", n); return WB200_EINVAL; }
+    if (n_D < 1 || n_D > 65536) { set_error("lhaf_batch: number of loop vectors %d outside [1, 65536]", n_D); return WB200_EINVAL; }
     const int E = n / 2;
     if (E > BW_EMAX) { set_error("lhaf_batch: %d edges exceed the limit of %d", E, BW_EMAX); return WB200_ENOSUP; }
     if (odd_variant && (E < 2 || edge_reps[1] != 1)) { set_error("lhaf_batch: odd variant needs edge_reps[1] == 1"); return WB200_EINVAL; }
@@ -685,7 +704,7 @@ extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double*
     }
     if (length != p.length) { set_error("lhaf_batch: output length must be %d (got %d)", p.length, length); return WB200_EINVAL; }
     if (p.N_max > BW_MAX_ORDER) { set_error("lhaf_batch: photon number %d too large", p.N_max); return WB200_ENOSUP; }
-    p.n = n; p.E = E; p.glynn = glynn; p.odd_variant = odd_variant; p.j0 = j0; p.j1 = j1;
+    p.n = n; p.n_D = n_D; p.E = E; p.glynn = glynn; p.odd_variant = odd_variant; p.j0 = j0; p.j1 = j1;
     p.smax = n; p.T = p.N_max / 2; p.O = p.N_max;
     WB_CUDA(cudaSetDevice(device));
     int sms = 0;
@@ -693,10 +712,10 @@ extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double*
     DevBufB dA, dD, dpart, dout;
     WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * n * n));
     WB_CUDA(cudaMemcpy(dA.p, Ax, sizeof(double2) * n * n, cudaMemcpyHostToDevice));
-    WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * n));
-    WB_CUDA(cudaMemcpy(dD.p, Dx, sizeof(double2) * n, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * (size_t)n * n_D));
+    WB_CUDA(cudaMemcpy(dD.p, Dx, sizeof(double2) * (size_t)n * n_D, cudaMemcpyHostToDevice));
     p.A = (const double2*)dA.p; p.D = (const double2*)dD.p;
-    const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O) + sizeof(double) * 4 * (size_t)p.length;
+    const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
     int ctas = 1;
     const int wpc = bw_pick_warps(per_warp, &ctas);
     if (wpc < 1) { set_error("lhaf_batch: problem too large for shared memory (%zu bytes per warp)", per_warp); return WB200_ENOSUP; }
@@ -705,22 +724,32 @@ extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double*
     int grid = sms * ctas;
     const uint64_t total = j1 - j0, want = (total + wpc - 1) / wpc;
     if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
+    const size_t rows = (size_t)p.length * n_D;                 // independent outputs
+    while (grid > 1 && rows * (size_t)grid * wpc * 32 > ((size_t)1 << 31)) grid /= 2;   // bound the partial table (2 GiB)
     const int nwarps = grid * wpc;
-    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * (size_t)p.length * nwarps));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4 * (size_t)p.length));
+    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * rows * nwarps));
+    WB_CUDA(cudaMemset(dpart.p, 0, sizeof(double) * 4 * rows * nwarps));
+    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4 * rows));
     p.partials = (double*)dpart.p;
     EvPair ev;
     WB_CUDA(cudaEventCreate(&ev.e0));
     WB_CUDA(cudaEventCreate(&ev.e1));
     WB_CUDA(cudaEventRecord(ev.e0, 0));
     batch_kernel<<<grid, 32 * wpc, shm>>>(p);
-    batch_final_kernel<<<(p.length + 63) / 64, 64>>>((const double*)dpart.p, nwarps, p.length, (double*)dout.p);
+    batch_final_kernel<<<(unsigned)((rows + 63) / 64), 64>>>((const double*)dpart.p, nwarps, (int)rows, (double*)dout.p);
     WB_CUDA(cudaEventRecord(ev.e1, 0));
     WB_CUDA(cudaEventSynchronize(ev.e1));
     WB_CUDA(cudaGetLastError());
     float ms = 0;
     WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     if (kernel_ms) *kernel_ms = ms;
-    WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * 4 * (size_t)p.length, cudaMemcpyDeviceToHost));
+    WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * 4 * rows, cudaMemcpyDeviceToHost));
     return WB200_OK;
+}
+
+extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double* Dx, int n, const int32_t* edge_reps,
+                                     int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* out,
+                                     int length, double* kernel_ms) {
+    return wb200_lhaf_batch_gamma_host(device, Ax, Dx, n, 1, edge_reps, odd_variant, cutoff_extra, glynn, j0, j1, out,
+                                       length, kernel_ms);
 }
