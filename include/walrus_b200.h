@@ -90,6 +90,15 @@ int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, 
                                 const int32_t* edge_reps, int odd_variant, int cutoff_extra, int glynn,
                                 uint64_t j0, uint64_t j1, double* out, int length, double* kernel_ms);
 
+/* ---- montrealer ---------------------------------------------------------------------------------------
+ * Replaces montrealer / lmontrealer (thewalrus/_montrealer.py:37-102) as called by mtl / lmtl (:105-135):
+ * A: 2n x 2n complex (the matrix passed to mtl, NOT pre-multiplied by Xmat), zeta: 2n complex or NULL.
+ * Subset labels p in [p0, p1) of [0, 2^n) (label 0, the empty set, contributes nothing).
+ * out8 = V{re_hi, re_lo, im_hi, im_lo}, W{...} with V = sum_p (-1)^(|p|+1) tr(Sigma_p^n) and
+ * W = sum_p (-1)^(|p|+1) conj(zeta_p) Sigma_p^(n-1) zeta_p; the caller forms (-1)^(n+1) (V / 2n + W / 2). */
+int wb200_mtl_host(int device, const double* A, const double* zeta, int n_modes, uint64_t p0, uint64_t p1,
+                   double out8[8], double* kernel_ms);
+
 /* ---- permanent --------------------------------------------------------------------------------------
  * Replaces perm_bbfg (thewalrus/_permanent.py:130-168; method 0, steps k in [0, 2^(n-1)), final scale
  * 2^(1-n)) and perm_ryser (:86-127; method 1, steps k in [0, 2^n), no scale).  Step k evaluates the

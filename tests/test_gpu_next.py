@@ -1,0 +1,75 @@
+"""GPU parity tests for the SURVEY 8(f) components (run with -m gpu on a B200): the CUDA path through the public
+API against outputs of the reference itself (tests/golden/reference_outputs_next.json), the CPU oracle on seeded
+inputs, and the identities that tie each component to the core path.  Tolerance 1e-10 relative."""
+import numpy as np
+import pytest
+from conftest import dec
+
+import thewalrus_b200 as wb
+from oracle import walrus_oracle as wo
+from thewalrus_b200 import _engine
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def relv(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+# ------------------------------------------------------------------------------ loop_hafnian_batch_gamma
+def test_batch_gamma_vs_reference_outputs(golden_next):
+    for c in golden_next["batch_gamma"]:
+        got = wb.loop_hafnian_batch_gamma(dec(c["A"]), dec(c["D"]), c["fixed"], c["cutoff"], glynn=c["glynn"])
+        want = dec(c["value"])
+        assert got.shape == want.shape and got.dtype == np.complex128
+        assert relv(got, want) < TOL, (c["fixed"], c["cutoff"], c["glynn"])
+
+
+def test_batch_gamma_rows_equal_batch():
+    """gamma(A, D)[k] == loop_hafnian_batch(A, D[k]) on a larger case than the goldens hold."""
+    rng = np.random.default_rng(41)
+    n = 7
+    G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = (G + G.T) / np.sqrt(n)
+    D = rng.standard_normal((9, n)) + 1j * rng.standard_normal((9, n))
+    for fixed, cutoff in (([1, 2, 0, 1, 1, 2], 6), ([1, 1, 1, 0, 2, 2], 5)):
+        got = wb.loop_hafnian_batch_gamma(A, D, fixed, cutoff)
+        for k in range(len(D)):
+            assert relv(got[k], wb.loop_hafnian_batch(A, D[k], fixed, cutoff)) < TOL
+        assert relv(got[3], wo.loop_hafnian_batch(A, D[3], fixed, cutoff)) < TOL
+
+
+# ------------------------------------------------------------------------------ montrealer
+def test_montrealer_vs_reference_outputs(golden_next):
+    for c in golden_next["mtl"]:
+        assert relv(wb.mtl(dec(c["A"])), dec(c["value"])) < TOL, (c["N"], c["kind"])
+    for c in golden_next["lmtl"]:
+        assert relv(wb.lmtl(dec(c["A"]), dec(c["zeta"])), dec(c["value"])) < TOL, (c["N"], c["kind"])
+
+
+@pytest.mark.parametrize("n", [2, 5, 9, 11])
+def test_montrealer_vs_oracle_and_ranges(n):
+    rng = np.random.default_rng(100 + n)
+    G = rng.standard_normal((2 * n, 2 * n)) + 1j * rng.standard_normal((2 * n, 2 * n))
+    A = (G + G.T) / (2 * n)
+    zeta = 0.5 * (rng.standard_normal(2 * n) + 1j * rng.standard_normal(2 * n))
+    assert relv(wb.mtl(A), wo.mtl(A)) < TOL
+    assert relv(wb.lmtl(A, zeta), wo.lmtl(A, zeta)) < TOL
+    # contiguous label ranges add up (the C-ABI unit of multi-GPU sharding)
+    cuts = [0, 1, (1 << n) // 3, (1 << n) - 5 if n > 2 else 2, 1 << n]
+    parts = sum(_engine.mtl_range(A, zeta, a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a)
+    full = _engine.mtl_range(A, zeta, 0, 1 << n)
+    V = lambda t: complex(t[0] + t[1], t[2] + t[3])
+    W = lambda t: complex(t[4] + t[5], t[6] + t[7])
+    assert relv(V(parts), V(full)) < 1e-12 and relv(W(parts), W(full)) < 1e-12
+
+
+def test_montrealer_input_checks():
+    with pytest.raises(TypeError):
+        wb.mtl([[0, 1], [1, 0]])
+    with pytest.raises(ValueError):
+        wb.mtl(np.zeros((3, 3)))
+    with pytest.raises(ValueError):
+        wb.lmtl(np.zeros((4, 4)), np.zeros(3))

@@ -249,6 +249,20 @@ def lhaf_batch_gamma_range(Ax, Dx, edge_reps, odd_variant, cutoff_extra, glynn, 
     return out
 
 
+def mtl_range(A, zeta, p0, p1, device=None):
+    """Partial montrealer sums over subset labels [p0, p1) -> 8 doubles (V and W partials, see the header)."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    A, pA = _lib.as_c128(A)
+    pz = None
+    if zeta is not None:
+        zeta, pz = _lib.as_c128(zeta)
+    out = np.zeros(8)
+    rc = lib.wb200_mtl_host(idx, pA, pz, A.shape[0] // 2, p0, p1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_mtl_host")
+    return out
+
+
 def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False):
     """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU."""
     lib = _lib.load()

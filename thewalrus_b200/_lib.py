@@ -42,6 +42,8 @@ SIGNATURES = {
     "wb200_lhaf_batch_gamma_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, ctypes.c_int,
                                                    _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64, _u64,
                                                    _c_double_p, ctypes.c_int, _c_double_p]),
+    "wb200_mtl_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _u64, _u64, _c_double_p,
+                                      _c_double_p]),
     "wb200_perm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "wb200_perm_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _u64, _u64, _vp, _vp, ctypes.c_size_t, _vp]),
     "wb200_perm_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _u64, _u64,
