@@ -117,6 +117,14 @@ int wb200_perm_f64_host(int device, const double* M, int n, int method, uint64_t
 int wb200_perm_int64_host(int device, const int64_t* M, int n, int method, uint64_t k0, uint64_t k1,
                           int64_t* out, double* kernel_ms);
 
+/* ---- Bristolian ------------------------------------------------------------------------------------
+ * Replaces brs / ubrs (thewalrus/_permanent.py:198-249): sum over row subsets Y of A (m x n complex; label bit i,
+ * MSB first, keeps row i) of (-1)^(m-|Y|) perm_bbfg(A_Y^H A_Y + E), labels j in [j0, j1) of [0, 2^m).
+ * E: n x n complex or NULL (ubrs: E = NULL and j0 = 1).  out4 is the (hi, lo) sum WITHOUT the 2^(1-n) factor of
+ * perm_bbfg (:167), which the caller applies.  m <= 40, n <= 32. */
+int wb200_brs_host(int device, const double* A, const double* E, int m, int n, uint64_t j0, uint64_t j1,
+                   double out4[4], double* kernel_ms);
+
 /* ---- torontonian ------------------------------------------------------------------------------------
  * Replaces rec_torontonian / numba_tor (thewalrus/_torontonian.py:123-154, 189-247):
  * sum over S subset of [N] of (-1)^(N-|S|) / sqrt(det(I - O_S)).  O: 2N x 2N complex Hermitian in the

@@ -73,3 +73,59 @@ def test_montrealer_input_checks():
         wb.mtl(np.zeros((3, 3)))
     with pytest.raises(ValueError):
         wb.lmtl(np.zeros((4, 4)), np.zeros(3))
+
+
+# ------------------------------------------------------------------------------ Bristolian
+def _brs_scale(A, E):
+    return max(1.0, float(np.abs(wo.perm_bbfg(A.conj().T @ A + (0 if E is None else E))))) * 2 ** A.shape[0]
+
+
+def test_bristolian_vs_reference_outputs(golden_next):
+    for c in golden_next["brs"]:
+        A, E = dec(c["A"]), dec(c["E"])
+        assert abs(wb.brs(A, E) - dec(c["value"])) < TOL * _brs_scale(A, E), (c["m"], c["n"])
+    for c in golden_next["ubrs"]:
+        A = dec(c["A"])
+        assert abs(wb.ubrs(A) - dec(c["value"])) < TOL * _brs_scale(A, None), (c["m"], c["n"])
+    for c in golden_next["fock_threshold"]:
+        U = dec(c["U"])
+        assert abs(wb.fock_threshold_prob(c["n"], c["d"], U) - c["unitary"]) < 1e-12
+        assert abs(wb.fock_threshold_prob(c["n"], c["d"], np.sqrt(0.8) * U) - c["lossy"]) < 1e-12
+
+
+@pytest.mark.parametrize("m,n", [(3, 7), (6, 9), (9, 12), (4, 17), (12, 6)])
+def test_bristolian_vs_oracle_and_ranges(m, n):
+    rng = np.random.default_rng(1000 * m + n)
+    A = (rng.standard_normal((m, n)) + 1j * rng.standard_normal((m, n))) / np.sqrt(m)
+    Eh = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    E = 0.05 * (Eh @ Eh.conj().T)
+    if m + n <= 21:
+        assert abs(wb.brs(A, E) - wo.brs(A, E)) < TOL * _brs_scale(A, E)
+        assert abs(wb.ubrs(A) - wo.ubrs(A)) < TOL * _brs_scale(A, None)
+    # brs with a single row subset label equals +-perm of the Gram matrix (ties the kernel to wb.perm)
+    j = (1 << m) - 2                                    # all rows but the last
+    Ay = A[: m - 1]
+    one = _engine.brs_range(A, E, j, j + 1)
+    got = complex(one[0] + one[1], one[2] + one[3]) / 2.0 ** (n - 1)
+    want = -wb.perm(Ay.conj().T @ Ay + E)
+    assert abs(got - want) < TOL * max(1.0, abs(want))
+    # contiguous label ranges add up
+    cuts = [0, 1, (1 << m) // 3, 1 << m]
+    parts = sum(_engine.brs_range(A, E, a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a)
+    full = _engine.brs_range(A, E, 0, 1 << m)
+    c4 = lambda t: complex(t[0] + t[1], t[2] + t[3])
+    assert abs(c4(parts) - c4(full)) < 1e-12 * _brs_scale(A, E) * 2.0 ** (n - 1)
+
+
+def test_fock_prob_matches_permanent():
+    rng = np.random.default_rng(8)
+    Z = rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6))
+    U = np.linalg.qr(Z)[0]
+    n_in, n_out = [1, 0, 2, 1, 0, 1], [0, 2, 1, 0, 1, 1]
+    p = wb.fock_prob(n_in, n_out, U)
+    rows = [i for i, c in enumerate(n_out) for _ in range(c)]
+    cols = [i for i, c in enumerate(n_in) for _ in range(c)]
+    want = abs(wo.perm(U[np.ix_(rows, cols)])) ** 2 / (2 * 2)
+    assert abs(p - want) < 1e-12
+    with pytest.raises(ValueError):
+        wb.fock_prob([1, 0], [1, 1], np.eye(2))

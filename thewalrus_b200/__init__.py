@@ -16,7 +16,7 @@ from ._hafnian import (  # noqa: F401
 )
 from .loop_hafnian_batch import loop_hafnian_batch  # noqa: F401
 from .loop_hafnian_batch_gamma import loop_hafnian_batch_gamma  # noqa: F401
-from ._permanent import perm, perm_bbfg, perm_ryser  # noqa: F401
+from ._permanent import brs, fock_prob, fock_threshold_prob, perm, perm_bbfg, perm_ryser, ubrs  # noqa: F401
 from ._torontonian import tor, tor_input_checks  # noqa: F401
 from ._montrealer import lmtl, mtl  # noqa: F401
 from . import quantum  # noqa: F401

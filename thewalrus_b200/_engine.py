@@ -263,6 +263,20 @@ def mtl_range(A, zeta, p0, p1, device=None):
     return out
 
 
+def brs_range(A, E, j0, j1, device=None):
+    """Partial Bristolian sum over row-subset labels [j0, j1) -> 4 doubles (without the 2^(1-n) factor)."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    A, pA = _lib.as_c128(A)
+    pE = None
+    if E is not None:
+        E, pE = _lib.as_c128(E)
+    out = np.zeros(4)
+    rc = lib.wb200_brs_host(idx, pA, pE, A.shape[0], A.shape[1], j0, j1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_brs_host")
+    return out
+
+
 def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False):
     """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU."""
     lib = _lib.load()

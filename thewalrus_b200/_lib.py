@@ -52,6 +52,8 @@ SIGNATURES = {
                                            _c_double_p, _c_double_p]),
     "wb200_perm_int64_host": (ctypes.c_int, [ctypes.c_int, _c_int64_p, ctypes.c_int, ctypes.c_int, _u64, _u64,
                                              _c_int64_p, _c_double_p]),
+    "wb200_brs_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, ctypes.c_int, _u64, _u64,
+                                      _c_double_p, _c_double_p]),
     "wb200_tor_num_prefixes": (ctypes.c_int, [ctypes.c_int, _c_uint64_p]),
     "wb200_tor_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "wb200_tor_dev": (ctypes.c_int, [_vp, ctypes.c_int, _u64, _u64, _vp, _vp, ctypes.c_size_t, _vp]),

@@ -381,6 +381,113 @@ int perm_i64_dev(const int64_t* dM, int n, int method, uint64_t k0, uint64_t k1,
                                              nullptr, d_out, &grid, st);
 }
 
+
+// =================================================================================================
+// Bristolian (thewalrus/_permanent.py:198-249): sum over row subsets Y of the m x n matrix A of
+// (-1)^(m - |Y|) perm(A_Y^H A_Y + E), each permanent by the Glynn/BBFG Gray-code sum above.
+// =================================================================================================
+// One warp per work unit = (outer subset j, inner chunk): the warp builds the n x n Gram matrix of its subset in
+// its slice of shared memory, its 32 lanes sweep aligned equal segments of the inner Gray code (same flipped row
+// in every lane), and lane 0 adds sign * (warp sum) to the warp's double-double total.  Units are dealt to warps
+// round-robin; partial totals are combined in fixed order.
+constexpr int BRS_WARPS = 8;
+
+struct BrsParams {
+    const C128* A;     // m x n
+    const C128* E;     // n x n or null
+    int m, n, log_chunks, log_seg;   // inner steps 2^(n-1) = chunks * 32 lanes * 2^log_seg (or fewer lanes, see kernel)
+    unsigned long long j0, j1;
+    double* partials;  // (gridDim.x * BRS_WARPS) x 4
+};
+
+template <int NP>
+__global__ void __launch_bounds__(32 * BRS_WARPS) brs_kernel(BrsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = p.n, m = p.m;
+    C128* G = reinterpret_cast<C128*>(smem_raw) + (size_t)warp * n * NP;     // G[row * NP + col]
+    const unsigned long long gw = (unsigned long long)blockIdx.x * BRS_WARPS + warp;
+    const unsigned long long nw = (unsigned long long)gridDim.x * BRS_WARPS;
+    const unsigned long long units = (p.j1 - p.j0) << p.log_chunks;
+    const unsigned long long inner = 1ull << (n - 1);
+    const unsigned long long seg = 1ull << p.log_seg;                         // steps per lane per unit
+    cdd tot;
+    tot.re = {0.0, 0.0}; tot.im = {0.0, 0.0};
+    for (unsigned long long u = gw; u < units; u += nw) {
+        const unsigned long long j = p.j0 + (u >> p.log_chunks), chunk = u & ((1ull << p.log_chunks) - 1ull);
+        // ---- Gram matrix of the kept rows (bit i of the MSB-first label keeps row i: find_kept_edges)
+        __syncwarp();
+        for (int idx = lane; idx < n * NP; idx += 32) {
+            const int a = idx / NP, b = idx - a * NP;
+            C128 g = {0.0, 0.0};
+            if (b < n) {
+                if (p.E) g = p.E[a * n + b];
+                for (int y = 0; y < m; ++y) {
+                    if ((j >> (m - 1 - y)) & 1ull) {
+                        const C128 ya = p.A[y * n + a], yb = p.A[y * n + b];
+                        g.re += ya.re * yb.re + ya.im * yb.im;        // conj(ya) * yb
+                        g.im += ya.re * yb.im - ya.im * yb.re;
+                    }
+                }
+            }
+            G[idx] = g;
+        }
+        __syncwarp();
+        const int kept = __popcll(j);
+        // ---- this lane's segment of the inner Gray code
+        const unsigned long long kb = (chunk * 32ull + (unsigned long long)lane) << p.log_seg;
+        KahanC acc;
+        if (kb < inner) {
+            const unsigned long long gray = kb ^ (kb >> 1);
+            C128 r[NP];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) r[q] = {0.0, 0.0};
+            for (int row = 0; row < n; ++row) {
+                const double d = ((gray >> row) & 1ull) ? -1.0 : 1.0;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) axpy(r[q], d, G[row * NP + q]);
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+                if (q >= n) r[q] = {1.0, 0.0};
+            acc.add(weigh(product<NP, C128>(r), true, (kb & 1ull) != 0));
+            for (unsigned long long t = 1; t < seg; ++t) {
+                const unsigned long long k = kb + t;
+                const int row = __ffsll((long long)t) - 1;            // = ctz(k): kb is a multiple of seg
+                const bool set = ((k ^ (k >> 1)) >> row) & 1ull;
+                const double d = set ? -2.0 : 2.0;
+                const C128* grow = G + row * NP;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) axpy(r[q], d, grow[q]);
+                acc.add(weigh(product<NP, C128>(r), true, (k & 1ull) != 0));
+            }
+        }
+        cdd v = acc.get();
+        v.re = warp_reduce_dd(v.re);
+        v.im = warp_reduce_dd(v.im);
+        if (lane == 0) {
+            const double sg = ((m - kept) & 1) ? -1.0 : 1.0;
+            dd_add_dd(tot.re, dd{sg * v.re.hi, sg * v.re.lo});
+            dd_add_dd(tot.im, dd{sg * v.im.hi, sg * v.im.lo});
+        }
+    }
+    if (lane == 0) {
+        double* o = p.partials + gw * 4;
+        o[0] = tot.re.hi; o[1] = tot.re.lo; o[2] = tot.im.hi; o[3] = tot.im.lo;
+    }
+}
+
+template <int NP>
+static int launch_brs(BrsParams p, int grid, cudaStream_t st) {
+    const size_t shm = sizeof(C128) * (size_t)p.n * NP * BRS_WARPS;
+    WB_CUDA(cudaFuncSetAttribute(brs_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    brs_kernel<NP><<<grid, 32 * BRS_WARPS, shm, st>>>(p);
+    WB_CUDA(cudaGetLastError());
+    return WB200_OK;
+}
+
+constexpr int BRS_MAX_N = 32, BRS_MAX_M = 40;
+
 }  // namespace wb
 
 using namespace wb;
@@ -403,5 +510,65 @@ extern "C" int wb200_perm_dev(const double* dM, int n, int method, uint64_t k0, 
     if (rc) return rc;
     final_reduce_kernel<<<1, 32, 0, st>>>(partials, grid, d_out4);
     WB_CUDA(cudaGetLastError());
+    return WB200_OK;
+}
+
+extern "C" int wb200_brs_host(int device, const double* A, const double* E, int m, int n, uint64_t j0, uint64_t j1,
+                              double out4[4], double* kernel_ms) {
+    if (!A || !out4) { set_error("brs: null pointer"); return WB200_EINVAL; }
+    if (m < 1 || n < 1) { set_error("brs: A must be m x n with m, n >= 1 (got %d x %d)", m, n); return WB200_EINVAL; }
+    if (n > BRS_MAX_N || m > BRS_MAX_M) { set_error("brs: %d x %d exceeds the kernel limits (%d rows, %d columns)", m, n, BRS_MAX_M, BRS_MAX_N); return WB200_ENOSUP; }
+    const uint64_t outer = 1ull << m;
+    if (j0 > j1 || j1 > outer) { set_error("brs: bad subset range"); return WB200_EINVAL; }
+    WB_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    if (device_sm_count(device, &sms)) return WB200_ECUDA;
+    struct Buf { void* p = nullptr; ~Buf() { if (p) cudaFree(p); } } dA, dE, dpart, dout;
+    WB_CUDA(cudaMalloc(&dA.p, sizeof(C128) * m * n));
+    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(C128) * m * n, cudaMemcpyHostToDevice));
+    if (E) {
+        WB_CUDA(cudaMalloc(&dE.p, sizeof(C128) * n * n));
+        WB_CUDA(cudaMemcpy(dE.p, E, sizeof(C128) * n * n, cudaMemcpyHostToDevice));
+    }
+    BrsParams p;
+    p.A = (const C128*)dA.p; p.E = (const C128*)dE.p; p.m = m; p.n = n; p.j0 = j0; p.j1 = j1;
+    // inner Gray code of 2^(n-1) steps = chunks x 32 lanes x 2^log_seg; more chunks when there are few outer subsets
+    const int inner_bits = n - 1;
+    int log_seg = inner_bits > 5 ? inner_bits - 5 : 0, log_chunks = 0;
+    const uint64_t nouter = j1 - j0, target = (uint64_t)sms * BRS_WARPS * 4;
+    while (log_seg > 10 && (nouter << log_chunks) < target) { --log_seg; ++log_chunks; }
+    p.log_seg = log_seg; p.log_chunks = log_chunks;
+    const uint64_t units = nouter << log_chunks;
+    int grid = (int)((units + BRS_WARPS - 1) / BRS_WARPS);
+    if (grid > sms * 2) grid = sms * 2;
+    if (grid < 1) grid = 1;
+    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * grid * BRS_WARPS));
+    WB_CUDA(cudaMemset(dpart.p, 0, sizeof(double) * 4 * grid * BRS_WARPS));
+    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4));
+    p.partials = (double*)dpart.p;
+    cudaEvent_t e0, e1;
+    WB_CUDA(cudaEventCreate(&e0));
+    WB_CUDA(cudaEventCreate(&e1));
+    WB_CUDA(cudaEventRecord(e0, 0));
+    int rc;
+    if (n <= 4) rc = launch_brs<4>(p, grid, 0);
+    else if (n <= 8) rc = launch_brs<8>(p, grid, 0);
+    else if (n <= 12) rc = launch_brs<12>(p, grid, 0);
+    else if (n <= 16) rc = launch_brs<16>(p, grid, 0);
+    else if (n <= 20) rc = launch_brs<20>(p, grid, 0);
+    else if (n <= 24) rc = launch_brs<24>(p, grid, 0);
+    else if (n <= 28) rc = launch_brs<28>(p, grid, 0);
+    else rc = launch_brs<32>(p, grid, 0);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    final_reduce_kernel<<<1, 32>>>((const double*)dpart.p, grid * BRS_WARPS, (double*)dout.p);
+    WB_CUDA(cudaEventRecord(e1, 0));
+    WB_CUDA(cudaEventSynchronize(e1));
+    WB_CUDA(cudaGetLastError());
+    float ms = 0;
+    WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms) *kernel_ms = ms;
+    WB_CUDA(cudaMemcpy(out4, dout.p, 4 * sizeof(double), cudaMemcpyDeviceToHost));
     return WB200_OK;
 }
