@@ -139,6 +139,16 @@ int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, doubl
 int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
                    double* kernel_ms);
 
+/* ---- loop torontonian -------------------------------------------------------------------------------
+ * Replaces rec_ltorontonian / recursiveLTor / numba_ltor (thewalrus/_torontonian.py:276-345, 369-412):
+ * sum over S of (-1)^(N-|S|) exp(gamma_S (I - O_S)^-1 gamma_S^* / 2) / sqrt(det(I - O_S)).
+ * O as for wb200_tor_*; gamma: 2N complex in the same (x..., p...) order.  Same prefix ranges, workspace and
+ * output convention as the torontonian (the sum is real for Hermitian O, as in rec_ltorontonian). */
+int wb200_ltor_dev(const double* dO, const double* dGamma, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                   void* d_workspace, size_t workspace_bytes, void* stream);
+int wb200_ltor_host(int device, const double* O, const double* gamma, int n_modes, uint64_t p0, uint64_t p1,
+                    double out2[2], double* kernel_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -129,3 +129,69 @@ def test_fock_prob_matches_permanent():
     assert abs(p - want) < 1e-12
     with pytest.raises(ValueError):
         wb.fock_prob([1, 0], [1, 1], np.eye(2))
+
+
+# ------------------------------------------------------------------------------ loop torontonian
+def _rand_O_gamma(N, seed, scale=0.8):
+    rng = np.random.default_rng(seed)
+    B = rng.standard_normal((2 * N, 2 * N)) + 1j * rng.standard_normal((2 * N, 2 * N))
+    H = B @ B.conj().T
+    O = scale * H / np.linalg.norm(H, 2)
+    g = 0.5 * (rng.standard_normal(N) + 1j * rng.standard_normal(N))
+    return O, np.concatenate([g, g.conj()])
+
+
+def test_ltor_vs_reference_outputs(golden_next):
+    for c in golden_next["ltor"]:
+        O, gamma = dec(c["O"]), dec(c["gamma"])
+        got = wb.ltor(O, gamma)
+        assert isinstance(got, np.complex128)
+        assert relv(got, dec(c["direct"])) < TOL, len(gamma)
+        assert relv(got, dec(c["rec"])) < 1e-9, len(gamma)   # the reference's two variants differ by ~1e-11
+
+
+def test_ltor_vs_oracle_and_ranges():
+    for N, seed in ((2, 1), (3, 2), (7, 3), (10, 4), (12, 5)):
+        O, gamma = _rand_O_gamma(N, seed)
+        want = wo.ltor_direct(O, gamma)
+        assert relv(wb.ltor(O, gamma), want) < TOL, N
+        total = _engine.tor_num_prefixes(N)
+        if total >= 4:   # prefix ranges are additive (the multi-GPU shard unit)
+            cut = [0, total // 4, total // 2 + 1, total]
+            parts = [_engine.tor_range(O, cut[i], cut[i + 1], gamma=gamma) for i in range(3)]
+            assert relv(sum(p[0] + p[1] for p in parts), want) < TOL, N
+
+
+def test_ltor_without_displacement_is_tor():
+    """thewalrus/tests/test_torontonian.py:260-273."""
+    for N in (1, 2, 6, 11):
+        O, _ = _rand_O_gamma(N, 20 + N)
+        assert relv(wb.ltor(O, np.zeros(2 * N)), wb.tor(O)) < TOL
+
+
+def test_ltor_input_checks():
+    O, gamma = _rand_O_gamma(3, 9)
+    with pytest.raises(ValueError, match="gamma must be a vector matching the dimension of A"):
+        wb.ltor(O, gamma[:-1])
+    with pytest.raises(TypeError):
+        wb.ltor(O, list(gamma))
+
+
+def test_threshold_detection_prob_vs_reference_outputs(golden_next):
+    for c in golden_next["threshold"]:
+        mu, cov = np.array(c["mu"]), np.array(c["cov"])
+        assert abs(wb.threshold_detection_prob(mu, cov, c["det"]) - c["displaced"]) < 1e-12
+        assert abs(wb.threshold_detection_prob(0 * mu, cov, c["det"]) - c["zero_mean"]) < 1e-12
+
+
+def test_threshold_probabilities_sum_to_one():
+    """All 2^M click patterns of a displaced 5-mode state (thewalrus/tests/test_torontonian.py:331-357 idea)."""
+    from itertools import product
+
+    rng = np.random.default_rng(77)
+    M = 5
+    S = rng.standard_normal((2 * M, 2 * M))
+    cov = S @ S.T / (2 * M) + np.identity(2 * M)
+    mu = 0.4 * rng.standard_normal(2 * M)
+    tot = sum(wb.threshold_detection_prob(mu, cov, np.array(d)) for d in product([0, 1], repeat=M))
+    assert abs(tot - 1.0) < 1e-9

@@ -1,7 +1,7 @@
 """walrus_b200 — B200-native (sm_100a CUDA) exponential-sum hot path of The Walrus.
 
 Drop-in for the reference's matrix functions on that path:
-``hafnian``, ``loop_hafnian``, ``hafnian_repeated``, ``perm``, ``tor``, ``loop_hafnian_batch`` and the
+``hafnian``, ``loop_hafnian``, ``hafnian_repeated``, ``perm``, ``tor``, ``ltor``, ``loop_hafnian_batch`` and the
 batched GBS-probability front end.  See DESIGN.md for scope and INTEGRATION.md for the binding.
 """
 from ._hafnian import (  # noqa: F401
@@ -17,7 +17,7 @@ from ._hafnian import (  # noqa: F401
 from .loop_hafnian_batch import loop_hafnian_batch  # noqa: F401
 from .loop_hafnian_batch_gamma import loop_hafnian_batch_gamma  # noqa: F401
 from ._permanent import brs, fock_prob, fock_threshold_prob, perm, perm_bbfg, perm_ryser, ubrs  # noqa: F401
-from ._torontonian import tor, tor_input_checks  # noqa: F401
+from ._torontonian import ltor, numba_vac_prob, threshold_detection_prob, tor, tor_input_checks  # noqa: F401
 from ._montrealer import lmtl, mtl  # noqa: F401
 from . import quantum  # noqa: F401
 from .quantum import density_matrix_element, probabilities, probabilities_batch  # noqa: F401

@@ -191,8 +191,8 @@ def lhaf_general_range(Ax, Dx, oddV, oddloop, edge_reps, glynn, j0, j1, device=N
     return out
 
 
-def tor_range(O, p0, p1, device=None):
-    """Partial torontonian sum over prefixes [p0, p1) -> (hi, lo)."""
+def tor_range(O, p0, p1, device=None, gamma=None):
+    """Partial (loop) torontonian sum over prefixes [p0, p1) -> (hi, lo); ``gamma`` selects the loop variant."""
     torch = _torch()
     dev = require_cuda(device)
     lib = _lib.load()
@@ -204,9 +204,14 @@ def tor_range(O, p0, p1, device=None):
         dO = _to_dev(O, dev)
         ws = _workspace(dev, nbytes)
         out = torch.empty(4, dtype=torch.float64, device=dev)
-        rc = lib.wb200_tor_dev(dO.data_ptr(), N, p0, p1, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                               torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(rc, "wb200_tor_dev")
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if gamma is None:
+            rc = lib.wb200_tor_dev(dO.data_ptr(), N, p0, p1, out.data_ptr(), ws.data_ptr(), ws.numel() * 8, st)
+        else:
+            dG = _to_dev(gamma, dev)
+            rc = lib.wb200_ltor_dev(dO.data_ptr(), dG.data_ptr(), N, p0, p1, out.data_ptr(), ws.data_ptr(),
+                                    ws.numel() * 8, st)
+        _lib.check(rc, "wb200_tor_dev" if gamma is None else "wb200_ltor_dev")
         return out.cpu().numpy()[:2]
 
 

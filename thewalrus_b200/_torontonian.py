@@ -1,10 +1,11 @@
-"""Torontonian front end — drop-in for thewalrus.tor (thewalrus/_torontonian.py:23-58)."""
+"""Torontonian front ends — drop-ins for thewalrus.tor, ltor and threshold_detection_prob
+(thewalrus/_torontonian.py:23-120)."""
 import numpy as np
 
 from . import _engine
 from ._prep import dd_sum
 
-__all__ = ["tor", "tor_input_checks"]
+__all__ = ["tor", "ltor", "threshold_detection_prob", "numba_vac_prob", "tor_input_checks"]
 
 
 def tor_input_checks(A, loops=None):
@@ -47,3 +48,66 @@ def tor(A, recursive=True, *, group=None, device=None):
     hi, lo = dd_sum([(p[0], p[1]) for p in table])
     val = hi + lo
     return np.complex128(val) if is_complex else np.float64(val)
+
+
+def ltor(A, gamma, recursive=True, *, group=None, device=None):
+    """Loop torontonian  sum_S (-1)^(N-|S|) exp(gamma_S (I - A_S)^-1 gamma_S^* / 2) / sqrt(det(I - A_S))
+    (thewalrus/_torontonian.py:61-74; rec_ltorontonian :320-345, numba_ltor :369-412).
+
+    Like ``rec_ltorontonian`` (the reference default) the exponent is evaluated as the squared norm of the
+    forward-substituted vector, so the value is real; it is returned as ``np.complex128`` as the reference does.
+    ``recursive`` is accepted for signature compatibility (both reference variants compute the same number).
+    """
+    tor_input_checks(A, gamma)
+    del recursive
+    N = A.shape[0] // 2
+    if N == 0:
+        return np.complex128(1.0)
+    A = np.asarray(A, dtype=np.complex128)
+    gamma = np.asarray(gamma, dtype=np.complex128)
+    if N == 1:
+        # two subsets: {} -> -1, {0} -> exp(x^H B^-1 x / 2) / sqrt(det B), B = I - A, x = conj(gamma)
+        B = np.identity(2) - A
+        d1 = B[0, 0].real
+        l10 = B[1, 0] / d1
+        d2 = (B[1, 1] - l10 * B[0, 1]).real
+        x = gamma.conj()
+        z1 = x[1] - l10 * x[0]
+        q = abs(x[0]) ** 2 / d1 + abs(z1) ** 2 / d2
+        return np.complex128(-1.0 + np.exp(0.5 * q) / np.sqrt(d1 * d2))
+    total = _engine.tor_num_prefixes(N)
+    table = _engine.run_sharded(total, lambda lo, hi: _engine.tor_range(A, lo, hi, device, gamma=gamma), group,
+                                width=2)
+    hi, lo = dd_sum([(p[0], p[1]) for p in table])
+    return np.complex128(hi + lo)
+
+
+def numba_vac_prob(alpha, sigma):
+    """Vacuum probability  exp(-alpha^H sigma^-1 alpha / 2) / sqrt(det sigma)  (thewalrus/_torontonian.py:348-366)."""
+    alpha = np.asarray(alpha, dtype=np.complex128)
+    sigma = np.asarray(sigma, dtype=np.complex128)
+    return (np.exp(-0.5 * alpha.conj() @ np.linalg.solve(sigma, alpha)).real / np.sqrt(np.linalg.det(sigma))).real
+
+
+def threshold_detection_prob(mu, cov, det_pattern, hbar=2, atol=1e-10, rtol=1e-10, *, group=None, device=None):
+    """Probability of the click pattern ``det_pattern`` for the Gaussian state (mu, cov)
+    (thewalrus/_torontonian.py:77-120): ``tor`` of the clicked block of ``O = I - Q^-1`` for zero-mean states,
+    ``ltor`` with ``gamma = (sigma^-1 alpha)^*`` times the vacuum probability for displaced ones."""
+    from .quantum import Qmat
+
+    mu, cov = np.asarray(mu), np.asarray(cov)
+    n = cov.shape[0] // 2
+    clicked = np.where(np.asarray(det_pattern) == 1)[0]
+    rows = np.concatenate([clicked, clicked + n])
+    if np.allclose(mu, 0, atol=atol, rtol=rtol):
+        Q = Qmat(cov, hbar)
+        O = np.identity(2 * n) - np.linalg.inv(Q)
+        Os = np.ascontiguousarray(O[np.ix_(rows, rows)])
+        return tor(Os, group=group, device=device) / np.sqrt(np.linalg.det(Q))
+    alpha = np.concatenate((mu[:n] + 1j * mu[n:], mu[:n] - 1j * mu[n:])) / np.sqrt(2 * hbar)
+    sigma = Qmat(cov, hbar=hbar).conj()
+    inv_sigma = np.linalg.inv(sigma)
+    O = np.identity(2 * n) - inv_sigma
+    gamma = (inv_sigma @ alpha).conj()
+    O_red = np.ascontiguousarray(O[np.ix_(rows, rows)])
+    return numba_vac_prob(alpha, sigma) * ltor(O_red, gamma[rows], group=group, device=device).real

@@ -21,19 +21,39 @@ constexpr int TOR_THREADS = 256;
 constexpr int TOR_DC = 9;        // modes expanded breadth-first inside a CTA
 constexpr int TOR_G = 5;         // log2(prefixes per CTA)
 constexpr int TOR_MAX_MODES = 32;
+constexpr int TOR_BUF = 2304;       // max over BFS levels of nodes * dim^2, DC = 9: 64 nodes of 6 x 6
+constexpr int TOR_BUF_LOOP = 3200;  // bordered nodes: 128 nodes of 5 x 5
 
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
     return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
 }
 
-// interleave modes and form B = I - O
-__global__ void tor_prep_kernel(const double2* __restrict__ O, int N, double2* __restrict__ B) {
-    const int n2 = 2 * N;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n2 * n2; idx += gridDim.x * blockDim.x) {
-        const int r = idx / n2, c = idx % n2;
+// interleave modes and form B = I - O.  Loop torontonian (gamma != nullptr): B is bordered by one extra
+// row/column  B[2N][c] = gamma_c, B[c][2N] = conj(gamma_c), B[2N][2N] = 0.  Eliminating a pivot k of the
+// bordered Hermitian matrix updates the border row exactly like the forward substitution of the reference
+// (solve_triangular, thewalrus/_torontonian.py:250-273: x_i -= L_ik z_k with x = conj(gamma)) and subtracts
+// |x_k|^2 / d_k from the corner, so after the kept modes are eliminated  -corner = x^H (I - O_S)^-1 x,
+// the exponent of recursiveLTor (:307-309) / numba_ltor (:404), and excluded modes drop out of the border
+// together with their rows.  The border index is never a pivot.
+__global__ void tor_prep_kernel(const double2* __restrict__ O, const double2* __restrict__ gamma, int N,
+                                double2* __restrict__ B) {
+    const int n2 = 2 * N, ld = n2 + (gamma ? 1 : 0);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ld * ld; idx += gridDim.x * blockDim.x) {
+        const int r = idx / ld, c = idx % ld;
         const int sr = (r >> 1) + (r & 1) * N, sc = (c >> 1) + (c & 1) * N;
-        double2 v = O[(size_t)sr * n2 + sc];
-        B[idx] = make_double2((r == c ? 1.0 : 0.0) - v.x, -v.y);
+        double2 out;
+        if (r < n2 && c < n2) {
+            const double2 v = O[(size_t)sr * n2 + sc];
+            out = make_double2((r == c ? 1.0 : 0.0) - v.x, -v.y);
+        } else if (r == n2 && c == n2) {
+            out = make_double2(0.0, 0.0);
+        } else if (r == n2) {
+            out = gamma[sc];
+        } else {
+            const double2 g = gamma[sr];
+            out = make_double2(g.x, -g.y);
+        }
+        B[idx] = out;
     }
 }
 
@@ -100,15 +120,59 @@ __device__ __forceinline__ double tail2(const double2* T, double det, double sgn
     return sum;
 }
 
+// one scalar pivot of a 5x5 bordered node held in registers (lower triangle, index 4 = border)
+template <int K>
+__device__ __forceinline__ double pivot5(double2 (&a)[5][5]) {
+    const double d = a[K][K].x, inv = 1.0 / d;
+#pragma unroll
+    for (int r = K + 1; r < 5; ++r)
+#pragma unroll
+        for (int c = K + 1; c <= r; ++c) {
+            const double2 q = cmulc(a[r][K], a[c][K]);
+            a[r][c].x -= q.x * inv;
+            a[r][c].y -= q.y * inv;
+        }
+    return d;
+}
+
+// loop torontonian: finish a 2-mode bordered (5x5) node, 4 subsets; exponent = -corner / 2
+__device__ __forceinline__ double tail2_loop(const double2* T, double det, double sgn) {
+    double2 a[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = T[r * 5 + c];
+    double sum = sgn * exp(-0.5 * a[4][4].x) / sqrt(det);                     // {}
+    {                                                                         // {m1}: pivots 2, 3
+        const double d1 = a[2][2].x, i1 = 1.0 / d1;
+        const double2 e = a[3][2], g2 = a[4][2];
+        const double d2 = a[3][3].x - (e.x * e.x + e.y * e.y) * i1;
+        double2 u = a[4][3];
+        { const double2 q = cmulc(g2, e); u.x -= q.x * i1; u.y -= q.y * i1; }
+        const double corner = a[4][4].x - (g2.x * g2.x + g2.y * g2.y) * i1 - (u.x * u.x + u.y * u.y) / d2;
+        sum -= sgn * exp(-0.5 * corner) / sqrt(det * d1 * d2);
+    }
+    const double p0 = pivot5<0>(a);
+    const double p1 = pivot5<1>(a);
+    const double det01 = det * p0 * p1;
+    sum -= sgn * exp(-0.5 * a[4][4].x) / sqrt(det01);                         // {m0}
+    const double p2 = pivot5<2>(a);
+    const double p3 = pivot5<3>(a);
+    sum += sgn * exp(-0.5 * a[4][4].x) / sqrt(det01 * p2 * p3);               // {m0, m1}
+    return sum;
+}
+
+// AUG = 0: torontonian; AUG = 1: loop torontonian (every matrix carries the border row/column).
+template <int AUG>
 __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem_tor[];
-    const int N = p.N, n2 = 2 * N, DC = p.DC, g = p.g, P = p.P;
-    const int dg = 2 * (DC + g);
+    const int N = p.N, n2 = 2 * N + AUG, DC = p.DC, g = p.g, P = p.P;
+    const int dg = 2 * (DC + g) + AUG;
     double2* T = reinterpret_cast<double2*>(smem_tor);   // n2 x n2
     double2* T0 = T + n2 * n2;                            // dg x dg
     double2* W = T0 + dg * dg;                            // dg x dg
     double2* bufA = W + dg * dg;
-    const int bufsz = 2304;                               // max level size for DC = 9 (see host)
+    constexpr int bufsz = AUG ? TOR_BUF_LOOP : TOR_BUF;   // max level size for DC = 9 (see host)
     double2* bufB = bufA + bufsz;
     double* detA = reinterpret_cast<double*>(bufB + bufsz);  // 256 each: det, sgn ping-pong; inv1, inv2
     double* sgnA = detA + 256;
@@ -153,7 +217,7 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
             }
             __syncthreads();
             // level 0 node: trailing 2DC x 2DC block
-            int dim = 2 * DC;
+            int dim = 2 * DC + AUG;
             for (int idx = tid; idx < dim * dim; idx += TOR_THREADS) {
                 const int r = idx / dim, c = idx % dim;
                 bufA[idx] = W[(2 * g + r) * dg + 2 * g + c];
@@ -163,7 +227,7 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
             double2* cur = bufA; double2* nxt = bufB;
             double* dcur = detA; double* scur = sgnA; double* dnxt = detB; double* snxt = sgnB;
             int nodes = 1;
-            while (dim > 4) {
+            while (dim > 4 + AUG) {
                 const int cd = dim - 2;
                 // per-node pivots
                 for (int nd = tid; nd < nodes; nd += TOR_THREADS) {
@@ -199,7 +263,10 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
                 nodes *= 2; dim = cd;
             }
             // ---- 2-mode nodes finished by single threads
-            for (int nd = tid; nd < nodes; nd += TOR_THREADS) dd_add(acc, tail2(cur + nd * 16, dcur[nd], scur[nd]));
+            for (int nd = tid; nd < nodes; nd += TOR_THREADS) {
+                if (AUG) dd_add(acc, tail2_loop(cur + nd * 25, dcur[nd], scur[nd]));
+                else dd_add(acc, tail2(cur + nd * 16, dcur[nd], scur[nd]));
+            }
         }
     }
     __shared__ double red[(TOR_THREADS / 32) * 4];
@@ -235,9 +302,9 @@ extern "C" int wb200_tor_num_prefixes(int n_modes, uint64_t* count) {
     return WB200_OK;
 }
 
-// workspace: interleaved I - O (2N x 2N complex) followed by 4 doubles per CTA
+// workspace: interleaved (bordered) I - O, (2N + 1) x (2N + 1) complex, followed by 4 doubles per CTA
 static size_t tor_ws_partials_offset(int N) {
-    return (sizeof(double2) * (size_t)(2 * N) * (2 * N) + 255) & ~(size_t)255;
+    return (sizeof(double2) * (size_t)(2 * N + 1) * (2 * N + 1) + 255) & ~(size_t)255;
 }
 constexpr int TOR_MAX_GRID = 1024;
 
@@ -246,15 +313,16 @@ extern "C" size_t wb200_tor_workspace_bytes(int n_modes) {
     return tor_ws_partials_offset(n_modes) + sizeof(double) * 4 * TOR_MAX_GRID;
 }
 
-extern "C" int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
-                             void* d_workspace, size_t workspace_bytes, void* stream) {
+// shared launcher: dGamma == nullptr -> torontonian, else loop torontonian
+static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                      void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!dO || !d_out4 || !d_workspace) { set_error("tor: null pointer"); return WB200_EINVAL; }
     uint64_t total = 0;
     int rc = wb200_tor_num_prefixes(n_modes, &total);
     if (rc) return rc;
     if (p0 > p1 || p1 > total) { set_error("tor: bad prefix range"); return WB200_EINVAL; }
     if (workspace_bytes < wb200_tor_workspace_bytes(n_modes)) { set_error("tor: workspace too small"); return WB200_EINVAL; }
-    const int N = n_modes, n2 = 2 * N;
+    const int N = n_modes, aug = dGamma ? 1 : 0, n2 = 2 * N + aug;
     cudaStream_t st = (cudaStream_t)stream;
     TorParams p;
     tor_shape(N, &p.P, &p.g, &p.DC);
@@ -265,38 +333,61 @@ extern "C" int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_
     int dev = 0, sms = 0;
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
-    const int dg = 2 * (p.DC + p.g);
-    const size_t shm = sizeof(double2) * ((size_t)n2 * n2 + 2 * (size_t)dg * dg + 2 * 2304) + sizeof(double) * 6 * 256;
-    WB_CUDA(cudaFuncSetAttribute(tor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    const int dg = 2 * (p.DC + p.g) + aug;
+    const size_t shm = sizeof(double2) * ((size_t)n2 * n2 + 2 * (size_t)dg * dg + 2 * (aug ? TOR_BUF_LOOP : TOR_BUF)) +
+                       sizeof(double) * 6 * 256;
+    {
+        const int max_n2 = 2 * TOR_MAX_MODES + 1, max_dg = 2 * (TOR_DC + TOR_G) + 1;
+        const int max_shm = (int)(sizeof(double2) * ((size_t)max_n2 * max_n2 + 2 * (size_t)max_dg * max_dg + 2 * TOR_BUF_LOOP) +
+                                  sizeof(double) * 6 * 256);
+        if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
+        else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
+    }
     const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
     int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
     if (grid > TOR_MAX_GRID) grid = TOR_MAX_GRID;
-    tor_prep_kernel<<<8, 256, 0, st>>>(reinterpret_cast<const double2*>(dO), N, dB);
-    tor_kernel<<<grid, TOR_THREADS, shm, st>>>(p, dpart);
+    tor_prep_kernel<<<8, 256, 0, st>>>(reinterpret_cast<const double2*>(dO), reinterpret_cast<const double2*>(dGamma), N, dB);
+    if (aug) tor_kernel<1><<<grid, TOR_THREADS, shm, st>>>(p, dpart);
+    else tor_kernel<0><<<grid, TOR_THREADS, shm, st>>>(p, dpart);
     final_reduce_kernel<<<1, 32, 0, st>>>(dpart, grid, d_out4);
     WB_CUDA(cudaGetLastError());
     return WB200_OK;
 }
 
-extern "C" int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
-                              double* kernel_ms) {
+extern "C" int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                             void* d_workspace, size_t workspace_bytes, void* stream) {
+    return tor_launch(dO, nullptr, n_modes, p0, p1, d_out4, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int wb200_ltor_dev(const double* dO, const double* dGamma, int n_modes, uint64_t p0, uint64_t p1,
+                              double* d_out4, void* d_workspace, size_t workspace_bytes, void* stream) {
+    if (!dGamma) { set_error("ltor: null gamma"); return WB200_EINVAL; }
+    return tor_launch(dO, dGamma, n_modes, p0, p1, d_out4, d_workspace, workspace_bytes, stream);
+}
+
+static int tor_host_impl(int device, const double* O, const double* gamma, int n_modes, uint64_t p0, uint64_t p1,
+                         double out2[2], double* kernel_ms) {
     if (!O || !out2) { set_error("tor: null pointer"); return WB200_EINVAL; }
     uint64_t total = 0;
     int rc = wb200_tor_num_prefixes(n_modes, &total);
     if (rc) return rc;
     const int n2 = 2 * n_modes;
     WB_CUDA(cudaSetDevice(device));
-    DevBufT dO, dws, dout;
+    DevBufT dO, dG, dws, dout;
     const size_t wsb = wb200_tor_workspace_bytes(n_modes);
     WB_CUDA(cudaMalloc(&dO.p, sizeof(double) * 2 * n2 * n2));
     WB_CUDA(cudaMalloc(&dws.p, wsb));
     WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4));
     WB_CUDA(cudaMemcpy(dO.p, O, sizeof(double) * 2 * n2 * n2, cudaMemcpyHostToDevice));
+    if (gamma) {
+        WB_CUDA(cudaMalloc(&dG.p, sizeof(double) * 2 * n2));
+        WB_CUDA(cudaMemcpy(dG.p, gamma, sizeof(double) * 2 * n2, cudaMemcpyHostToDevice));
+    }
     cudaEvent_t e0, e1;
     WB_CUDA(cudaEventCreate(&e0));
     WB_CUDA(cudaEventCreate(&e1));
     WB_CUDA(cudaEventRecord(e0, 0));
-    rc = wb200_tor_dev((const double*)dO.p, n_modes, p0, p1, (double*)dout.p, dws.p, wsb, nullptr);
+    rc = tor_launch((const double*)dO.p, (const double*)dG.p, n_modes, p0, p1, (double*)dout.p, dws.p, wsb, nullptr);
     if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
     WB_CUDA(cudaEventRecord(e1, 0));
     WB_CUDA(cudaEventSynchronize(e1));
@@ -309,4 +400,15 @@ extern "C" int wb200_tor_host(int device, const double* O, int n_modes, uint64_t
     WB_CUDA(cudaMemcpy(o4, dout.p, 4 * sizeof(double), cudaMemcpyDeviceToHost));
     out2[0] = o4[0]; out2[1] = o4[1];
     return WB200_OK;
+}
+
+extern "C" int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
+                              double* kernel_ms) {
+    return tor_host_impl(device, O, nullptr, n_modes, p0, p1, out2, kernel_ms);
+}
+
+extern "C" int wb200_ltor_host(int device, const double* O, const double* gamma, int n_modes, uint64_t p0, uint64_t p1,
+                               double out2[2], double* kernel_ms) {
+    if (!gamma) { set_error("ltor: null gamma"); return WB200_EINVAL; }
+    return tor_host_impl(device, O, gamma, n_modes, p0, p1, out2, kernel_ms);
 }
