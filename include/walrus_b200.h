@@ -70,6 +70,13 @@ int wb200_lhaf_general_steps(const int32_t* edge_reps, int n_edges, int glynn, i
  * nv <= 64; per pattern at most 32 edges and series order <= 200. */
 int wb200_lhaf_patterns_host(int device, const double* A, const double* gamma, int nv, const int32_t* rpt,
                              int64_t B, int glynn, double* out, double* kernel_ms);
+/* Same, with a table of loop vectors: gamma is n_gamma x nv complex and pattern b uses row gamma_index[b]
+ * (gamma_index may be NULL when n_gamma == 1).  This is the call the batched chain-rule samplers make: one mode
+ * step of generate_hafnian_sample / generate_torontonian_sample (thewalrus/samples.py:245-249, 459-470) for
+ * ALL samples (and fan-out channels) at once, each with its own heterodyne-shifted gamma. */
+int wb200_lhaf_patterns_multi_host(int device, const double* A, const double* gamma, int n_gamma,
+                                   const int32_t* gamma_index, int nv, const int32_t* rpt, int64_t B, int glynn,
+                                   double* out, double* kernel_ms);
 
 /* ---- loop_hafnian_batch sweep -------------------------------------------------------------------------
  * Replaces _calc_loop_hafnian_batch_even / _odd (thewalrus/loop_hafnian_batch.py:51-208).  Ax (n x n, n = 2E),

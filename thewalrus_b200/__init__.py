@@ -19,7 +19,7 @@ from .loop_hafnian_batch_gamma import loop_hafnian_batch_gamma  # noqa: F401
 from ._permanent import brs, fock_prob, fock_threshold_prob, perm, perm_bbfg, perm_ryser, ubrs  # noqa: F401
 from ._torontonian import ltor, numba_vac_prob, threshold_detection_prob, tor, tor_input_checks  # noqa: F401
 from ._montrealer import lmtl, mtl  # noqa: F401
-from . import quantum  # noqa: F401
+from . import quantum, samples  # noqa: F401
 from .quantum import density_matrix_element, probabilities, probabilities_batch  # noqa: F401
 
 __version__ = "0.1.0"

@@ -282,38 +282,57 @@ def brs_range(A, E, j0, j1, device=None):
     return out
 
 
-def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False):
-    """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU."""
+def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False, gamma_index=None):
+    """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU.
+    ``gamma`` may be a table ``[G, nv]`` with ``gamma_index[B]`` selecting each pattern's row."""
     lib = _lib.load()
     idx = _dev_index(device)
     A, pA = _lib.as_c128(A)
     pG = None
+    n_gamma = 0
     if gamma is not None:
         gamma, pG = _lib.as_c128(gamma)
+        n_gamma = 1 if gamma.ndim == 1 else gamma.shape[0]
     rpt = np.ascontiguousarray(rpt, dtype=np.int32)
     B, nv = rpt.shape
+    pI = None
+    if gamma_index is not None:
+        gamma_index = np.ascontiguousarray(gamma_index, dtype=np.int32)
+        if gamma_index.shape != (B,):
+            raise ValueError("gamma_index must have one entry per pattern")
+        pI = gamma_index.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     out = np.zeros(B, dtype=np.complex128)
     ms = ctypes.c_double(0.0)
-    rc = lib.wb200_lhaf_patterns_host(idx, pA, pG, nv, rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B,
-                                      1 if glynn else 0, _lib.dptr(out.view(np.float64)), ctypes.byref(ms))
-    _lib.check(rc, "wb200_lhaf_patterns_host")
+    rc = lib.wb200_lhaf_patterns_multi_host(idx, pA, pG, n_gamma, pI, nv,
+                                            rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B,
+                                            1 if glynn else 0, _lib.dptr(out.view(np.float64)), ctypes.byref(ms))
+    _lib.check(rc, "wb200_lhaf_patterns_multi_host")
     return (out, ms.value) if want_ms else out
 
 
-def run_sharded_patterns(A, gamma, rpt, glynn, group, device, local=None):
+def run_sharded_patterns(A, gamma, rpt, glynn, group, device, local=None, gamma_index=None):
     """Shard the PATTERNS in contiguous blocks over the ranks of ``group`` and all-gather the results
     (the batched front end shards the batch, not the subset index).  ``local`` overrides the
     per-rank evaluator (tests use the oracle there)."""
-    local = local or (lambda r: lhaf_patterns_local(A, gamma, r, glynn, device))
+    if local is None:
+        if gamma_index is None:
+            local = lambda r, a=0, b=None: lhaf_patterns_local(A, gamma, r, glynn, device)  # noqa: E731
+        else:
+            gamma_index = np.ascontiguousarray(gamma_index, dtype=np.int32)
+            local = lambda r, a=0, b=None: lhaf_patterns_local(A, gamma, r, glynn, device,  # noqa: E731
+                                                                gamma_index=gamma_index[a:b])
+    else:
+        user = local
+        local = lambda r, a=0, b=None: user(r)  # noqa: E731
     rank, world = _rank_world(group, None)
     B = rpt.shape[0]
     if world == 1:
-        return local(rpt)
+        return local(rpt, 0, B)
     torch = _torch()
     import torch.distributed as dist
 
     lo, hi = shard_range(B, rank, world)
-    mine = local(rpt[lo:hi]) if hi > lo else np.zeros(0, dtype=np.complex128)
+    mine = local(rpt[lo:hi], lo, hi) if hi > lo else np.zeros(0, dtype=np.complex128)
     g = None if group is True else group
     backend = dist.get_backend(g)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")

@@ -377,7 +377,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restri
 
 struct PatParams {
     const double2* A;
-    const double2* D;  // gamma or null
+    const double2* D;  // gamma(s) or null: n_gamma x nv
+    const int32_t* gidx;  // per-pattern row of D, or null (all patterns use row 0)
     int nv, glynn, smax, T, O;
     long long B;
     const PatDesc* desc;
@@ -411,6 +412,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
         const PatDesc* d = p.desc + pat;
         const int E = d->E, N = d->N, odd = d->odd;
         const unsigned long long steps = d->steps;
+        const double2* Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.nv : p.D;
         __syncwarp();
         if (lane < BW_EMAX) { w.eu[lane] = d->u[lane]; w.ev[lane] = d->v[lane]; w.er[lane] = d->r[lane]; }
         __syncwarp();
@@ -429,8 +431,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
             }
             __syncwarp();
             const int k = s_k[warp];
-            subset_traces(w, p.A, p.nv, p.D, odd, -1, k, T, lane);
-            if (odd >= 0) fac_odd(w, order, __ldg(p.D + odd), w.ov, lane);
+            subset_traces(w, p.A, p.nv, Dp, odd, -1, k, T, lane);
+            if (odd >= 0) fac_odd(w, order, __ldg(Dp + odd), w.ov, lane);
             else fac_even(w, order, lane);
             exp_series(w, w.cs0, order, lane);
             if (lane == 0) {
@@ -450,14 +452,15 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
 }
 
 __global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigned long long* __restrict__ coff,
-                                 const double* __restrict__ partial, const double2* __restrict__ D, int glynn,
-                                 long long B, double2* __restrict__ out) {
+                                 const double* __restrict__ partial, const double2* __restrict__ D,
+                                 const int32_t* __restrict__ gidx, int nv, int glynn, long long B,
+                                 double2* __restrict__ out) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     const PatDesc* d = desc + p;
     if (d->kind == 1) { out[p] = make_double2(1.0, 0.0); return; }
     if (d->kind == 2) { out[p] = make_double2(0.0, 0.0); return; }
-    if (d->kind == 3) { out[p] = D[d->odd]; return; }
+    if (d->kind == 3) { out[p] = D[(gidx ? (size_t)gidx[p] * nv : 0) + d->odd]; return; }
     dd re = {0.0, 0.0}, im = {0.0, 0.0};
     for (unsigned long long c = coff[p]; c < coff[p + 1]; ++c) {
         dd_add_dd(re, dd{partial[c * 4 + 0], partial[c * 4 + 1]});
@@ -653,19 +656,34 @@ using namespace wb;
 
 extern "C" int wb200_lhaf_patterns_host(int device, const double* A, const double* gamma, int nv, const int32_t* rpt,
                                         int64_t B, int glynn, double* out, double* kernel_ms) {
+    return wb200_lhaf_patterns_multi_host(device, A, gamma, gamma ? 1 : 0, nullptr, nv, rpt, B, glynn, out, kernel_ms);
+}
+
+extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const double* gamma, int n_gamma,
+                                              const int32_t* gamma_index, int nv, const int32_t* rpt, int64_t B,
+                                              int glynn, double* out, double* kernel_ms) {
     if (!A || !rpt || !out) { set_error("lhaf_patterns: null pointer"); return WB200_EINVAL; }
+    if (gamma && n_gamma < 1) { set_error("lhaf_patterns: n_gamma must be >= 1 when gamma is given"); return WB200_EINVAL; }
+    if (gamma && n_gamma > 1 && !gamma_index) { set_error("lhaf_patterns: gamma_index is required for n_gamma > 1"); return WB200_EINVAL; }
+    if (gamma && gamma_index)
+        for (int64_t i = 0; i < B; ++i)
+            if (gamma_index[i] < 0 || gamma_index[i] >= n_gamma) { set_error("lhaf_patterns: gamma_index[%lld] = %d outside [0, %d)", (long long)i, gamma_index[i], n_gamma); return WB200_EINVAL; }
     if (nv < 1 || nv > BW_NVMAX) { set_error("lhaf_patterns: %d vertices outside [1, %d]", nv, BW_NVMAX); return nv > BW_NVMAX ? WB200_ENOSUP : WB200_EINVAL; }
     if (B < 0) { set_error("lhaf_patterns: negative batch"); return WB200_EINVAL; }
     if (B == 0) { if (kernel_ms) *kernel_ms = 0.0; return WB200_OK; }
     WB_CUDA(cudaSetDevice(device));
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    DevBufB dA, dD, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
+    DevBufB dA, dD, dgi, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
     WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * nv * nv));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * nv * nv, cudaMemcpyHostToDevice));
     if (gamma) {
-        WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * nv));
-        WB_CUDA(cudaMemcpy(dD.p, gamma, sizeof(double2) * nv, cudaMemcpyHostToDevice));
+        WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * (size_t)n_gamma * nv));
+        WB_CUDA(cudaMemcpy(dD.p, gamma, sizeof(double2) * (size_t)n_gamma * nv, cudaMemcpyHostToDevice));
+        if (gamma_index) {
+            WB_CUDA(cudaMalloc(&dgi.p, sizeof(int32_t) * (size_t)B));
+            WB_CUDA(cudaMemcpy(dgi.p, gamma_index, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice));
+        }
     }
     WB_CUDA(cudaMalloc(&drpt.p, sizeof(int32_t) * (size_t)B * nv));
     WB_CUDA(cudaMemcpy(drpt.p, rpt, sizeof(int32_t) * (size_t)B * nv, cudaMemcpyHostToDevice));
@@ -696,7 +714,7 @@ extern "C" int wb200_lhaf_patterns_host(int device, const double* A, const doubl
     }
     if (nchunks > 0) {
         PatParams p;
-        p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.nv = nv; p.glynn = glynn;
+        p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.gidx = (const int32_t*)dgi.p; p.nv = nv; p.glynn = glynn;
         p.smax = 2 * meta.maxE; p.T = meta.maxN / 2; p.O = meta.anyOdd ? meta.maxN : meta.maxN / 2;
         p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p;
         p.nchunks = nchunks; p.counter = (unsigned long long*)dcounter.p;
@@ -715,8 +733,8 @@ extern "C" int wb200_lhaf_patterns_host(int device, const double* A, const doubl
         WB_CUDA(cudaGetLastError());
     }
     pat_final_kernel<<<(unsigned)((B + 127) / 128), 128>>>((const PatDesc*)ddesc.p, (const unsigned long long*)dcoff.p,
-                                                           (const double*)dpartial.p, (const double2*)dD.p, glynn, B,
-                                                           (double2*)dout.p);
+                                                           (const double*)dpartial.p, (const double2*)dD.p,
+                                                           (const int32_t*)dgi.p, nv, glynn, B, (double2*)dout.p);
     WB_CUDA(cudaEventRecord(ev.e1, 0));
     WB_CUDA(cudaEventSynchronize(ev.e1));
     WB_CUDA(cudaGetLastError());

@@ -13,8 +13,9 @@ import numpy as np
 
 from . import _engine
 
-__all__ = ["Qmat", "Amat", "complex_to_real_displacements", "density_matrix_element", "probabilities",
-           "probabilities_batch", "lhaf_patterns"]
+__all__ = ["Qmat", "Amat", "Covmat", "Xmat", "sympmat", "complex_to_real_displacements", "density_matrix_element",
+           "probabilities", "probabilities_batch", "lhaf_patterns", "photon_number_mean_vector", "adj_scaling",
+           "adj_to_qmat", "gen_Qmat_from_graph", "is_valid_cov", "is_classical_cov", "williamson"]
 
 
 def Qmat(cov, hbar=2):
@@ -50,16 +51,19 @@ def _prefactor(mu, cov, hbar=2):
     return np.exp(-0.5 * beta @ np.linalg.inv(Q) @ beta.conj()) / np.sqrt(np.linalg.det(Q))
 
 
-def lhaf_patterns(A, gamma, rpt, glynn=True, *, group=None, device=None):
+def lhaf_patterns(A, gamma, rpt, glynn=True, *, gamma_index=None, group=None, device=None):
     """``[loop_hafnian(A, gamma, reps=r) for r in rpt]`` (``gamma=None``: ``hafnian_repeated(A, r)``) on the GPU.
 
-    ``rpt``: integer array ``[B, len(A)]``.  With ``group`` the patterns are sharded over the ranks in
-    contiguous blocks and the results all-gathered (one collective).
+    ``rpt``: integer array ``[B, len(A)]``.  ``gamma`` may also be a table ``[G, len(A)]`` of loop vectors with
+    ``gamma_index[B]`` naming the row each pattern uses (the batched samplers' call).  With ``group`` the
+    patterns are sharded over the ranks in contiguous blocks and the results all-gathered (one collective).
     """
     rpt = np.ascontiguousarray(rpt, dtype=np.int32)
     if rpt.ndim != 2 or rpt.shape[1] != len(A):
         raise ValueError("rpt must have shape [batch, len(A)]")
-    return _engine.run_sharded_patterns(A, gamma, rpt, glynn, group, device)
+    if gamma is not None and np.ndim(gamma) == 2 and gamma_index is None and len(gamma) != 1:
+        raise ValueError("a table of loop vectors needs gamma_index")
+    return _engine.run_sharded_patterns(A, gamma, rpt, glynn, group, device, gamma_index=gamma_index)
 
 
 def _state(mu, cov, hbar, tol):
@@ -107,3 +111,124 @@ def probabilities(mu, cov, cutoff, parallel=False, hbar=2.0, rtol=1e-05, atol=1e
     M = len(mu) // 2
     pats = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(-1, M)
     return probabilities_batch(mu, cov, pats, hbar=hbar, group=group, device=device).reshape([cutoff] * M)
+
+
+# ---------------------------------------------------------------------------------------------------
+# host-side state helpers used by the samplers (O(M^3) NumPy; no GPU work)
+# ---------------------------------------------------------------------------------------------------
+def Xmat(N):
+    """[[0, I], [I, 0]] (conversions.py:46-66)."""
+    Z, I = np.zeros((N, N)), np.identity(N)
+    return np.block([[Z, I], [I, Z]])
+
+
+def sympmat(N):
+    """Symplectic form [[0, I], [-I, 0]] (thewalrus/symplectic.py sympmat)."""
+    Z, I = np.zeros((N, N)), np.identity(N)
+    return np.block([[Z, I], [-I, Z]])
+
+
+def Covmat(Q, hbar=2):
+    """xp Wigner covariance from the Husimi matrix, the inverse of Qmat (conversions.py:99-121)."""
+    n = len(Q) // 2
+    Nm = Q[:n, :n] - np.identity(n)     # <a_i^dagger a_j>
+    Mm = Q[n:, :n]                      # <a_i a_j>
+    xx = 2 * (Nm.real + Mm.real) + np.identity(n)
+    pp = 2 * (Nm.real - Mm.real) + np.identity(n)
+    xp = 2 * (Mm.imag + Nm.imag)
+    return (hbar / 2) * np.block([[xx, xp], [xp.T, pp]])
+
+
+def photon_number_mean_vector(mu, cov, hbar=2):
+    """<n_j> = (mu_j^2 + mu_(j+N)^2 + cov_jj + cov_(j+N)(j+N) - hbar) / (2 hbar)
+    (quantum/means_and_variances.py:31-66)."""
+    mu, cov = np.asarray(mu), np.asarray(cov)
+    N = len(mu) // 2
+    d = np.diag(cov)
+    return (mu[:N] ** 2 + mu[N:] ** 2 + d[:N] + d[N:] - hbar) / (2 * hbar)
+
+
+def adj_scaling(A, n_mean):
+    """Scale x such that the pure GBS state encoding x A has total mean photon number ``n_mean``:
+    sum_i (x s_i)^2 / (1 - (x s_i)^2) = n_mean over the singular values s_i (quantum/adjacency_matrices.py:90-146)."""
+    from scipy.optimize import brentq
+
+    sv = np.linalg.svd(A, compute_uv=False)
+    eps = 1e-10
+    if 1000 * eps >= sv[0]:
+        raise ValueError("The singular values of the matrix A are too small.")
+
+    def excess(x):
+        v2 = (x * sv) ** 2
+        return np.sum(v2 / (1.0 - v2)) - n_mean
+
+    return brentq(excess, 0.0, 1.0 / (eps + sv[0]), xtol=1e-15, rtol=1e-14)
+
+
+def adj_to_qmat(A, n_mean):
+    """Husimi matrix of the pure state encoding the graph A at mean photon number n_mean:
+    Q = (I - X (xA (+) xA^*))^-1 (quantum/adjacency_matrices.py:149-170)."""
+    A = np.asarray(A)
+    if A.shape[0] != A.shape[1]:
+        raise ValueError("Matrix must be square.")
+    n = len(A)
+    As = adj_scaling(A, n_mean) * A
+    Z = np.zeros_like(As)
+    return np.linalg.inv(np.identity(2 * n) - Xmat(n) @ np.block([[As, Z], [Z, As.conj()]]))
+
+
+gen_Qmat_from_graph = adj_to_qmat
+
+
+def is_valid_cov(cov, hbar=2, rtol=1e-05, atol=1e-08):
+    """Square, symmetric, even-sized and cov + i hbar/2 Omega >= 0 (quantum/gaussian_checks.py:26-57)."""
+    cov = np.asarray(cov)
+    if cov.ndim != 2 or cov.shape[0] != cov.shape[1] or cov.shape[0] % 2:
+        return False
+    if not np.allclose(cov, cov.T, rtol=rtol, atol=atol):
+        return False
+    vals = np.linalg.eigvalsh(cov + 0.5j * hbar * sympmat(cov.shape[0] // 2))
+    vals[np.abs(vals) < atol] = 0.0
+    return bool(np.all(vals >= 0))
+
+
+def is_classical_cov(cov, hbar=2, atol=1e-08):
+    """Valid and cov - hbar/2 I >= 0, i.e. a positive P function (quantum/gaussian_checks.py:79-99)."""
+    if not is_valid_cov(cov, hbar=hbar, atol=atol):
+        return False
+    vals = np.linalg.eigvalsh(np.asarray(cov) - 0.5 * hbar * np.identity(len(cov)))
+    vals[np.abs(vals) < atol] = 0.0
+    return bool(np.all(vals >= 0))
+
+
+def williamson(V, rtol=1e-05, atol=1e-08):
+    """Williamson form V = S D S^T with S symplectic and D = diag(nu, nu) (thewalrus/decompositions.py:50-102).
+
+    Gamma = V^(-1/2) Omega V^(-1/2) is real antisymmetric; its real Schur form is block diagonal with blocks
+    [[0, b_i], [-b_i, 0]], |b_i| = 1 / nu_i.  Orienting every block positively and regrouping the Schur vectors
+    from (x1, p1, x2, p2, ...) to (x1.., p1..) gives the orthogonal O with S = V^(1/2) O diag(nu, nu)^(-1/2).
+    """
+    from scipy.linalg import schur, sqrtm
+
+    V = np.asarray(V)
+    if V.shape[0] != V.shape[1]:
+        raise ValueError("The input matrix is not square")
+    if not np.allclose(V, V.T, rtol=rtol, atol=atol):
+        raise ValueError("The input matrix is not symmetric")
+    if V.shape[0] % 2 != 0:
+        raise ValueError("The input matrix must have an even number of rows/columns")
+    n = V.shape[0] // 2
+    if not np.all(np.linalg.eigvalsh(V) > 0):
+        raise ValueError("Input matrix is not positive definite")
+    # S is only fixed up to a rotation inside every mode's (x, p) plane; taking the root with sqrtm and its
+    # inverse with inv, as the reference does, lands in the same gauge, so seeded sample streams agree.
+    root = np.real_if_close(sqrtm(V))
+    iroot = np.linalg.inv(root)
+    blocks, O = schur(iroot @ sympmat(n) @ iroot)
+    beta = np.diag(blocks, k=1)[::2]
+    first = np.where(beta > 0, 2 * np.arange(n), 2 * np.arange(n) + 1)   # column playing "x" in each block
+    second = np.where(beta > 0, 2 * np.arange(n) + 1, 2 * np.arange(n))
+    O = O[:, np.concatenate([first, second])]
+    nu = 1.0 / np.abs(beta)
+    dd = np.concatenate([nu, nu])
+    return np.diag(dd), (root @ O) / np.sqrt(dd)
