@@ -11,6 +11,8 @@ scaling: total work fixed) and the partial sums are combined by one all-reduce i
 
 Other workloads (the remaining BASELINE configs and the north-star targets):
 --workload hafnian24|hafnian56|lhaf50|perm32|perm40|tor48|gbs16
+and the SURVEY 8(f) components: ltor48 (loop torontonian), mtl14 (montrealer, 14 modes), brs12 (Bristolian of a
+12 x 12 block), hsample8 (batched chain-rule photon-number sampler, 8 modes; unit: samples/s).
 """
 import argparse
 import ctypes
@@ -45,12 +47,29 @@ def make_input(workload):
         Q, R = np.linalg.qr(Z)
         U = Q * (np.diag(R) / np.abs(np.diag(R)))  # Haar phase fix (thewalrus/random.py:115-134)
         return kind, n, np.ascontiguousarray(U[:n, :n])
-    if kind == "tor":  # n = 2N
+    if kind in ("tor", "ltor"):  # n = 2N
         N = n // 2
         rng = np.random.default_rng(1000 * 4 + n)
         B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
         H = B @ B.conj().T
-        return kind, n, 0.9 * H / np.linalg.norm(H, 2)
+        O = 0.9 * H / np.linalg.norm(H, 2)
+        if kind == "tor":
+            return kind, n, O
+        g = 0.2 * (rng.standard_normal(N) + 1j * rng.standard_normal(N))
+        return kind, n, (O, np.concatenate([g, g.conj()]))
+    if kind == "mtl":  # n = modes; 2n x 2n complex symmetric adjacency-like matrix
+        rng = np.random.default_rng(1000 * 6 + n)
+        G = rng.standard_normal((2 * n, 2 * n)) + 1j * rng.standard_normal((2 * n, 2 * n))
+        return kind, n, (G + G.T) / np.sqrt(8.0 * n)
+    if kind == "brs":  # n x n block of a 2n-mode Haar unitary (lossy interferometer) and E = I - A^H A
+        rng = np.random.default_rng(1000 * 7 + n)
+        Z = (rng.standard_normal((2 * n, 2 * n)) + 1j * rng.standard_normal((2 * n, 2 * n))) / np.sqrt(2)
+        Q, R = np.linalg.qr(Z)
+        A = np.ascontiguousarray((Q * (np.diag(R) / np.abs(np.diag(R))))[:n, :n])
+        return kind, n, (A, np.identity(n) - A.conj().T @ A)
+    if kind == "hsample":  # n = modes: GBS state as in config 3, smaller squeezing so chains stay below the cutoff
+        mu, cov, _ = make_gbs_state(n, 1, seed=1000 * 8 + n, r=0.4)
+        return kind, n, (mu, cov)
     raise SystemExit(f"unknown workload {workload}")
 
 
@@ -75,7 +94,7 @@ def make_gbs_state(M, B, seed, r=0.5, eta=0.8, hbar=2.0, mean_photons=0.45, max_
     return mu, cov, np.ascontiguousarray(pats[:B])
 
 
-def tor_tree_flops(N, DC=9):
+def tor_tree_flops(N, DC=9, aug=0):
     """Executed flops of the Schur-complement tree kernel (torontonian.cu) per torontonian, counted from its
     loops: an included child of a breadth-first node of dimension d updates (d-2)^2 complex entries with four
     a*conj(b) products (6 flops) and four real-scaled subtractions (4 flops) = 40 flops; a 2-mode leaf node
@@ -83,12 +102,12 @@ def tor_tree_flops(N, DC=9):
     DC = min(DC, N)
     per_prefix = 0.0
     for lvl in range(max(0, DC - 2)):
-        d = 2 * (DC - lvl)
+        d = 2 * (DC - lvl) + aug
         per_prefix += (1 << lvl) * (d - 2) ** 2 * 40.0
-    per_prefix += (1 << max(0, DC - 2)) * 70.0
+    per_prefix += (1 << max(0, DC - 2)) * (150.0 if aug else 70.0)
     lead = 0.0
     for i in range(N - DC):  # on average half of the leading modes are eliminated, on the full trailing block
-        d = 2 * (N - i)
+        d = 2 * (N - i) + aug
         lead += 0.5 * ((d - 1) ** 2 + (d - 2) ** 2) * 10.0
     prefixes = 1 << (N - DC)
     return prefixes * per_prefix + (prefixes / 32.0) * lead
@@ -117,6 +136,28 @@ def units_and_flops(kind, n):
                 "Schur-complement tree: 40 flops per updated entry of every included child node (torontonian.cu), "
                 "averaged per subset; the kernel is shared-memory bound, the FP64 fraction is reported for scale only",
                 "FP64 DFMA (vector pipe), operands in shared memory")
+    if kind == "ltor":
+        N = n // 2
+        f = tor_tree_flops(N, aug=1) / float(1 << N)
+        ek3 = N * (N - 1) * (N - 2) / 8.0 + 3 * N * (N - 1) / 4.0 + N / 2.0
+        return (1 << N, f, (4.0 / 3.0) * 8.0 * ek3,
+                "bordered Schur-complement tree (torontonian.cu, AUG = 1): 40 flops per updated entry of every included "
+                "child node incl. the border row/column; shared-memory bound, the FP64 fraction is reported for scale only",
+                "FP64 DFMA (vector pipe), operands in shared memory")
+    if kind == "mtl":
+        # reference: powertrace(Sigma_p, n + 1) = n - 1 products of the 2k x 2k sub-matrix per subset, k ~ Binomial(n, 1/2)
+        ek3 = n * (n - 1) * (n - 2) / 8.0 + 3 * n * (n - 1) / 4.0 + n / 2.0
+        ref = 8.0 * 8.0 * ek3 * (n - 1)
+        return (1 << n, ref * ((n // 2) / max(1.0, n - 1.0)), ref,
+                "reference: 8 (2k)^3 (n-1) per subset (product chain to tr Sigma_p^n), averaged over k ~ Bin(n, 1/2); the "
+                "kernel pairs traces and needs ~n/2 products",
+                "FP64 DFMA (vector pipe), warp per subset, operands in shared memory")
+    if kind == "brs":
+        per = (1 << (n - 1)) * (8.0 * n - 4) + 8.0 * n * n * (n / 2.0)
+        return (1 << n, per, per,
+                "per row subset Y: Gram matrix A_Y^H A_Y + E (8 n^2 |Y| flops, |Y| ~ n/2) and a Glynn permanent of it "
+                "(2^(n-1) Gray steps x (8n - 4))",
+                "FP64 DFMA (vector pipe), warp per row subset")
     raise ValueError(kind)
 
 
@@ -163,7 +204,33 @@ def gbs_reference_flops(pats):
     return float(np.sum(2.0 ** (Np - 1) * 8.0 * (2 * Np) ** 3 * (Np - 1)))
 
 
-def cpu_baseline(kind, n, X, seconds=15.0):
+def sampler_reference_flops(det, cutoff):
+    """Reference-algorithm flops of the chains that produced the patterns ``det[S, M]``.  At mode i a chain needs the
+    loop hafnians of the repetition patterns (n_1 .. n_(i-1), k), k = 0..cutoff.  Each is counted as the reference
+    evaluates a repeated-vertex loop hafnian: pair the vertices (matched_reps), prod(edge_reps + 1) mixed-radix
+    subsets (Glynn halves the first edge), per subset the product chain 8 s^3 (N/2 - 1) plus N/2 mat-vecs 8 s^2 on
+    the s = 2 #edges reduced matrix (an upper bound: edges with delta = 0 drop out)."""
+    from thewalrus_b200._prep import glynn_steps, matched_reps
+
+    det = np.asarray(det, dtype=np.int64)
+    S, M = det.shape
+    total = 0.0
+    for mode in range(M):
+        pref, counts = np.unique(det[:, :mode], axis=0, return_counts=True) if mode else (np.zeros((1, 0), dtype=np.int64), np.array([S]))
+        for row, cnt in zip(pref, counts):
+            for k in range(cutoff + 1):
+                rpt = list(row) + [k]
+                N = int(sum(rpt))
+                if N < 2:
+                    continue
+                _, er, odd = matched_reps(rpt)
+                s_dim, T = 2 * len(er), N // 2
+                steps = glynn_steps(er, True, odd is not None)
+                total += cnt * steps * (8.0 * s_dim ** 3 * max(T - 1, 0) + 8.0 * s_dim ** 2 * T)
+    return total
+
+
+def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
     """Time the oracle's C port (reference algorithm) on the host cores over a bounded sample."""
     from oracle import c_oracle as co
 
@@ -196,6 +263,49 @@ def cpu_baseline(kind, n, X, seconds=15.0):
         dt = time.perf_counter() - t0
         threads = 1
         what = "full recursive torontonian (single thread, as the reference)"
+    elif kind in ("ltor", "mtl", "brs"):
+        from oracle import walrus_oracle as wo
+
+        total = 1 << (n // 2 if kind == "ltor" else n)
+        j0, sample, dt = total // 3, 0, 0.0       # a window in the middle of the index space: typical subset sizes
+        step = {"ltor": 2000, "mtl": 2000, "brs": 8}[kind]
+        t0 = time.perf_counter()
+        while dt < seconds and j0 + sample < total:
+            a, b = j0 + sample, min(total, j0 + sample + step)
+            if kind == "ltor":
+                wo.ltor_direct(X[0], X[1], a, b)
+            elif kind == "mtl":
+                wo.montrealer(np.vstack([X[n:], X[:n]]), None, a, b)     # Xmat(n) @ A, as mtl does
+            else:
+                wo.brs(X[0], X[1], a, b)
+            sample += b - a
+            dt = time.perf_counter() - t0
+        threads = 1
+        what = (f"{sample} of {total} subsets starting at index {j0} through the NumPy restatement of the reference "
+                "(single thread, as the reference)")
+    elif kind == "hsample":
+        # the reference's chain (one sample at a time, one loop_hafnian_batch per mode) with the oracle as its kernel
+        from oracle import walrus_oracle as wo
+        from thewalrus_b200 import quantum as wq
+        from thewalrus_b200 import samples as wsamples
+
+        def oracle_patterns(A, gamma, rpt, glynn=True, *, gamma_index=None, group=None, device=None):
+            gamma = np.atleast_2d(gamma)
+            return np.array([wo.loop_hafnian(A, gamma[g], [int(v) for v in r]) for r, g in zip(rpt, gamma_index)])
+
+        saved, wq.lhaf_patterns = wq.lhaf_patterns, oracle_patterns
+        try:
+            ch = wsamples._Chain(X[1], X[0], 2)
+            t0 = time.perf_counter()
+            sample = 0
+            while time.perf_counter() - t0 < seconds:
+                wsamples._hafnian_chains(ch, 1, cutoff, None)
+                sample += 1
+            dt = time.perf_counter() - t0
+        finally:
+            wq.lhaf_patterns = saved
+        return {"value": sample / dt, "unit": "samples/s", "cores": 1, "kind": "port", "seconds": dt,
+                "sample": f"{sample} chains, one at a time, every loop hafnian through the NumPy restatement (single thread)"}
     else:  # gbs: X = (A, gamma, rpt); one loop hafnian per pattern through the NumPy oracle, single thread as the reference
         from oracle import walrus_oracle as wo
 
@@ -220,6 +330,8 @@ def metric_name(workload):
         return METRIC
     if workload.startswith("gbs"):
         return f"{workload} GBS pattern probabilities/s"
+    if workload.startswith("hsample"):
+        return f"{workload} GBS photon-number samples/s"
     return f"{workload} subsets/s"
 
 
@@ -246,13 +358,16 @@ def run_reference_arm(args):
     if args.workload.startswith("gbs"):
         M, mu, cov, pats, A, gamma, rpt = gbs_inputs(args.workload, args.batch)
         kind, n, X, units, ref_flops, unit = "gbs", 2 * M, (A, gamma, rpt), len(rpt), gbs_reference_flops(pats) / len(rpt), "patterns/s"
+    elif args.workload.startswith("hsample"):
+        kind, n, X = make_input(args.workload)
+        units, ref_flops, unit = min(args.batch, 2048), 0.0, "samples/s"
     else:
         kind, n, X = make_input(args.workload)
         units, _, ref_flops, _, _ = units_and_flops(kind, n)
         unit = "subsets/s"
     vals = []
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(kind, n, X, seconds=per)
+        cb = cpu_baseline(kind, n, X, seconds=per, cutoff=args.cutoff)
         if i >= args.warmup:
             vals.append(cb)
     v = statistics.mean(c["value"] for c in vals)
@@ -276,6 +391,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="hafnian50")
     ap.add_argument("--batch", type=int, default=100000, help="patterns per step of the gbs workload")
+    ap.add_argument("--cutoff", type=int, default=6, help="per-mode photon cutoff of the hsample workload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -308,11 +424,24 @@ def main():
         pipe = "FP64 DFMA (vector pipe), warp per subset, operands in shared memory"
         unit = "patterns/s"
         lo, hi = shard_range(units, rank, world)
+    elif args.workload.startswith("hsample"):
+        kind, n, X = make_input(args.workload)
+        units = min(args.batch, 2048)          # chains per step, split over the ranks
+        unit = "samples/s"
+        lo, hi = shard_range(units, rank, world)
+        from thewalrus_b200 import samples as wsamples
+
+        chain = wsamples._Chain(X[1], X[0], 2)
+        my_flops = ref_flops = 0.0             # filled from the patterns actually drawn (below)
+        model = ("reference-algorithm flops of the loop hafnians a chain evaluates: per mode and outcome k one repeated-"
+                 "vertex loop hafnian = prod(edge_reps + 1) mixed-radix subsets x (8 s^3 (N/2 - 1) + 8 s^2 N/2) on the "
+                 "s = 2 #edges reduced matrix; these are small problems, the step is launch/latency bound")
+        pipe = "FP64 DFMA (vector pipe), warp per subset, operands in shared memory"
     else:
         kind, n, X = make_input(args.workload)
         units, my_flops, ref_flops, model, pipe = units_and_flops(kind, n)
         unit = "subsets/s"
-        lo, hi = shard_range(units if kind != "tor" else _engine.tor_num_prefixes(n // 2), rank, world)
+        lo, hi = shard_range(units if kind not in ("tor", "ltor") else _engine.tor_num_prefixes(n // 2), rank, world)
 
     # ---- device-resident inputs for the kernel-only number
     dA = dD = None
@@ -332,8 +461,21 @@ def main():
         dA = torch.from_numpy(np.ascontiguousarray(X, dtype=np.complex128).view(np.float64).reshape(-1)).to(dev)
         wsb = lib.wb200_tor_workspace_bytes(n // 2)
         launches_per_step = 3      # tor_prep, tor_kernel, final_reduce
+    elif kind == "ltor":
+        dA = torch.from_numpy(np.ascontiguousarray(X[0], dtype=np.complex128).view(np.float64).reshape(-1)).to(dev)
+        dD = torch.from_numpy(np.ascontiguousarray(X[1], dtype=np.complex128).view(np.float64).reshape(-1)).to(dev)
+        wsb = lib.wb200_tor_workspace_bytes(n // 2)
+        launches_per_step = 3      # tor_prep, tor_kernel<1>, final_reduce
+    elif kind == "mtl":
+        launches_per_step = 2      # mtl_kernel, final reduction
+    elif kind == "brs":
+        launches_per_step = 2      # brs_kernel, final reduction
+    elif kind == "hsample":
+        launches_per_step = 4 * n  # one patterns call (prep, scan, main, final) per mode
     else:
         launches_per_step = 4      # pat_prep, scan, pat_main, pat_final
+    host_entry = kind in ("gbs", "mtl", "brs", "hsample")   # *_host entry points: they time their own launches
+    drawn = []
     ws = torch.empty((wsb + 7) // 8, dtype=torch.float64, device=dev)
     out = torch.zeros(4, dtype=torch.float64, device=dev)
     table = torch.zeros((world, 4), dtype=torch.float64, device=dev)
@@ -351,12 +493,26 @@ def main():
         elif kind == "tor":
             rc = lib.wb200_tor_dev(dA.data_ptr(), n // 2, lo, hi, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
                                    stream.cuda_stream)
+        elif kind == "ltor":
+            rc = lib.wb200_ltor_dev(dA.data_ptr(), dD.data_ptr(), n // 2, lo, hi, out.data_ptr(), ws.data_ptr(),
+                                    ws.numel() * 8, stream.cuda_stream)
+        elif kind in ("mtl", "brs", "hsample"):
+            _engine.kernel_ms_log = []
+            if kind == "mtl":
+                _engine.mtl_range(X, None, lo, hi, dev)
+            elif kind == "brs":
+                _engine.brs_range(X[0], X[1], lo, hi, dev)
+            else:
+                drawn.append(wsamples._hafnian_chains(chain, hi - lo, args.cutoff, dev))
+            inner_ms.append(sum(_engine.kernel_ms_log))
+            _engine.kernel_ms_log = None
+            rc = 0
         else:
             _, ms = _engine.lhaf_patterns_local(A, gamma, rpt[lo:hi], True, dev, want_ms=True)
             inner_ms.append(ms)
             rc = 0
         _lib.check(rc, "kernel step")
-        if world > 1 and not is_gbs:  # the one collective of the path: all-reduce of the (hi, lo) partials
+        if world > 1 and not host_entry:  # the one collective of the path: all-reduce of the (hi, lo) partials
             table.zero_()
             table[rank] = out
             dist.all_reduce(table)
@@ -391,7 +547,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     value = units * args.steps / (total_ms * 1e-3)
-    if is_gbs:
+    if host_entry:
         res = 0j
     elif world > 1:
         res = _engine.combine4(table.cpu().numpy())
@@ -410,6 +566,15 @@ def main():
             return wb.perm(X, method="glynn", group=grp)
         if kind == "tor":
             return wb.tor(X, group=grp)
+        if kind == "ltor":
+            return wb.ltor(X[0], X[1], group=grp)
+        if kind == "mtl":
+            return wb.mtl(X, group=grp)
+        if kind == "brs":
+            return wb.brs(X[0], X[1], group=grp)
+        if kind == "hsample":   # every rank draws its share of the samples (independent chains, no collective)
+            got = wsamples.hafnian_sample_state(X[1], hi - lo, mean=X[0], cutoff=args.cutoff, max_photons=10 ** 6)
+            return float(got.sum())
         return float(np.sum(wb.probabilities_batch(mu, cov, pats, group=grp)))
 
     e2e_step()
@@ -428,7 +593,9 @@ def main():
     if rank == 0:
         peak = ctypes.c_double(0)
         lib.wb200_fp64_peak(local, 1 if kind in ("hafnian", "lhaf") else 0, ctypes.byref(peak))
-        per_gpu_units = (hi - lo) if kind != "tor" else units / world
+        per_gpu_units = (hi - lo) if kind not in ("tor", "ltor") else units / world
+        if kind == "hsample":
+            my_flops = ref_flops = sampler_reference_flops(np.concatenate(drawn), args.cutoff) / max(1, len(drawn) * (hi - lo))
         kms = statistics.mean(kern_ms)
         achieved = per_gpu_units * my_flops / (kms * 1e-3) * 1e-12
         if is_gbs:
@@ -436,19 +603,34 @@ def main():
             cfg_in = (f"{M}-mode Gaussian state (Haar interferometer, r=0.5, eta=0.8, displaced), {units} Poisson(0.45) "
                       "patterns with <= 10 photons")
             api = "thewalrus_b200.probabilities_batch(mu, cov, patterns) with host NumPy arrays"
+        elif kind == "hsample":
+            # per mode step: B block + one gamma row per chain + patterns in, lhafs out
+            K = args.cutoff + 1
+            h2d = int(sum(16 * m * m + (hi - lo) * (16 * m + 4 * m * K + 4 * K) for m in range(1, n + 1)))
+            d2h = int(n * (hi - lo) * K * 16)
+            cfg_in = (f"{n}-mode Gaussian state (Haar interferometer, r=0.4, eta=0.8, displaced), {units} chains per step "
+                      f"advanced together, cutoff {args.cutoff}")
+            api = "thewalrus_b200.samples.hafnian_sample_state(cov, S, mean=mu, cutoff) with host NumPy arrays"
         else:
-            h2d, d2h = int(X.nbytes), 32
+            Xs = X if isinstance(X, tuple) else (X,)
+            h2d, d2h = int(sum(np.asarray(x).nbytes for x in Xs)), 32
             cfg_in = {"hafnian": "random complex symmetric G+G^T, seed 1000*config+n", "lhaf": "random complex symmetric G+G^T, loops = diagonal",
-                      "perm": "n x n block of a 2n Haar unitary", "tor": "random Hermitian O = 0.9 H/||H||, 2N x 2N"}[kind]
+                      "perm": "n x n block of a 2n Haar unitary", "tor": "random Hermitian O = 0.9 H/||H||, 2N x 2N",
+                      "ltor": "random Hermitian O = 0.9 H/||H||, 2N x 2N, gamma = (g, g*) with g ~ 0.2 CN(0,1)",
+                      "mtl": "random complex symmetric 2n x 2n matrix / sqrt(8n)",
+                      "brs": "n x n block A of a 2n-mode Haar unitary, E = I - A^H A"}[kind]
             api = {"hafnian": "thewalrus_b200.hafnian(A)", "lhaf": "thewalrus_b200.hafnian(A, loop=True)",
-                   "perm": "thewalrus_b200.perm(A, method='glynn')", "tor": "thewalrus_b200.tor(O)"}[kind] + " with a host NumPy array"
+                   "perm": "thewalrus_b200.perm(A, method='glynn')", "tor": "thewalrus_b200.tor(O)",
+                   "ltor": "thewalrus_b200.ltor(O, gamma)", "mtl": "thewalrus_b200.mtl(A)",
+                   "brs": "thewalrus_b200.brs(A, E)"}[kind] + " with a host NumPy array"
         line = {
             "metric": metric_name(args.workload),
             "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "n": n, "units_per_step": units,
-                       "units": "photon-number patterns" if is_gbs else "subsets (reference `steps`)",
+                       "units": ("photon-number patterns" if is_gbs else "photon-number samples (accepted or not)"
+                                 if kind == "hsample" else "subsets (reference `steps`)"),
                        "input": cfg_in,
                        "parallelism": (f"pattern shards x{world}, one all-gather" if is_gbs else f"subset-index shards x{world}, one all-reduce"),
                        "l2_flush": True,
@@ -469,7 +651,7 @@ def main():
             "result": {"re": res.real, "im": res.imag, "e2e_re": complex(r_e2e).real},
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(kind, n, X)
+            line["cpu_baseline"] = cpu_baseline(kind, n, X, cutoff=args.cutoff)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

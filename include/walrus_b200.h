@@ -31,6 +31,10 @@ extern "C" {
 const char* wb200_last_error(void);
 int wb200_version(void);
 int wb200_device_count(int* count);
+/* The *_host wrappers keep their device scratch in a thread-local cache between calls (a wrapper called once per
+ * sampler mode or per pattern batch would otherwise spend more time in cudaMalloc/cudaFree than in its kernel).
+ * This returns the calling thread's idle blocks to the driver. */
+int wb200_release_scratch(void);
 
 /* FP64 pipe micro-benchmark used as the roofline denominator (MEASURED_PEAKS.json has no FP64 entry).
  * kind 0 = DFMA chains, 1 = DMMA m8n8k4 chains.  Result in TFLOP/s. */

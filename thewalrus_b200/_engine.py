@@ -254,6 +254,14 @@ def lhaf_batch_gamma_range(Ax, Dx, edge_reps, odd_variant, cutoff_extra, glynn, 
     return out
 
 
+kernel_ms_log = None   # set to a list to collect the kernel times the *_host entry points report (bench.py)
+
+
+def _log_ms(ms):
+    if kernel_ms_log is not None:
+        kernel_ms_log.append(ms.value)
+
+
 def mtl_range(A, zeta, p0, p1, device=None):
     """Partial montrealer sums over subset labels [p0, p1) -> 8 doubles (V and W partials, see the header)."""
     lib = _lib.load()
@@ -263,8 +271,10 @@ def mtl_range(A, zeta, p0, p1, device=None):
     if zeta is not None:
         zeta, pz = _lib.as_c128(zeta)
     out = np.zeros(8)
-    rc = lib.wb200_mtl_host(idx, pA, pz, A.shape[0] // 2, p0, p1, _lib.dptr(out), None)
+    ms = ctypes.c_double(0.0)
+    rc = lib.wb200_mtl_host(idx, pA, pz, A.shape[0] // 2, p0, p1, _lib.dptr(out), ctypes.byref(ms))
     _lib.check(rc, "wb200_mtl_host")
+    _log_ms(ms)
     return out
 
 
@@ -277,8 +287,10 @@ def brs_range(A, E, j0, j1, device=None):
     if E is not None:
         E, pE = _lib.as_c128(E)
     out = np.zeros(4)
-    rc = lib.wb200_brs_host(idx, pA, pE, A.shape[0], A.shape[1], j0, j1, _lib.dptr(out), None)
+    ms = ctypes.c_double(0.0)
+    rc = lib.wb200_brs_host(idx, pA, pE, A.shape[0], A.shape[1], j0, j1, _lib.dptr(out), ctypes.byref(ms))
     _lib.check(rc, "wb200_brs_host")
+    _log_ms(ms)
     return out
 
 
@@ -307,6 +319,7 @@ def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False, g
                                             rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B,
                                             1 if glynn else 0, _lib.dptr(out.view(np.float64)), ctypes.byref(ms))
     _lib.check(rc, "wb200_lhaf_patterns_multi_host")
+    _log_ms(ms)
     return (out, ms.value) if want_ms else out
 
 

@@ -24,6 +24,7 @@ SIGNATURES = {
     "wb200_last_error": (ctypes.c_char_p, []),
     "wb200_version": (ctypes.c_int, []),
     "wb200_device_count": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)]),
+    "wb200_release_scratch": (ctypes.c_int, []),
     "wb200_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, _c_double_p]),
     "wb200_hafnian_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),
     "wb200_hafnian_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _u64, _u64, _vp, _vp, ctypes.c_size_t, _vp]),

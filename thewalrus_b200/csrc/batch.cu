@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) mtl_kernel(MtlParams p) {
 
 struct DevBufB {
     void* p = nullptr;
-    ~DevBufB() { if (p) cudaFree(p); }
+    ~DevBufB() { if (p) pool_free(p); }
 };
 struct EvPair {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -675,24 +675,24 @@ extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
     DevBufB dA, dD, dgi, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
-    WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * nv * nv));
+    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * nv * nv));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * nv * nv, cudaMemcpyHostToDevice));
     if (gamma) {
-        WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * (size_t)n_gamma * nv));
+        WB_POOL(pool_alloc(&dD.p, sizeof(double2) * (size_t)n_gamma * nv));
         WB_CUDA(cudaMemcpy(dD.p, gamma, sizeof(double2) * (size_t)n_gamma * nv, cudaMemcpyHostToDevice));
         if (gamma_index) {
-            WB_CUDA(cudaMalloc(&dgi.p, sizeof(int32_t) * (size_t)B));
+            WB_POOL(pool_alloc(&dgi.p, sizeof(int32_t) * (size_t)B));
             WB_CUDA(cudaMemcpy(dgi.p, gamma_index, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice));
         }
     }
-    WB_CUDA(cudaMalloc(&drpt.p, sizeof(int32_t) * (size_t)B * nv));
+    WB_POOL(pool_alloc(&drpt.p, sizeof(int32_t) * (size_t)B * nv));
     WB_CUDA(cudaMemcpy(drpt.p, rpt, sizeof(int32_t) * (size_t)B * nv, cudaMemcpyHostToDevice));
-    WB_CUDA(cudaMalloc(&ddesc.p, sizeof(PatDesc) * (size_t)B));
-    WB_CUDA(cudaMalloc(&dnch.p, sizeof(unsigned int) * (size_t)B));
-    WB_CUDA(cudaMalloc(&dcoff.p, sizeof(unsigned long long) * ((size_t)B + 1)));
-    WB_CUDA(cudaMalloc(&dmeta.p, sizeof(PatMeta)));
-    WB_CUDA(cudaMalloc(&dcounter.p, sizeof(unsigned long long)));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double2) * (size_t)B));
+    WB_POOL(pool_alloc(&ddesc.p, sizeof(PatDesc) * (size_t)B));
+    WB_POOL(pool_alloc(&dnch.p, sizeof(unsigned int) * (size_t)B));
+    WB_POOL(pool_alloc(&dcoff.p, sizeof(unsigned long long) * ((size_t)B + 1)));
+    WB_POOL(pool_alloc(&dmeta.p, sizeof(PatMeta)));
+    WB_POOL(pool_alloc(&dcounter.p, sizeof(unsigned long long)));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double2) * (size_t)B));
     WB_CUDA(cudaMemset(dmeta.p, 0, sizeof(PatMeta)));
     WB_CUDA(cudaMemset(dcounter.p, 0, sizeof(unsigned long long)));
     EvPair ev;
@@ -718,7 +718,7 @@ extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const
         p.smax = 2 * meta.maxE; p.T = meta.maxN / 2; p.O = meta.anyOdd ? meta.maxN : meta.maxN / 2;
         p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p;
         p.nchunks = nchunks; p.counter = (unsigned long long*)dcounter.p;
-        WB_CUDA(cudaMalloc(&dpartial.p, sizeof(double) * 4 * (size_t)nchunks));
+        WB_POOL(pool_alloc(&dpartial.p, sizeof(double) * 4 * (size_t)nchunks));
         p.partial = (double*)dpartial.p;
         const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
         int ctas = 1;
@@ -792,9 +792,9 @@ extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const d
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
     DevBufB dA, dD, dpart, dout;
-    WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * n * n));
+    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * n * n));
     WB_CUDA(cudaMemcpy(dA.p, Ax, sizeof(double2) * n * n, cudaMemcpyHostToDevice));
-    WB_CUDA(cudaMalloc(&dD.p, sizeof(double2) * (size_t)n * n_D));
+    WB_POOL(pool_alloc(&dD.p, sizeof(double2) * (size_t)n * n_D));
     WB_CUDA(cudaMemcpy(dD.p, Dx, sizeof(double2) * (size_t)n * n_D, cudaMemcpyHostToDevice));
     p.A = (const double2*)dA.p; p.D = (const double2*)dD.p;
     const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
@@ -809,9 +809,9 @@ extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const d
     const size_t rows = (size_t)p.length * n_D;                 // independent outputs
     while (grid > 1 && rows * (size_t)grid * wpc * 32 > ((size_t)1 << 31)) grid /= 2;   // bound the partial table (2 GiB)
     const int nwarps = grid * wpc;
-    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * rows * nwarps));
+    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 4 * rows * nwarps));
     WB_CUDA(cudaMemset(dpart.p, 0, sizeof(double) * 4 * rows * nwarps));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4 * rows));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4 * rows));
     p.partials = (double*)dpart.p;
     EvPair ev;
     WB_CUDA(cudaEventCreate(&ev.e0));
@@ -850,7 +850,7 @@ extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, i
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
     DevBufB dA, dz, dzc, dpart, dout;
-    WB_CUDA(cudaMalloc(&dA.p, sizeof(double2) * n2 * n2));
+    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * n2 * n2));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * n2 * n2, cudaMemcpyHostToDevice));
     MtlParams p;
     memset(&p, 0, sizeof(p));
@@ -858,8 +858,8 @@ extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, i
     if (zeta) {
         double zc[2 * BW_NVMAX];
         for (int i = 0; i < n2; ++i) { zc[2 * i] = zeta[2 * i]; zc[2 * i + 1] = -zeta[2 * i + 1]; }
-        WB_CUDA(cudaMalloc(&dz.p, sizeof(double2) * n2));
-        WB_CUDA(cudaMalloc(&dzc.p, sizeof(double2) * n2));
+        WB_POOL(pool_alloc(&dz.p, sizeof(double2) * n2));
+        WB_POOL(pool_alloc(&dzc.p, sizeof(double2) * n2));
         WB_CUDA(cudaMemcpy(dz.p, zeta, sizeof(double2) * n2, cudaMemcpyHostToDevice));
         WB_CUDA(cudaMemcpy(dzc.p, zc, sizeof(double2) * n2, cudaMemcpyHostToDevice));
         p.zeta = (const double2*)dz.p; p.zetac = (const double2*)dzc.p;
@@ -874,8 +874,8 @@ extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, i
     const uint64_t want = (p1 - p0 + wpc - 1) / wpc;
     if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
     const int nwarps = grid * wpc;
-    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 8 * nwarps));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 8));
+    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 8 * nwarps));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 8));
     p.partials = (double*)dpart.p;
     EvPair ev;
     WB_CUDA(cudaEventCreate(&ev.e0));

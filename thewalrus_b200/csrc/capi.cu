@@ -39,6 +39,71 @@ int device_sm_count(int device, int* sms) {
     return WB200_OK;
 }
 
+// ---- caching device allocator ------------------------------------------------------------------
+namespace {
+struct PoolBlock {
+    void* p;
+    size_t bytes;
+    int device;
+    bool busy;
+};
+struct Pool {
+    PoolBlock blk[64];
+    int n = 0;
+};
+thread_local Pool g_pool;
+}  // namespace
+
+int pool_alloc(void** p, size_t bytes) {
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (bytes < 256) bytes = 256;
+    Pool& pl = g_pool;
+    int best = -1;
+    for (int i = 0; i < pl.n; ++i) {
+        const PoolBlock& b = pl.blk[i];
+        if (b.busy || b.device != dev || b.bytes < bytes) continue;
+        if (best < 0 || b.bytes < pl.blk[best].bytes) best = i;
+    }
+    if (best >= 0 && pl.blk[best].bytes <= 4 * bytes + (1u << 20)) {   // do not pin a huge block under a tiny request
+        pl.blk[best].busy = true;
+        *p = pl.blk[best].p;
+        return WB200_OK;
+    }
+    // round up so that slowly growing requests (one more mode per sampler step) keep hitting the same block
+    size_t want = 256;
+    while (want < bytes) want <<= 1;
+    if (want > (64u << 20)) want = (bytes + (16u << 20) - 1) / (16u << 20) * (16u << 20);
+    int slot = -1;
+    if (pl.n < 64) slot = pl.n++;
+    else {
+        for (int i = 0; i < pl.n; ++i)                                     // table full: recycle the smallest idle block
+            if (!pl.blk[i].busy && (slot < 0 || pl.blk[i].bytes < pl.blk[slot].bytes)) slot = i;
+        if (slot >= 0) {
+            int cur = dev;
+            if (pl.blk[slot].device != cur) cudaSetDevice(pl.blk[slot].device);
+            cudaFree(pl.blk[slot].p);
+            if (pl.blk[slot].device != cur) cudaSetDevice(cur);
+        }
+    }
+    void* q = nullptr;
+    WB_CUDA(cudaMalloc(&q, want));
+    if (slot < 0) {                                                        // every block is in use: untracked allocation
+        *p = q;
+        return WB200_OK;
+    }
+    pl.blk[slot] = PoolBlock{q, want, dev, true};
+    *p = q;
+    return WB200_OK;
+}
+
+void pool_free(void* p) {
+    Pool& pl = g_pool;
+    for (int i = 0; i < pl.n; ++i)
+        if (pl.blk[i].p == p) { pl.blk[i].busy = false; return; }
+    cudaFree(p);   // untracked (table was full)
+}
+
 int check_perm_args(int n, int method, uint64_t k0, uint64_t k1);
 int perm_f64_dev(const double*, int, int, uint64_t, uint64_t, double*, void*, cudaStream_t);
 int perm_i64_dev(const int64_t*, int, int, uint64_t, uint64_t, unsigned long long*, cudaStream_t);
@@ -46,8 +111,8 @@ int perm_i64_dev(const int64_t*, int, int, uint64_t, uint64_t, unsigned long lon
 // RAII device scratch for the host-buffer wrappers
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) { WB_CUDA(cudaMalloc(&p, bytes ? bytes : 8)); return WB200_OK; }
+    ~DevBuf() { if (p) pool_free(p); }
+    int alloc(size_t bytes) { return pool_alloc(&p, bytes); }
 };
 struct Timer {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -206,5 +271,20 @@ extern "C" int wb200_perm_int64_host(int device, const int64_t* M, int n, int me
     if (rc) return rc;
     if (tm.stop(0, kernel_ms)) return WB200_ECUDA;
     WB_CUDA(cudaMemcpy(out, dout.p, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    return WB200_OK;
+}
+
+extern "C" int wb200_release_scratch(void) {
+    Pool& pl = g_pool;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    int kept = 0;
+    for (int i = 0; i < pl.n; ++i) {
+        if (pl.blk[i].busy) { pl.blk[kept++] = pl.blk[i]; continue; }
+        cudaSetDevice(pl.blk[i].device);
+        cudaFree(pl.blk[i].p);
+    }
+    pl.n = kept;
+    cudaSetDevice(cur);
     return WB200_OK;
 }

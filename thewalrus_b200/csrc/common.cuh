@@ -19,6 +19,18 @@ void set_error(const char* fmt, ...);
         }                                                                                  \
     } while (0)
 
+// Caching device allocator behind the *_host wrappers (capi.cu): a thread-local free list per device, so a
+// wrapper that is called in a loop (one call per mode of a sampler chain, one per pattern batch) pays for
+// cudaMalloc / cudaFree only the first time.  Blocks return to the list when the wrapper's RAII buffers go out
+// of scope, i.e. after its final synchronous copy; wb200_release_scratch() gives them back to the driver.
+int pool_alloc(void** p, size_t bytes);
+void pool_free(void* p);
+#define WB_POOL(call)                       \
+    do {                                    \
+        int rc__ = (call);                  \
+        if (rc__ != WB200_OK) return rc__;  \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // error-free transformations; compiled without fast-math so the compiler keeps them
 // ---------------------------------------------------------------------------------------------

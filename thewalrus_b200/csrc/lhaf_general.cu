@@ -254,7 +254,7 @@ static size_t lg_smem_bytes(int n) {
 
 struct DevBufLg {
     void* p = nullptr;
-    ~DevBufLg() { if (p) cudaFree(p); }
+    ~DevBufLg() { if (p) pool_free(p); }
 };
 
 }  // namespace wb
@@ -296,14 +296,14 @@ extern "C" int wb200_lhaf_general_host(int device, const double* A, const double
     if ((has_odd ? N : N / 2) > LG_MAX_ORDER) { set_error("lhaf_general: photon number %d too large", N); return WB200_ENOSUP; }
     WB_CUDA(cudaSetDevice(device));
     DevBufLg dA, dD, dV, dout, dpart;
-    WB_CUDA(cudaMalloc(&dA.p, sizeof(double) * 2 * n * n));
+    WB_POOL(pool_alloc(&dA.p, sizeof(double) * 2 * n * n));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double) * 2 * n * n, cudaMemcpyHostToDevice));
     if (D) {
-        WB_CUDA(cudaMalloc(&dD.p, sizeof(double) * 2 * n));
+        WB_POOL(pool_alloc(&dD.p, sizeof(double) * 2 * n));
         WB_CUDA(cudaMemcpy(dD.p, D, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
     }
     if (has_odd) {
-        WB_CUDA(cudaMalloc(&dV.p, sizeof(double) * 2 * n));
+        WB_POOL(pool_alloc(&dV.p, sizeof(double) * 2 * n));
         WB_CUDA(cudaMemcpy(dV.p, oddV, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
         p.oddloop = make_double2(oddloop[0], oddloop[1]);
     }
@@ -317,8 +317,8 @@ extern "C" int wb200_lhaf_general_host(int device, const double* A, const double
     if (occ < 1) occ = 1;
     uint64_t total = j1 - j0, maxgrid = (uint64_t)sms * occ;
     int grid = (int)(total < maxgrid ? (total ? total : 1) : maxgrid);
-    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * grid));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4));
+    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 4 * grid));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
     cudaEvent_t e0, e1;
     WB_CUDA(cudaEventCreate(&e0));
     WB_CUDA(cudaEventCreate(&e1));

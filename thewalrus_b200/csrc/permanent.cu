@@ -523,11 +523,11 @@ extern "C" int wb200_brs_host(int device, const double* A, const double* E, int 
     WB_CUDA(cudaSetDevice(device));
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    struct Buf { void* p = nullptr; ~Buf() { if (p) cudaFree(p); } } dA, dE, dpart, dout;
-    WB_CUDA(cudaMalloc(&dA.p, sizeof(C128) * m * n));
+    struct Buf { void* p = nullptr; ~Buf() { if (p) pool_free(p); } } dA, dE, dpart, dout;
+    WB_POOL(pool_alloc(&dA.p, sizeof(C128) * m * n));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(C128) * m * n, cudaMemcpyHostToDevice));
     if (E) {
-        WB_CUDA(cudaMalloc(&dE.p, sizeof(C128) * n * n));
+        WB_POOL(pool_alloc(&dE.p, sizeof(C128) * n * n));
         WB_CUDA(cudaMemcpy(dE.p, E, sizeof(C128) * n * n, cudaMemcpyHostToDevice));
     }
     BrsParams p;
@@ -542,9 +542,9 @@ extern "C" int wb200_brs_host(int device, const double* A, const double* E, int 
     int grid = (int)((units + BRS_WARPS - 1) / BRS_WARPS);
     if (grid > sms * 2) grid = sms * 2;
     if (grid < 1) grid = 1;
-    WB_CUDA(cudaMalloc(&dpart.p, sizeof(double) * 4 * grid * BRS_WARPS));
+    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 4 * grid * BRS_WARPS));
     WB_CUDA(cudaMemset(dpart.p, 0, sizeof(double) * 4 * grid * BRS_WARPS));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
     p.partials = (double*)dpart.p;
     cudaEvent_t e0, e1;
     WB_CUDA(cudaEventCreate(&e0));

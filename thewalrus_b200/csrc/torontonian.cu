@@ -284,7 +284,7 @@ static void tor_shape(int N, int* P, int* g, int* DC) {
 
 struct DevBufT {
     void* p = nullptr;
-    ~DevBufT() { if (p) cudaFree(p); }
+    ~DevBufT() { if (p) pool_free(p); }
 };
 
 }  // namespace wb
@@ -375,12 +375,12 @@ static int tor_host_impl(int device, const double* O, const double* gamma, int n
     WB_CUDA(cudaSetDevice(device));
     DevBufT dO, dG, dws, dout;
     const size_t wsb = wb200_tor_workspace_bytes(n_modes);
-    WB_CUDA(cudaMalloc(&dO.p, sizeof(double) * 2 * n2 * n2));
-    WB_CUDA(cudaMalloc(&dws.p, wsb));
-    WB_CUDA(cudaMalloc(&dout.p, sizeof(double) * 4));
+    WB_POOL(pool_alloc(&dO.p, sizeof(double) * 2 * n2 * n2));
+    WB_POOL(pool_alloc(&dws.p, wsb));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
     WB_CUDA(cudaMemcpy(dO.p, O, sizeof(double) * 2 * n2 * n2, cudaMemcpyHostToDevice));
     if (gamma) {
-        WB_CUDA(cudaMalloc(&dG.p, sizeof(double) * 2 * n2));
+        WB_POOL(pool_alloc(&dG.p, sizeof(double) * 2 * n2));
         WB_CUDA(cudaMemcpy(dG.p, gamma, sizeof(double) * 2 * n2, cudaMemcpyHostToDevice));
     }
     cudaEvent_t e0, e1;
