@@ -255,7 +255,7 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
         co.perm_range(X, 0, 0, sample)
         dt = time.perf_counter() - t0
         what = f"first {sample} of {1 << (n - 1)} Gray-code steps (the reference itself is single-threaded; the port splits the range over threads)"
-    elif kind == "tor":
+    elif kind == "tor" and n <= 48:
         N = n // 2
         sample = 1 << N
         t0 = time.perf_counter()
@@ -263,16 +263,18 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
         dt = time.perf_counter() - t0
         threads = 1
         what = "full recursive torontonian (single thread, as the reference)"
-    elif kind in ("ltor", "mtl", "brs"):
+    elif kind in ("tor", "ltor", "mtl", "brs"):   # tor: only beyond 24 modes, where the full recursion takes > 10 min
         from oracle import walrus_oracle as wo
 
-        total = 1 << (n // 2 if kind == "ltor" else n)
+        total = 1 << (n // 2 if kind in ("tor", "ltor") else n)
         j0, sample, dt = total // 3, 0, 0.0       # a window in the middle of the index space: typical subset sizes
-        step = {"ltor": 2000, "mtl": 2000, "brs": 8}[kind]
+        step = {"tor": 2000, "ltor": 2000, "mtl": 2000, "brs": 8}[kind]
         t0 = time.perf_counter()
         while dt < seconds and j0 + sample < total:
             a, b = j0 + sample, min(total, j0 + sample + step)
-            if kind == "ltor":
+            if kind == "tor":
+                wo.tor_direct(X, a, b)
+            elif kind == "ltor":
                 wo.ltor_direct(X[0], X[1], a, b)
             elif kind == "mtl":
                 wo.montrealer(np.vstack([X[n:], X[:n]]), None, a, b)     # Xmat(n) @ A, as mtl does

@@ -21,8 +21,6 @@ constexpr int TOR_THREADS = 256;
 constexpr int TOR_DC = 9;        // modes expanded breadth-first inside a CTA
 constexpr int TOR_G = 5;         // log2(prefixes per CTA)
 constexpr int TOR_MAX_MODES = 32;
-constexpr int TOR_BUF = 2304;       // max over BFS levels of nodes * dim^2, DC = 9: 64 nodes of 6 x 6
-constexpr int TOR_BUF_LOOP = 3200;  // bordered nodes: 128 nodes of 5 x 5
 
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
     return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
@@ -57,48 +55,58 @@ __global__ void tor_prep_kernel(const double2* __restrict__ O, const double2* __
     }
 }
 
-// In-place elimination of the leading mode (rows/cols off, off+1) of the dim x dim matrix T (stride ld).
-// Returns d1 * d2.  All threads of the CTA participate.
-__device__ double eliminate_mode(double2* T, int ld, int off, int dim) {
-    const int tid = threadIdx.x;
-    // pivot 1
-    const double d1 = T[off * ld + off].x;
-    const double i1 = 1.0 / d1;
+// Lower-triangle enumeration: el -> (r, c), r >= c, el = r (r + 1) / 2 + c.
+__device__ __forceinline__ void tri_decode(int el, int& r, int& c) {
+    int rr = (int)((__fsqrt_rn((float)(8 * el + 1)) - 1.0f) * 0.5f);
+    while (rr * (rr + 1) / 2 > el) --rr;
+    while ((rr + 1) * (rr + 2) / 2 <= el) ++rr;
+    r = rr;
+    c = el - rr * (rr + 1) / 2;
+}
+
+// One entry of the Schur complement of the leading mode (rows/cols 0, 1) of the Hermitian matrix P (stride ld):
+// both scalar pivots fused.  Reads only the lower triangle of P (columns 0, 1 and the entry itself), so it can
+// run in place.  r, c >= 2 index P.
+__device__ __forceinline__ double2 schur_entry(const double2* P, int ld, int r, int c, double2 e, double i1, double i2) {
+    double2 v = P[r * ld + c];
+    const double2 a = P[r * ld], b = P[c * ld];
+    double2 ur = P[r * ld + 1], uc = P[c * ld + 1];
+    { const double2 q = cmulc(a, e); ur.x -= q.x * i1; ur.y -= q.y * i1; }
+    { const double2 q = cmulc(b, e); uc.x -= q.x * i1; uc.y -= q.y * i1; }
+    { const double2 q = cmulc(a, b); v.x -= q.x * i1; v.y -= q.y * i1; }
+    { const double2 q = cmulc(ur, uc); v.x -= q.x * i2; v.y -= q.y * i2; }
+    return v;
+}
+
+// Eliminate the leading mode of P (dim x dim, stride ld) into Q (stride ldq; Q may be P + 2 (ld + 1) with ldq = ld:
+// in place).  Lower triangle only.  All threads of the CTA take part; returns d1 * d2.
+__device__ double eliminate_into(const double2* P, int ld, int dim, double2* Q, int ldq) {
     __syncthreads();
-    for (int idx = tid; idx < (dim - off - 1) * (dim - off - 1); idx += TOR_THREADS) {
-        const int r = off + 1 + idx / (dim - off - 1), c = off + 1 + idx % (dim - off - 1);
-        if (c == off + 1 || r >= off + 2) {  // column off+1 (needed for pivot 2) and the trailing block
-            double2 a = T[r * ld + off], b = T[c * ld + off];
-            double2 pr = cmulc(a, b);
-            T[r * ld + c].x -= pr.x * i1;
-            T[r * ld + c].y -= pr.y * i1;
-        }
-    }
-    __syncthreads();
-    const double d2 = T[(off + 1) * ld + off + 1].x;
-    const double i2 = 1.0 / d2;
-    __syncthreads();
-    for (int idx = tid; idx < (dim - off - 2) * (dim - off - 2); idx += TOR_THREADS) {
-        const int r = off + 2 + idx / (dim - off - 2), c = off + 2 + idx % (dim - off - 2);
-        double2 a = T[r * ld + off + 1], b = T[c * ld + off + 1];
-        double2 pr = cmulc(a, b);
-        T[r * ld + c].x -= pr.x * i2;
-        T[r * ld + c].y -= pr.y * i2;
+    const double d1 = P[0].x, i1 = 1.0 / d1;
+    const double2 e = P[ld];
+    const double d2 = P[ld + 1].x - (e.x * e.x + e.y * e.y) * i1, i2 = 1.0 / d2;
+    const int cd = dim - 2, tri = cd * (cd + 1) / 2;
+    for (int el = threadIdx.x; el < tri; el += TOR_THREADS) {
+        int r, c;
+        tri_decode(el, r, c);
+        Q[r * ldq + c] = schur_entry(P, ld, r + 2, c + 2, e, i1, i2);
     }
     __syncthreads();
     return d1 * d2;
 }
 
 struct TorParams {
-    const double2* B;   // interleaved I - O, 2N x 2N
+    const double2* B;   // interleaved (bordered) I - O
     int N, P, g, DC;    // modes, prefix modes, log2 prefixes per CTA, BFS modes
+    int off_depth, off_pool, off_desc;   // shared-memory layout, in double2 units from the start
     uint64_t p0, p1;
 };
 
-// finish a 2-mode (4x4 Hermitian) node in registers: 4 subsets
-__device__ __forceinline__ double tail2(const double2* T, double det, double sgn) {
-    const double t00 = T[0].x, t11 = T[5].x, t22 = T[10].x, t33 = T[15].x;
-    const double2 t10 = T[4], t20 = T[8], t30 = T[12], t21 = T[9], t31 = T[13], t32 = T[14];
+// finish a 2-mode (4x4 Hermitian, stride ld, lower triangle) node in registers: 4 subsets
+__device__ __forceinline__ double tail2(const double2* T, int ld, double det, double sgn) {
+    const double t00 = T[0].x, t11 = T[ld + 1].x, t22 = T[2 * ld + 2].x, t33 = T[3 * ld + 3].x;
+    const double2 t10 = T[ld], t20 = T[2 * ld], t30 = T[3 * ld], t21 = T[2 * ld + 1], t31 = T[3 * ld + 1],
+                  t32 = T[3 * ld + 2];
     double sum = sgn / sqrt(det);                                    // {}: two exclusions, sign unchanged
     const double detB = t22 * t33 - (t32.x * t32.x + t32.y * t32.y);  // {m1}
     sum -= sgn / sqrt(det * detB);
@@ -135,13 +143,13 @@ __device__ __forceinline__ double pivot5(double2 (&a)[5][5]) {
     return d;
 }
 
-// loop torontonian: finish a 2-mode bordered (5x5) node, 4 subsets; exponent = -corner / 2
-__device__ __forceinline__ double tail2_loop(const double2* T, double det, double sgn) {
+// loop torontonian: finish a 2-mode bordered (5x5, stride ld) node, 4 subsets; exponent = -corner / 2
+__device__ __forceinline__ double tail2_loop(const double2* T, int ld, double det, double sgn) {
     double2 a[5][5];
 #pragma unroll
     for (int r = 0; r < 5; ++r)
 #pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = T[r * 5 + c];
+        for (int c = 0; c <= r; ++c) a[r][c] = T[r * ld + c];
     double sum = sgn * exp(-0.5 * a[4][4].x) / sqrt(det);                     // {}
     {                                                                         // {m1}: pivots 2, 3
         const double d1 = a[2][2].x, i1 = 1.0 / d1;
@@ -162,110 +170,150 @@ __device__ __forceinline__ double tail2_loop(const double2* T, double det, doubl
     return sum;
 }
 
+// Row stride of a stored dim x dim matrix: odd, so that the column reads P[r * ld] / P[r * ld + 1] of a quarter
+// warp (8 lanes x 16 bytes) fall in 8 different 16-byte bank groups instead of one.
+__host__ __device__ __forceinline__ int tor_ld(int dim) { return dim | 1; }
+
+constexpr int TOR_MAXG = 5;
+constexpr int TOR_MAXNODES = 128;   // 2-mode tail nodes of a 9-mode breadth-first expansion
+
+// Shared-memory plan (double2 units): T (n2^2) | depth buffers of the prefix DFS | include-children pool of the
+// breadth-first expansion | node descriptors.  Returns the total in bytes.
+__host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, int* off_depth, int* off_pool, int* off_desc) {
+    const int n2 = 2 * N + aug, dg = 2 * (DC + g) + aug;
+    int off = n2 * tor_ld(n2);
+    *off_depth = off;
+    for (int k = 1; k <= g; ++k) off += (dg - 2 * k) * tor_ld(dg - 2 * k);
+    *off_pool = off;
+    for (int l = 0, dim = 2 * DC + aug; dim > 4 + aug; ++l, dim -= 2) off += (1 << l) * (dim - 2) * tor_ld(dim - 2);
+    *off_desc = off;
+    // descriptors: 2 x (ptr, ld) int + 2 x (det, sgn) double per node, ping-pong, + inv1/inv2 per parent
+    const size_t desc = (size_t)TOR_MAXNODES * (2 * 2 * sizeof(int) + 2 * 2 * sizeof(double)) + 2 * 64 * sizeof(double);
+    return (size_t)off * sizeof(double2) + desc;
+}
+
 // AUG = 0: torontonian; AUG = 1: loop torontonian (every matrix carries the border row/column).
+//
+// v2 of the tree walk.  Every node of the subset tree is a VIEW (offset, stride) of some stored Hermitian matrix
+// of which only the lower triangle is valid:
+//   * excluding the leading mode is free: the child is the parent's view advanced by two rows and columns;
+//   * including it writes the Schur complement (both pivots fused, lower triangle only) into fresh storage.
+// The first P - g modes (bits of the group id) are walked in place on T.  The next g modes select one of 2^g
+// prefixes; they are visited in index order as a depth-first walk with one buffer per depth, so stepping to the
+// next prefix costs ONE elimination (the level whose bit turns 0 -> 1; the levels below restart as exclusions).
+// The last DC modes are expanded breadth-first: level l has 2^l nodes, each served by 256 / 2^l threads, the
+// included children go to a pool that stays alive until the 2-mode tails have been summed in registers.
 template <int AUG>
 __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* __restrict__ partials) {
     extern __shared__ __align__(16) double smem_tor[];
     const int N = p.N, n2 = 2 * N + AUG, DC = p.DC, g = p.g, P = p.P;
-    const int dg = 2 * (DC + g) + AUG;
-    double2* T = reinterpret_cast<double2*>(smem_tor);   // n2 x n2
-    double2* T0 = T + n2 * n2;                            // dg x dg
-    double2* W = T0 + dg * dg;                            // dg x dg
-    double2* bufA = W + dg * dg;
-    constexpr int bufsz = AUG ? TOR_BUF_LOOP : TOR_BUF;   // max level size for DC = 9 (see host)
-    double2* bufB = bufA + bufsz;
-    double* detA = reinterpret_cast<double*>(bufB + bufsz);  // 256 each: det, sgn ping-pong; inv1, inv2
-    double* sgnA = detA + 256;
-    double* detB = sgnA + 256;
-    double* sgnB = detB + 256;
-    double* inv1 = sgnB + 256;
-    double* inv2 = inv1 + 256;
+    const int dg = 2 * (DC + g) + AUG, ldT = tor_ld(n2);
+    double2* S = reinterpret_cast<double2*>(smem_tor);
+    int* ptrA = reinterpret_cast<int*>(S + p.off_desc);
+    int* ldA = ptrA + TOR_MAXNODES;
+    int* ptrB = ldA + TOR_MAXNODES;
+    int* ldB = ptrB + TOR_MAXNODES;
+    double* detA = reinterpret_cast<double*>(ldB + TOR_MAXNODES);
+    double* sgnA = detA + TOR_MAXNODES;
+    double* detB = sgnA + TOR_MAXNODES;
+    double* sgnB = detB + TOR_MAXNODES;
+    double* inv1 = sgnB + TOR_MAXNODES;
+    double* inv2 = inv1 + 64;
     const int tid = threadIdx.x;
 
     dd acc = {0.0, 0.0};
     const uint64_t ngroups_first = p.p0 >> g, ngroups_last = (p.p1 + (1ull << g) - 1) >> g;
     for (uint64_t grp = ngroups_first + blockIdx.x; grp < ngroups_last; grp += gridDim.x) {
-        // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0)
+        // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0), in place on T
         __syncthreads();
-        for (int idx = tid; idx < n2 * n2; idx += TOR_THREADS) T[idx] = p.B[idx];
-        __syncthreads();
+        for (int idx = tid; idx < n2 * n2; idx += TOR_THREADS) S[(idx / n2) * ldT + idx % n2] = p.B[idx];
         double det0 = 1.0, sgn0 = 1.0;
         const int lead = P - g;
         for (int i = 0; i < lead; ++i) {
             const bool inc = (grp >> (lead - 1 - i)) & 1ull;
-            if (inc) det0 *= eliminate_mode(T, n2, 2 * i, n2);
+            double2* V = S + 2 * i * (ldT + 1);
+            if (inc) det0 *= eliminate_into(V, ldT, n2 - 2 * i, V + 2 * (ldT + 1), ldT);
             else sgn0 = -sgn0;
         }
-        __syncthreads();
-        for (int idx = tid; idx < dg * dg; idx += TOR_THREADS) {
-            const int r = idx / dg, c = idx % dg;
-            T0[idx] = T[(2 * lead + r) * n2 + 2 * lead + c];
-        }
-        __syncthreads();
-        // ---- phase B: the G prefixes of this group
+        // ---- phase B: the 2^g prefixes of this group, depth-first
+        int nptr[TOR_MAXG + 1], nld[TOR_MAXG + 1];
+        double ndet[TOR_MAXG + 1], nsgn[TOR_MAXG + 1];
+        nptr[0] = 2 * lead * (ldT + 1); nld[0] = ldT; ndet[0] = det0; nsgn[0] = sgn0;
+#pragma unroll
+        for (int k = 1; k <= TOR_MAXG; ++k) { nptr[k] = 0; nld[k] = 1; ndet[k] = 1.0; nsgn[k] = 1.0; }
+        int cur = -1;
         for (int sub = 0; sub < (1 << g); ++sub) {
             const uint64_t pfx = (grp << g) + sub;
             if (pfx < p.p0 || pfx >= p.p1) continue;
-            __syncthreads();
-            for (int idx = tid; idx < dg * dg; idx += TOR_THREADS) W[idx] = T0[idx];
-            __syncthreads();
-            double det = det0, sgn = sgn0;
-            for (int i = 0; i < g; ++i) {
-                const bool inc = (sub >> (g - 1 - i)) & 1;
-                if (inc) det *= eliminate_mode(W, dg, 2 * i, dg);
-                else sgn = -sgn;
-            }
-            __syncthreads();
-            // level 0 node: trailing 2DC x 2DC block
-            int dim = 2 * DC + AUG;
-            for (int idx = tid; idx < dim * dim; idx += TOR_THREADS) {
-                const int r = idx / dim, c = idx % dim;
-                bufA[idx] = W[(2 * g + r) * dg + 2 * g + c];
-            }
-            if (tid == 0) { detA[0] = det; sgnA[0] = sgn; }
-            __syncthreads();
-            double2* cur = bufA; double2* nxt = bufB;
-            double* dcur = detA; double* scur = sgnA; double* dnxt = detB; double* snxt = sgnB;
-            int nodes = 1;
-            while (dim > 4 + AUG) {
-                const int cd = dim - 2;
-                // per-node pivots
-                for (int nd = tid; nd < nodes; nd += TOR_THREADS) {
-                    const double2* Tn = cur + nd * dim * dim;
-                    const double d1 = Tn[0].x, i1 = 1.0 / d1;
-                    const double2 e = Tn[dim];  // T[1][0]
-                    const double d2 = Tn[dim + 1].x - (e.x * e.x + e.y * e.y) * i1;
-                    inv1[nd] = i1; inv2[nd] = 1.0 / d2;
-                    dnxt[2 * nd] = dcur[nd]; snxt[2 * nd] = -scur[nd];            // exclude
-                    dnxt[2 * nd + 1] = dcur[nd] * d1 * d2; snxt[2 * nd + 1] = scur[nd];  // include
-                }
-                __syncthreads();
-                const int per = cd * cd;
-                for (int idx = tid; idx < nodes * 2 * per; idx += TOR_THREADS) {
-                    const int child = idx / per, el = idx % per;
-                    const int nd = child >> 1, r = el / cd + 2, c = el % cd + 2;
-                    const double2* Tn = cur + nd * dim * dim;
-                    double2 v = Tn[r * dim + c];
-                    if (child & 1) {
-                        const double i1 = inv1[nd], i2 = inv2[nd];
-                        const double2 a = Tn[r * dim], b = Tn[c * dim], e = Tn[dim];
-                        double2 ur = Tn[r * dim + 1], uc = Tn[c * dim + 1];
-                        { double2 q = cmulc(a, e); ur.x -= q.x * i1; ur.y -= q.y * i1; }
-                        { double2 q = cmulc(b, e); uc.x -= q.x * i1; uc.y -= q.y * i1; }
-                        { double2 q = cmulc(a, b); v.x -= q.x * i1; v.y -= q.y * i1; }
-                        { double2 q = cmulc(ur, uc); v.x -= q.x * i2; v.y -= q.y * i2; }
+            // levels before `first` are shared with the previously materialised prefix
+            const int first = cur < 0 ? 0 : g - (32 - __clz(sub ^ cur));
+            cur = sub;
+            int dbuf = p.off_depth;
+#pragma unroll
+            for (int lvl = 0; lvl < TOR_MAXG; ++lvl) {
+                if (lvl < g) {
+                    const int dim = dg - 2 * lvl, cdim = dim - 2, cld = tor_ld(cdim);
+                    if (lvl >= first) {
+                        const bool inc = (sub >> (g - 1 - lvl)) & 1;
+                        if (inc) {
+                            ndet[lvl + 1] = ndet[lvl] * eliminate_into(S + nptr[lvl], nld[lvl], dim, S + dbuf, cld);
+                            nsgn[lvl + 1] = nsgn[lvl];
+                            nptr[lvl + 1] = dbuf; nld[lvl + 1] = cld;
+                        } else {
+                            ndet[lvl + 1] = ndet[lvl]; nsgn[lvl + 1] = -nsgn[lvl];
+                            nptr[lvl + 1] = nptr[lvl] + 2 * (nld[lvl] + 1); nld[lvl + 1] = nld[lvl];
+                        }
                     }
-                    nxt[child * per + el] = v;
+                    dbuf += cdim * cld;
+                }
+            }
+            // ---- breadth-first expansion of the last DC modes
+            int rptr = nptr[0], rld = nld[0];
+            double rdet = ndet[0], rsgn = nsgn[0];
+#pragma unroll
+            for (int k = 1; k <= TOR_MAXG; ++k)
+                if (k == g) { rptr = nptr[k]; rld = nld[k]; rdet = ndet[k]; rsgn = nsgn[k]; }
+            __syncthreads();   // previous prefix's tails are done with the descriptors and the pool
+            if (tid == 0) { ptrA[0] = rptr; ldA[0] = rld; detA[0] = rdet; sgnA[0] = rsgn; }
+            int* pc = ptrA; int* lc = ldA; double* dc = detA; double* sc = sgnA;
+            int* pn = ptrB; int* ln = ldB; double* dn = detB; double* sn = sgnB;
+            int nodes = 1, shift = 8, pool = p.off_pool;
+            __syncthreads();
+            for (int dim = 2 * DC + AUG; dim > 4 + AUG; dim -= 2) {
+                const int cd = dim - 2, tri = cd * (cd + 1) / 2, cld = tor_ld(cd), csz = cd * cld;
+                const int nd = tid >> shift, lane = tid & ((1 << shift) - 1), step = 1 << shift;
+                const int myptr = pc[nd], myld = lc[nd];
+                const double2* Pn = S + myptr;
+                double2* Qn = S + pool + nd * csz;
+                if (lane == 0) {
+                    const double d1 = Pn[0].x, i1 = 1.0 / d1;
+                    const double2 e = Pn[myld];
+                    const double d2 = Pn[myld + 1].x - (e.x * e.x + e.y * e.y) * i1;
+                    inv1[nd] = i1; inv2[nd] = 1.0 / d2;
+                    const double dt = dc[nd], sg = sc[nd];
+                    pn[2 * nd] = myptr + 2 * (myld + 1); ln[2 * nd] = myld; dn[2 * nd] = dt; sn[2 * nd] = -sg;   // exclude
+                    pn[2 * nd + 1] = pool + nd * csz; ln[2 * nd + 1] = cld; dn[2 * nd + 1] = dt * d1 * d2; sn[2 * nd + 1] = sg;
                 }
                 __syncthreads();
-                { double2* t = cur; cur = nxt; nxt = t; }
-                { double* t = dcur; dcur = dnxt; dnxt = t; t = scur; scur = snxt; snxt = t; }
-                nodes *= 2; dim = cd;
+                {
+                    const double i1 = inv1[nd], i2 = inv2[nd];
+                    const double2 e = Pn[myld];
+                    for (int el = lane; el < tri; el += step) {
+                        int r, c;
+                        tri_decode(el, r, c);
+                        Qn[r * cld + c] = schur_entry(Pn, myld, r + 2, c + 2, e, i1, i2);
+                    }
+                }
+                __syncthreads();
+                pool += nodes * csz;
+                { int* t = pc; pc = pn; pn = t; t = lc; lc = ln; ln = t; }
+                { double* t = dc; dc = dn; dn = t; t = sc; sc = sn; sn = t; }
+                nodes *= 2; --shift;
             }
             // ---- 2-mode nodes finished by single threads
             for (int nd = tid; nd < nodes; nd += TOR_THREADS) {
-                if (AUG) dd_add(acc, tail2_loop(cur + nd * 25, dcur[nd], scur[nd]));
-                else dd_add(acc, tail2(cur + nd * 16, dcur[nd], scur[nd]));
+                if (AUG) dd_add(acc, tail2_loop(S + pc[nd], lc[nd], dc[nd], sc[nd]));
+                else dd_add(acc, tail2(S + pc[nd], lc[nd], dc[nd], sc[nd]));
             }
         }
     }
@@ -276,10 +324,13 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
     block_reduce_store(a2, red, partials);
 }
 
-static void tor_shape(int N, int* P, int* g, int* DC) {
+// DC modes expanded breadth-first, 2^g prefixes per CTA group; g shrinks if shared memory does not allow 5.
+static void tor_shape(int N, int aug, int* P, int* g, int* DC) {
     *DC = N < TOR_DC ? N : TOR_DC;
     *P = N - *DC;
     *g = *P < TOR_G ? *P : TOR_G;
+    int a, b, c;
+    while (*g > 0 && tor_smem_plan(N, aug, *g, *DC, &a, &b, &c) > 225 * 1024) --*g;
 }
 
 struct DevBufT {
@@ -297,7 +348,7 @@ extern "C" int wb200_tor_num_prefixes(int n_modes, uint64_t* count) {
         return (n_modes > TOR_MAX_MODES) ? WB200_ENOSUP : WB200_EINVAL;
     }
     int P, g, DC;
-    tor_shape(n_modes, &P, &g, &DC);
+    tor_shape(n_modes, 0, &P, &g, &DC);
     *count = 1ull << P;
     return WB200_OK;
 }
@@ -322,27 +373,21 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     if (rc) return rc;
     if (p0 > p1 || p1 > total) { set_error("tor: bad prefix range"); return WB200_EINVAL; }
     if (workspace_bytes < wb200_tor_workspace_bytes(n_modes)) { set_error("tor: workspace too small"); return WB200_EINVAL; }
-    const int N = n_modes, aug = dGamma ? 1 : 0, n2 = 2 * N + aug;
+    const int N = n_modes, aug = dGamma ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     TorParams p;
-    tor_shape(N, &p.P, &p.g, &p.DC);
+    tor_shape(N, aug, &p.P, &p.g, &p.DC);
     p.N = N; p.p0 = p0; p.p1 = p1;
+    const size_t shm = tor_smem_plan(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc);
     double2* dB = reinterpret_cast<double2*>(d_workspace);
     double* dpart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_workspace) + tor_ws_partials_offset(N));
     p.B = dB;
     int dev = 0, sms = 0;
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
-    const int dg = 2 * (p.DC + p.g) + aug;
-    const size_t shm = sizeof(double2) * ((size_t)n2 * n2 + 2 * (size_t)dg * dg + 2 * (aug ? TOR_BUF_LOOP : TOR_BUF)) +
-                       sizeof(double) * 6 * 256;
-    {
-        const int max_n2 = 2 * TOR_MAX_MODES + 1, max_dg = 2 * (TOR_DC + TOR_G) + 1;
-        const int max_shm = (int)(sizeof(double2) * ((size_t)max_n2 * max_n2 + 2 * (size_t)max_dg * max_dg + 2 * TOR_BUF_LOOP) +
-                                  sizeof(double) * 6 * 256);
-        if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
-        else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_shm));
-    }
+    if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
+    if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
     int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
     if (grid > TOR_MAX_GRID) grid = TOR_MAX_GRID;
