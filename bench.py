@@ -47,16 +47,18 @@ def make_input(workload):
         Q, R = np.linalg.qr(Z)
         U = Q * (np.diag(R) / np.abs(np.diag(R)))  # Haar phase fix (thewalrus/random.py:115-134)
         return kind, n, np.ascontiguousarray(U[:n, :n])
-    if kind in ("tor", "ltor"):  # n = 2N
+    if kind in ("tor", "ltor"):  # n = 2N: config 4 of SURVEY 8(d), all N detectors click
+        from thewalrus_b200.quantum import Qmat
+
         N = n // 2
-        rng = np.random.default_rng(1000 * 4 + n)
-        B = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
-        H = B @ B.conj().T
-        O = 0.9 * H / np.linalg.norm(H, 2)
-        if kind == "tor":
-            return kind, n, O
-        g = 0.2 * (rng.standard_normal(N) + 1j * rng.standard_normal(N))
-        return kind, n, (O, np.concatenate([g, g.conj()]))
+        # squeezing r = 1.5 instead of the 0.5 of config 3: with 0.2 photons per mode the all-click probability of 24
+        # modes is ~1e-18 and the alternating sum is pure rounding noise (in the reference too)
+        mu, cov, _ = make_gbs_state(N, 1, seed=1000 * 4 + n, r=1.5)
+        if kind == "tor":   # zero-mean state: threshold_detection_prob = tor(I - Q^-1) / sqrt(det Q)  (_torontonian.py:98-104)
+            return kind, n, np.ascontiguousarray(np.identity(n) - np.linalg.inv(Qmat(cov)))
+        sigma_inv = np.linalg.inv(Qmat(cov).conj())   # displaced state: the ltor arguments of _torontonian.py:106-120
+        alpha = np.concatenate([mu[:N] + 1j * mu[N:], mu[:N] - 1j * mu[N:]]) / 2.0
+        return kind, n, (np.ascontiguousarray(np.identity(n) - sigma_inv), (sigma_inv @ alpha).conj())
     if kind == "mtl":  # n = modes; 2n x 2n complex symmetric adjacency-like matrix
         rng = np.random.default_rng(1000 * 6 + n)
         G = rng.standard_normal((2 * n, 2 * n)) + 1j * rng.standard_normal((2 * n, 2 * n))
@@ -617,8 +619,8 @@ def main():
             Xs = X if isinstance(X, tuple) else (X,)
             h2d, d2h = int(sum(np.asarray(x).nbytes for x in Xs)), 32
             cfg_in = {"hafnian": "random complex symmetric G+G^T, seed 1000*config+n", "lhaf": "random complex symmetric G+G^T, loops = diagonal",
-                      "perm": "n x n block of a 2n Haar unitary", "tor": "random Hermitian O = 0.9 H/||H||, 2N x 2N",
-                      "ltor": "random Hermitian O = 0.9 H/||H||, 2N x 2N, gamma = (g, g*) with g ~ 0.2 CN(0,1)",
+                      "perm": "n x n block of a 2n Haar unitary", "tor": "O = I - Q^-1 of an N-mode GBS state (Haar interferometer, r=1.5, eta=0.8), all detectors click",
+                      "ltor": "O = I - sigma^-1, gamma = (sigma^-1 alpha)^* of the displaced N-mode GBS state, all detectors click",
                       "mtl": "random complex symmetric 2n x 2n matrix / sqrt(8n)",
                       "brs": "n x n block A of a 2n-mode Haar unitary, E = I - A^H A"}[kind]
             api = {"hafnian": "thewalrus_b200.hafnian(A)", "lhaf": "thewalrus_b200.hafnian(A, loop=True)",

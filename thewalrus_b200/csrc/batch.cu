@@ -153,16 +153,25 @@ __device__ inline void subset_setup(const WarpWs& w, const double2* __restrict__
         e = warp_sum2(e);
         if (lane == 0) w.ptr[2 * t] = e;
         if (2 * t + 1 > T) break;
-        for (int idx = lane; idx < s * s; idx += 32) {
-            const int r = idx / s, c = idx - r * s;
-            double2 a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);
-            int q = 0;
-            for (; q + 1 < s; q += 2) {
-                cfma(a0, Pc[r * s + q], w.M[q * s + c]);
-                cfma(a1, Pc[r * s + q + 1], w.M[(q + 1) * s + c]);
+        // Pnx = Pc * M with a 2 x 2 register tile per lane (s is even): four shared-memory loads feed four complex
+        // multiply-adds, half the LDS traffic and a quarter of the index arithmetic of one output per lane
+        {
+            const int h = s >> 1;
+            for (int t2 = lane; t2 < h * h; t2 += 32) {
+                const int tr = t2 / h, tc = t2 - tr * h;
+                const double2* p0 = Pc + 2 * tr * s;
+                const double2* p1 = p0 + s;
+                const double2* mc = w.M + 2 * tc;
+                double2 a00 = make_double2(0.0, 0.0), a01 = a00, a10 = a00, a11 = a00;
+                for (int q = 0; q < s; ++q) {
+                    const double2 x0 = p0[q], x1 = p1[q];
+                    const double2 y0 = mc[q * s], y1 = mc[q * s + 1];
+                    cfma(a00, x0, y0); cfma(a01, x0, y1);
+                    cfma(a10, x1, y0); cfma(a11, x1, y1);
+                }
+                double2* o = Pnx + 2 * tr * s + 2 * tc;
+                o[0] = a00; o[1] = a01; o[s] = a10; o[s + 1] = a11;
             }
-            if (q < s) cfma(a0, Pc[r * s + q], w.M[q * s + c]);
-            Pnx[idx] = make_double2(a0.x + a1.x, a0.y + a1.y);
         }
         __syncwarp();
         double2 o = make_double2(0.0, 0.0);

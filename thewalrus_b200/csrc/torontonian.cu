@@ -17,7 +17,8 @@
 
 namespace wb {
 
-constexpr int TOR_THREADS = 256;
+constexpr int TOR_THREADS = 512;       // torontonian: 16 warps hide the shared-memory / FP64 latency of the tree levels
+constexpr int TOR_THREADS_LOOP = 256;  // loop torontonian: the 5 x 5 register tail needs > 128 registers
 constexpr int TOR_DC = 9;        // modes expanded breadth-first inside a CTA
 constexpr int TOR_G = 5;         // log2(prefixes per CTA)
 constexpr int TOR_MAX_MODES = 32;
@@ -57,11 +58,21 @@ __global__ void tor_prep_kernel(const double2* __restrict__ O, const double2* __
 
 // Lower-triangle enumeration: el -> (r, c), r >= c, el = r (r + 1) / 2 + c.
 __device__ __forceinline__ void tri_decode(int el, int& r, int& c) {
-    int rr = (int)((__fsqrt_rn((float)(8 * el + 1)) - 1.0f) * 0.5f);
-    while (rr * (rr + 1) / 2 > el) --rr;
-    while ((rr + 1) * (rr + 2) / 2 <= el) ++rr;
+    int rr = (int)((__fsqrt_rn((float)(8 * el + 1)) - 1.0f) * 0.5f);   // exact up to one unit for el < 2^20
+    rr -= (rr * (rr + 1) / 2 > el) ? 1 : 0;
+    rr += ((rr + 1) * (rr + 2) / 2 <= el) ? 1 : 0;
     r = rr;
     c = el - rr * (rr + 1) / 2;
+}
+
+// 1 / d1 and 1 / d2 of the two pivots of a leading mode (d2 = t11 - |e|^2 / d1) from ONE division:
+// with w = d1 t11 - |e|^2 = d1 d2 and q = 1 / (d1 w):  1 / d1 = q w,  1 / d2 = d1 / w = q d1^2.
+__device__ __forceinline__ void pivot_inverses(double d1, double t11, double2 e, double& i1, double& i2, double& d1d2) {
+    const double w = fma(d1, t11, -(e.x * e.x + e.y * e.y));
+    const double q = 1.0 / (d1 * w);
+    i1 = q * w;
+    i2 = q * d1 * d1;
+    d1d2 = w;
 }
 
 // One entry of the Schur complement of the leading mode (rows/cols 0, 1) of the Hermitian matrix P (stride ld):
@@ -80,19 +91,20 @@ __device__ __forceinline__ double2 schur_entry(const double2* P, int ld, int r, 
 
 // Eliminate the leading mode of P (dim x dim, stride ld) into Q (stride ldq; Q may be P + 2 (ld + 1) with ldq = ld:
 // in place).  Lower triangle only.  All threads of the CTA take part; returns d1 * d2.
+template <int THREADS>
 __device__ double eliminate_into(const double2* P, int ld, int dim, double2* Q, int ldq) {
     __syncthreads();
-    const double d1 = P[0].x, i1 = 1.0 / d1;
     const double2 e = P[ld];
-    const double d2 = P[ld + 1].x - (e.x * e.x + e.y * e.y) * i1, i2 = 1.0 / d2;
+    double i1, i2, d1d2;
+    pivot_inverses(P[0].x, P[ld + 1].x, e, i1, i2, d1d2);
     const int cd = dim - 2, tri = cd * (cd + 1) / 2;
-    for (int el = threadIdx.x; el < tri; el += TOR_THREADS) {
+    for (int el = threadIdx.x; el < tri; el += THREADS) {
         int r, c;
         tri_decode(el, r, c);
         Q[r * ldq + c] = schur_entry(P, ld, r + 2, c + 2, e, i1, i2);
     }
     __syncthreads();
-    return d1 * d2;
+    return d1d2;
 }
 
 struct TorParams {
@@ -107,12 +119,12 @@ __device__ __forceinline__ double tail2(const double2* T, int ld, double det, do
     const double t00 = T[0].x, t11 = T[ld + 1].x, t22 = T[2 * ld + 2].x, t33 = T[3 * ld + 3].x;
     const double2 t10 = T[ld], t20 = T[2 * ld], t30 = T[3 * ld], t21 = T[2 * ld + 1], t31 = T[3 * ld + 1],
                   t32 = T[3 * ld + 2];
-    double sum = sgn / sqrt(det);                                    // {}: two exclusions, sign unchanged
+    double sum = rsqrt(det);                                         // {}: two exclusions, sign unchanged
     const double detB = t22 * t33 - (t32.x * t32.x + t32.y * t32.y);  // {m1}
-    sum -= sgn / sqrt(det * detB);
+    sum -= rsqrt(det * detB);
     const double i1 = 1.0 / t00;
     const double d2 = t11 - (t10.x * t10.x + t10.y * t10.y) * i1;
-    sum -= sgn / sqrt(det * t00 * d2);                               // {m0}
+    sum -= rsqrt(det * t00 * d2);                                    // {m0}
     // {m0, m1}: Schur complement of mode 0 on the m1 block
     const double i2 = 1.0 / d2;
     double2 u2 = t21, u3 = t31;   // column 1 after pivot 1
@@ -124,8 +136,8 @@ __device__ __forceinline__ double tail2(const double2* T, int ld, double det, do
     { double2 q = cmulc(t30, t20); s32.x -= q.x * i1; s32.y -= q.y * i1; }
     { double2 q = cmulc(u3, u2); s32.x -= q.x * i2; s32.y -= q.y * i2; }
     const double detS = s22 * s33 - (s32.x * s32.x + s32.y * s32.y);
-    sum += sgn / sqrt(det * t00 * d2 * detS);
-    return sum;
+    sum += rsqrt(det * t00 * d2 * detS);
+    return sgn * sum;
 }
 
 // one scalar pivot of a 5x5 bordered node held in registers (lower triangle, index 4 = border)
@@ -150,7 +162,7 @@ __device__ __forceinline__ double tail2_loop(const double2* T, int ld, double de
     for (int r = 0; r < 5; ++r)
 #pragma unroll
         for (int c = 0; c <= r; ++c) a[r][c] = T[r * ld + c];
-    double sum = sgn * exp(-0.5 * a[4][4].x) / sqrt(det);                     // {}
+    double sum = exp(-0.5 * a[4][4].x) * rsqrt(det);                          // {}
     {                                                                         // {m1}: pivots 2, 3
         const double d1 = a[2][2].x, i1 = 1.0 / d1;
         const double2 e = a[3][2], g2 = a[4][2];
@@ -158,16 +170,16 @@ __device__ __forceinline__ double tail2_loop(const double2* T, int ld, double de
         double2 u = a[4][3];
         { const double2 q = cmulc(g2, e); u.x -= q.x * i1; u.y -= q.y * i1; }
         const double corner = a[4][4].x - (g2.x * g2.x + g2.y * g2.y) * i1 - (u.x * u.x + u.y * u.y) / d2;
-        sum -= sgn * exp(-0.5 * corner) / sqrt(det * d1 * d2);
+        sum -= exp(-0.5 * corner) * rsqrt(det * d1 * d2);
     }
     const double p0 = pivot5<0>(a);
     const double p1 = pivot5<1>(a);
     const double det01 = det * p0 * p1;
-    sum -= sgn * exp(-0.5 * a[4][4].x) / sqrt(det01);                         // {m0}
+    sum -= exp(-0.5 * a[4][4].x) * rsqrt(det01);                              // {m0}
     const double p2 = pivot5<2>(a);
     const double p3 = pivot5<3>(a);
-    sum += sgn * exp(-0.5 * a[4][4].x) / sqrt(det01 * p2 * p3);               // {m0, m1}
-    return sum;
+    sum += exp(-0.5 * a[4][4].x) * rsqrt(det01 * p2 * p3);                    // {m0, m1}
+    return sgn * sum;
 }
 
 // Row stride of a stored dim x dim matrix: odd, so that the column reads P[r * ld] / P[r * ld + 1] of a quarter
@@ -203,8 +215,10 @@ __host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, i
 // next prefix costs ONE elimination (the level whose bit turns 0 -> 1; the levels below restart as exclusions).
 // The last DC modes are expanded breadth-first: level l has 2^l nodes, each served by 256 / 2^l threads, the
 // included children go to a pool that stays alive until the 2-mode tails have been summed in registers.
-template <int AUG>
-__global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* __restrict__ partials) {
+template <int AUG, int THREADS>
+__global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __restrict__ partials) {
+    constexpr int LOG_THREADS = THREADS == 512 ? 9 : 8;
+    static_assert(THREADS == 256 || THREADS == 512, "one node needs at least 4 threads at 64 nodes");
     extern __shared__ __align__(16) double smem_tor[];
     const int N = p.N, n2 = 2 * N + AUG, DC = p.DC, g = p.g, P = p.P;
     const int dg = 2 * (DC + g) + AUG, ldT = tor_ld(n2);
@@ -217,22 +231,26 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
     double* sgnA = detA + TOR_MAXNODES;
     double* detB = sgnA + TOR_MAXNODES;
     double* sgnB = detB + TOR_MAXNODES;
-    double* inv1 = sgnB + TOR_MAXNODES;
-    double* inv2 = inv1 + 64;
     const int tid = threadIdx.x;
+    __shared__ uchar2 tri_rc[160];   // el -> (r, c) of the lower triangle, up to 17 x 17 (the largest breadth-first child)
+    for (int el = tid; el < 160; el += THREADS) {
+        int r, c;
+        tri_decode(el, r, c);
+        tri_rc[el] = make_uchar2((unsigned char)r, (unsigned char)c);
+    }
 
     dd acc = {0.0, 0.0};
     const uint64_t ngroups_first = p.p0 >> g, ngroups_last = (p.p1 + (1ull << g) - 1) >> g;
     for (uint64_t grp = ngroups_first + blockIdx.x; grp < ngroups_last; grp += gridDim.x) {
         // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0), in place on T
         __syncthreads();
-        for (int idx = tid; idx < n2 * n2; idx += TOR_THREADS) S[(idx / n2) * ldT + idx % n2] = p.B[idx];
+        for (int idx = tid; idx < n2 * n2; idx += THREADS) S[(idx / n2) * ldT + idx % n2] = p.B[idx];
         double det0 = 1.0, sgn0 = 1.0;
         const int lead = P - g;
         for (int i = 0; i < lead; ++i) {
             const bool inc = (grp >> (lead - 1 - i)) & 1ull;
             double2* V = S + 2 * i * (ldT + 1);
-            if (inc) det0 *= eliminate_into(V, ldT, n2 - 2 * i, V + 2 * (ldT + 1), ldT);
+            if (inc) det0 *= eliminate_into<THREADS>(V, ldT, n2 - 2 * i, V + 2 * (ldT + 1), ldT);
             else sgn0 = -sgn0;
         }
         // ---- phase B: the 2^g prefixes of this group, depth-first
@@ -256,7 +274,7 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
                     if (lvl >= first) {
                         const bool inc = (sub >> (g - 1 - lvl)) & 1;
                         if (inc) {
-                            ndet[lvl + 1] = ndet[lvl] * eliminate_into(S + nptr[lvl], nld[lvl], dim, S + dbuf, cld);
+                            ndet[lvl + 1] = ndet[lvl] * eliminate_into<THREADS>(S + nptr[lvl], nld[lvl], dim, S + dbuf, cld);
                             nsgn[lvl + 1] = nsgn[lvl];
                             nptr[lvl + 1] = dbuf; nld[lvl + 1] = cld;
                         } else {
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
             if (tid == 0) { ptrA[0] = rptr; ldA[0] = rld; detA[0] = rdet; sgnA[0] = rsgn; }
             int* pc = ptrA; int* lc = ldA; double* dc = detA; double* sc = sgnA;
             int* pn = ptrB; int* ln = ldB; double* dn = detB; double* sn = sgnB;
-            int nodes = 1, shift = 8, pool = p.off_pool;
+            int nodes = 1, shift = LOG_THREADS, pool = p.off_pool;
             __syncthreads();
             for (int dim = 2 * DC + AUG; dim > 4 + AUG; dim -= 2) {
                 const int cd = dim - 2, tri = cd * (cd + 1) / 2, cld = tor_ld(cd), csz = cd * cld;
@@ -285,24 +303,18 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
                 const int myptr = pc[nd], myld = lc[nd];
                 const double2* Pn = S + myptr;
                 double2* Qn = S + pool + nd * csz;
+                // every thread of the node derives the two pivots itself: no separate pivot pass, one barrier per level
+                const double2 e = Pn[myld];
+                double i1, i2, d1d2;
+                pivot_inverses(Pn[0].x, Pn[myld + 1].x, e, i1, i2, d1d2);
                 if (lane == 0) {
-                    const double d1 = Pn[0].x, i1 = 1.0 / d1;
-                    const double2 e = Pn[myld];
-                    const double d2 = Pn[myld + 1].x - (e.x * e.x + e.y * e.y) * i1;
-                    inv1[nd] = i1; inv2[nd] = 1.0 / d2;
                     const double dt = dc[nd], sg = sc[nd];
                     pn[2 * nd] = myptr + 2 * (myld + 1); ln[2 * nd] = myld; dn[2 * nd] = dt; sn[2 * nd] = -sg;   // exclude
-                    pn[2 * nd + 1] = pool + nd * csz; ln[2 * nd + 1] = cld; dn[2 * nd + 1] = dt * d1 * d2; sn[2 * nd + 1] = sg;
+                    pn[2 * nd + 1] = pool + nd * csz; ln[2 * nd + 1] = cld; dn[2 * nd + 1] = dt * d1d2; sn[2 * nd + 1] = sg;
                 }
-                __syncthreads();
-                {
-                    const double i1 = inv1[nd], i2 = inv2[nd];
-                    const double2 e = Pn[myld];
-                    for (int el = lane; el < tri; el += step) {
-                        int r, c;
-                        tri_decode(el, r, c);
-                        Qn[r * cld + c] = schur_entry(Pn, myld, r + 2, c + 2, e, i1, i2);
-                    }
+                for (int el = lane; el < tri; el += step) {
+                    const uchar2 rc = tri_rc[el];
+                    Qn[rc.x * cld + rc.y] = schur_entry(Pn, myld, rc.x + 2, rc.y + 2, e, i1, i2);
                 }
                 __syncthreads();
                 pool += nodes * csz;
@@ -311,13 +323,13 @@ __global__ void __launch_bounds__(TOR_THREADS) tor_kernel(TorParams p, double* _
                 nodes *= 2; --shift;
             }
             // ---- 2-mode nodes finished by single threads
-            for (int nd = tid; nd < nodes; nd += TOR_THREADS) {
+            for (int nd = tid; nd < nodes; nd += THREADS) {
                 if (AUG) dd_add(acc, tail2_loop(S + pc[nd], lc[nd], dc[nd], sc[nd]));
                 else dd_add(acc, tail2(S + pc[nd], lc[nd], dc[nd], sc[nd]));
             }
         }
     }
-    __shared__ double red[(TOR_THREADS / 32) * 4];
+    __shared__ double red[(THREADS / 32) * 4];
     cdd a2;
     a2.re = acc;
     a2.im = {0.0, 0.0};
@@ -386,14 +398,14 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
     if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
-    if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1, TOR_THREADS_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0, TOR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
     int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
     if (grid > TOR_MAX_GRID) grid = TOR_MAX_GRID;
     tor_prep_kernel<<<8, 256, 0, st>>>(reinterpret_cast<const double2*>(dO), reinterpret_cast<const double2*>(dGamma), N, dB);
-    if (aug) tor_kernel<1><<<grid, TOR_THREADS, shm, st>>>(p, dpart);
-    else tor_kernel<0><<<grid, TOR_THREADS, shm, st>>>(p, dpart);
+    if (aug) tor_kernel<1, TOR_THREADS_LOOP><<<grid, TOR_THREADS_LOOP, shm, st>>>(p, dpart);
+    else tor_kernel<0, TOR_THREADS><<<grid, TOR_THREADS, shm, st>>>(p, dpart);
     final_reduce_kernel<<<1, 32, 0, st>>>(dpart, grid, d_out4);
     WB_CUDA(cudaGetLastError());
     return WB200_OK;
