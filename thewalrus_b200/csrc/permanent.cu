@@ -26,8 +26,12 @@
 
 namespace wb {
 
-constexpr int PERM_THREADS = 128;
-constexpr int PERM_MIN_CTAS = 2;        // <= 255 registers; the tile shapes below land at 8-16 warps per SM
+#ifndef WB_PERM_THREADS          // build-time overrides for the block-shape experiment (tools/gpu_perm_shape.sh)
+#define WB_PERM_THREADS 128
+#define WB_PERM_MIN_CTAS 2
+#endif
+constexpr int PERM_THREADS = WB_PERM_THREADS;
+constexpr int PERM_MIN_CTAS = WB_PERM_MIN_CTAS;   // <= 255 registers; the tile shapes below land at 8-16 warps per SM
 constexpr int PERM_BLOCK_GROUPS = 16;   // groups added in plain FP64 before the compensated fold
 
 struct C128 {
