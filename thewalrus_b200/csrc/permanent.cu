@@ -26,9 +26,12 @@
 
 namespace wb {
 
-#ifndef WB_PERM_THREADS          // build-time overrides for the block-shape experiment (tools/gpu_perm_shape.sh)
-#define WB_PERM_THREADS 128
-#define WB_PERM_MIN_CTAS 2
+// One 256-thread CTA per SM.  With several smaller CTAs per SM (128 x 2, 64 x 4, 32 x 8 were measured) only 6.3 of
+// the 8 warps the register file allows are resident on average and the FP64 pipe drops from 75 % to 71 % busy
+// (profiles/r01_perm_block_shape.txt); -D overrides exist for that experiment (tools/gpu_perm_shape.sh).
+#ifndef WB_PERM_THREADS
+#define WB_PERM_THREADS 256
+#define WB_PERM_MIN_CTAS 1
 #endif
 constexpr int PERM_THREADS = WB_PERM_THREADS;
 constexpr int PERM_MIN_CTAS = WB_PERM_MIN_CTAS;   // <= 255 registers; the tile shapes below land at 8-16 warps per SM

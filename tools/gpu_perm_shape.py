@@ -14,7 +14,9 @@ for path in libs:
     lib = ctypes.CDLL(path)
     lib.wb200_perm_host.restype = ctypes.c_int
     lib.wb200_perm_host.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, dp, dp]
-    for w, steps in (("perm32", 1 << 31), ("perm40", 1 << 34)):
+    import os
+    sizes = [int(x) for x in os.environ.get("PERM_SIZES", "32,40").split(",")]
+    for w, steps in [(f"perm{n}", 1 << min(n - 1, 34)) for n in sizes]:
         _, n, U = bench.make_input(w)
         U = np.ascontiguousarray(U, dtype=np.complex128)
         out = np.zeros(4)
