@@ -33,6 +33,17 @@ A5 = A[:5, :5] / 4; D5 = np.diag(A)[:5] / 4
 checks["lhaf_batch"] = rel(wb.loop_hafnian_batch(A5, D5, [1, 0, 2, 1], 6, group=True), wb.loop_hafnian_batch(A5, D5, [1, 0, 2, 1], 6))
 mu, cov, pats = bench.make_gbs_state(8, 1001, seed=77)
 checks["probabilities_batch"] = rel(wb.probabilities_batch(mu, cov, pats, group=True) + 1e-300, wb.probabilities_batch(mu, cov, pats) + 1e-300)
+_, _, (Ol, gl) = bench.make_input("ltor28")
+checks["ltor28"] = rel(wb.ltor(Ol, gl, group=True), wb.ltor(Ol, gl))
+_, _, Am = bench.make_input("mtl10")
+checks["mtl10"] = rel(wb.mtl(Am, group=True), wb.mtl(Am))
+zeta = 0.3 * (rng.standard_normal(20) + 1j * rng.standard_normal(20))
+checks["lmtl10"] = rel(wb.lmtl(Am, zeta, group=True), wb.lmtl(Am, zeta))
+_, _, (Ab, Eb) = bench.make_input("brs9")
+checks["brs9"] = rel(wb.brs(Ab, Eb, group=True), wb.brs(Ab, Eb))
+Dg = rng.standard_normal((3, 5)) + 1j * rng.standard_normal((3, 5))
+checks["lhaf_batch_gamma"] = rel(wb.loop_hafnian_batch_gamma(A5, Dg, [1, 0, 2, 1], 5, group=True),
+                                 wb.loop_hafnian_batch_gamma(A5, Dg, [1, 0, 2, 1], 5))
 # all ranks must hold bit-identical results
 v = wb.hafnian(A, group=True)
 t = torch.tensor([v.real, v.imag], dtype=torch.float64, device="cuda")
