@@ -81,6 +81,13 @@ int wb200_lhaf_patterns_host(int device, const double* A, const double* gamma, i
 int wb200_lhaf_patterns_multi_host(int device, const double* A, const double* gamma, int n_gamma,
                                    const int32_t* gamma_index, int nv, const int32_t* rpt, int64_t B, int glynn,
                                    double* out, double* kernel_ms);
+/* The batched-MATRIX front end: additionally a table of matrices, A is n_A x nv x nv and problem b uses matrix
+ * A_index[b] (NULL when n_A == 1).  One call evaluates B independent (loop) hafnians
+ * loop_hafnian(A[A_index[b]], gamma[gamma_index[b]], reps = rpt[b]) — e.g. hafnian(A_b) for a stack of small
+ * matrices with rpt = 1 (thewalrus/_hafnian.py:718-861 called in a Python loop by the reference's users). */
+int wb200_lhaf_matrices_host(int device, const double* A, int n_A, const int32_t* A_index, const double* gamma,
+                             int n_gamma, const int32_t* gamma_index, int nv, const int32_t* rpt, int64_t B, int glynn,
+                             double* out, double* kernel_ms);
 
 /* ---- loop_hafnian_batch sweep -------------------------------------------------------------------------
  * Replaces _calc_loop_hafnian_batch_even / _odd (thewalrus/loop_hafnian_batch.py:51-208).  Ax (n x n, n = 2E),

@@ -195,3 +195,37 @@ def test_threshold_probabilities_sum_to_one():
     mu = 0.4 * rng.standard_normal(2 * M)
     tot = sum(wb.threshold_detection_prob(mu, cov, np.array(d)) for d in product([0, 1], repeat=M))
     assert abs(tot - 1.0) < 1e-9
+
+
+# ------------------------------------------------------------------------------ batched-matrix front end
+def test_hafnian_batch_vs_single_calls_and_oracle():
+    rng = np.random.default_rng(61)
+    for n, B in ((2, 5), (6, 40), (9, 12), (12, 30), (16, 6)):
+        G = rng.standard_normal((B, n, n)) + 1j * rng.standard_normal((B, n, n))
+        As = G + np.swapaxes(G, 1, 2)
+        for loop in (False, True):
+            got = wb.hafnian_batch(As, loop=loop)
+            assert got.shape == (B,) and got.dtype == np.complex128
+            if n % 2 == 1 and not loop:
+                assert np.all(got == 0)
+                continue
+            want = np.array([wo.loop_hafnian(A, np.diag(A), [1] * n) if loop else wo.haf(A) for A in As])
+            assert relv(got, want) < TOL, (n, loop)
+            single = np.array([complex(wb.hafnian(np.ascontiguousarray(A), loop=loop)) for A in As[:3]])
+            assert relv(got[:3], single) < TOL
+
+
+def test_hafnian_batch_exact_matchings_and_checks():
+    rng = np.random.default_rng(62)
+    As = (rng.random((20, 10, 10)) < 0.5).astype(np.float64)
+    As = np.triu(As, 1)
+    As = As + np.swapaxes(As, 1, 2)
+    got = wb.hafnian_batch(As)
+    want = np.array([wo.hafnian_by_matchings(A) for A in As])
+    assert np.all(np.rint(got.real) == want) and np.max(np.abs(got.imag)) < 1e-9   # integer perfect-matching counts
+    with pytest.raises(ValueError, match="symmetric"):
+        wb.hafnian_batch(rng.standard_normal((2, 4, 4)))
+    with pytest.raises(ValueError, match="square"):
+        wb.hafnian_batch(np.zeros((2, 3, 4)))
+    assert wb.hafnian_batch(np.zeros((0, 4, 4))).shape == (0,)
+    assert np.all(wb.hafnian_batch(np.zeros((3, 0, 0))) == 1)

@@ -8,6 +8,7 @@ from ._hafnian import (  # noqa: F401
     _haf,
     find_kept_edges,
     hafnian,
+    hafnian_batch,
     hafnian_repeated,
     input_validation,
     loop_hafnian,

@@ -294,12 +294,14 @@ def brs_range(A, E, j0, j1, device=None):
     return out
 
 
-def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False, gamma_index=None):
+def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False, gamma_index=None, A_index=None):
     """Loop hafnians of the repetition patterns ``rpt[B, nv]`` of one matrix on this process's GPU.
-    ``gamma`` may be a table ``[G, nv]`` with ``gamma_index[B]`` selecting each pattern's row."""
+    ``gamma`` may be a table ``[G, nv]`` with ``gamma_index[B]`` selecting each pattern's row, and ``A`` a stack
+    ``[n_A, nv, nv]`` with ``A_index[B]`` selecting each pattern's matrix."""
     lib = _lib.load()
     idx = _dev_index(device)
     A, pA = _lib.as_c128(A)
+    n_A = 1 if A.ndim == 2 else A.shape[0]
     pG = None
     n_gamma = 0
     if gamma is not None:
@@ -313,27 +315,32 @@ def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False, g
         if gamma_index.shape != (B,):
             raise ValueError("gamma_index must have one entry per pattern")
         pI = gamma_index.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    pAI = None
+    if A_index is not None:
+        A_index = np.ascontiguousarray(A_index, dtype=np.int32)
+        if A_index.shape != (B,):
+            raise ValueError("A_index must have one entry per pattern")
+        pAI = A_index.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
     out = np.zeros(B, dtype=np.complex128)
     ms = ctypes.c_double(0.0)
-    rc = lib.wb200_lhaf_patterns_multi_host(idx, pA, pG, n_gamma, pI, nv,
-                                            rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B,
-                                            1 if glynn else 0, _lib.dptr(out.view(np.float64)), ctypes.byref(ms))
-    _lib.check(rc, "wb200_lhaf_patterns_multi_host")
+    rc = lib.wb200_lhaf_matrices_host(idx, pA, n_A, pAI, pG, n_gamma, pI, nv,
+                                      rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), B,
+                                      1 if glynn else 0, _lib.dptr(out.view(np.float64)), ctypes.byref(ms))
+    _lib.check(rc, "wb200_lhaf_matrices_host")
     _log_ms(ms)
     return (out, ms.value) if want_ms else out
 
 
-def run_sharded_patterns(A, gamma, rpt, glynn, group, device, local=None, gamma_index=None):
+def run_sharded_patterns(A, gamma, rpt, glynn, group, device, local=None, gamma_index=None, A_index=None):
     """Shard the PATTERNS in contiguous blocks over the ranks of ``group`` and all-gather the results
     (the batched front end shards the batch, not the subset index).  ``local`` overrides the
     per-rank evaluator (tests use the oracle there)."""
     if local is None:
-        if gamma_index is None:
-            local = lambda r, a=0, b=None: lhaf_patterns_local(A, gamma, r, glynn, device)  # noqa: E731
-        else:
-            gamma_index = np.ascontiguousarray(gamma_index, dtype=np.int32)
-            local = lambda r, a=0, b=None: lhaf_patterns_local(A, gamma, r, glynn, device,  # noqa: E731
-                                                                gamma_index=gamma_index[a:b])
+        gi = None if gamma_index is None else np.ascontiguousarray(gamma_index, dtype=np.int32)
+        ai = None if A_index is None else np.ascontiguousarray(A_index, dtype=np.int32)
+        local = lambda r, a=0, b=None: lhaf_patterns_local(  # noqa: E731
+            A, gamma, r, glynn, device, gamma_index=None if gi is None else gi[a:b],
+            A_index=None if ai is None else ai[a:b])
     else:
         user = local
         local = lambda r, a=0, b=None: user(r)  # noqa: E731

@@ -10,7 +10,7 @@ import numpy as np
 from . import _engine
 from ._prep import glynn_steps, matched_reps
 
-__all__ = ["hafnian", "loop_hafnian", "hafnian_repeated", "reduction", "input_validation", "_haf",
+__all__ = ["hafnian", "loop_hafnian", "hafnian_repeated", "hafnian_batch", "reduction", "input_validation", "_haf",
            "matched_reps", "find_kept_edges"]
 
 _DMMA_MAX_N = 64
@@ -197,3 +197,35 @@ def hafnian_repeated(A, rpt, mu=None, loop=False, rtol=1e-05, atol=1e-08, glynn=
     if loop:
         return loop_hafnian(A, D=np.asarray(mu), reps=rpt, glynn=glynn, group=group, device=device)
     return _haf(A, reps=rpt, glynn=glynn, group=group, device=device)
+
+
+def hafnian_batch(As, loop=False, rtol=1e-05, atol=1e-08, *, group=None, device=None):
+    """Hafnians (``loop=True``: loop hafnians, loops on the diagonals) of a stack of matrices ``As[B, n, n]`` ->
+    ``complex128[B]``: what ``[hafnian(A, loop=loop) for A in As]`` returns (thewalrus/_hafnian.py:718-861), in
+    ONE GPU call of the batched-matrix front end (``wb200_lhaf_matrices_host``: one warp per (matrix, subset)).
+    With ``group`` the matrices are sharded over the ranks in contiguous blocks and the results all-gathered.
+    Meant for many small matrices; beyond n = 28 the matrices go one by one through the DMMA kernel."""
+    if not isinstance(As, np.ndarray):
+        raise TypeError("Input matrix must be a NumPy array.")
+    if As.ndim != 3 or As.shape[1] != As.shape[2]:
+        raise ValueError("Input matrix must be square.")
+    if np.isnan(As).any():
+        raise ValueError("Input matrix must not contain NaNs.")
+    if not np.allclose(As, np.swapaxes(As, 1, 2), rtol=rtol, atol=atol):
+        raise ValueError("Input matrix must be symmetric.")
+    B, n = As.shape[0], As.shape[1]
+    if B == 0:
+        return np.zeros(0, dtype=np.complex128)
+    if n == 0:
+        return np.ones(B, dtype=np.complex128)
+    if n % 2 == 1 and not loop:
+        return np.zeros(B, dtype=np.complex128)
+    if n > 28:
+        return np.array([complex(hafnian(np.ascontiguousarray(A), loop=loop, group=group, device=device)) for A in As])
+    from .quantum import lhaf_patterns
+
+    Ac = np.ascontiguousarray(As, dtype=np.complex128)
+    idx = np.arange(B, dtype=np.int32)
+    gamma = np.ascontiguousarray(np.diagonal(Ac, axis1=1, axis2=2)) if loop else None
+    return lhaf_patterns(Ac, gamma, np.ones((B, n), dtype=np.int32), A_index=idx,
+                         gamma_index=idx if loop else None, group=group, device=device)

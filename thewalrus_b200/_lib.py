@@ -39,6 +39,9 @@ SIGNATURES = {
     "wb200_lhaf_patterns_multi_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _c_int32_p,
                                                       ctypes.c_int, _c_int32_p, ctypes.c_int64, ctypes.c_int,
                                                       _c_double_p, _c_double_p]),
+    "wb200_lhaf_matrices_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, ctypes.c_int, _c_int32_p, _c_double_p,
+                                                ctypes.c_int, _c_int32_p, ctypes.c_int, _c_int32_p, ctypes.c_int64,
+                                                ctypes.c_int, _c_double_p, _c_double_p]),
     "wb200_lhaf_batch_steps": (ctypes.c_int, [_c_int32_p, ctypes.c_int, _c_uint64_p]),
     "wb200_lhaf_batch_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _c_int32_p,
                                              ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64, _u64, _c_double_p,

@@ -388,6 +388,7 @@ struct PatParams {
     const double2* A;
     const double2* D;  // gamma(s) or null: n_gamma x nv
     const int32_t* gidx;  // per-pattern row of D, or null (all patterns use row 0)
+    const int32_t* aidx;  // per-pattern matrix of the table A[n_A][nv][nv], or null (all patterns use matrix 0)
     int nv, glynn, smax, T, O;
     long long B;
     const PatDesc* desc;
@@ -422,6 +423,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
         const int E = d->E, N = d->N, odd = d->odd;
         const unsigned long long steps = d->steps;
         const double2* Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.nv : p.D;
+        const double2* Ap = p.aidx ? p.A + (size_t)__ldg(p.aidx + pat) * p.nv * p.nv : p.A;
         __syncwarp();
         if (lane < BW_EMAX) { w.eu[lane] = d->u[lane]; w.ev[lane] = d->v[lane]; w.er[lane] = d->r[lane]; }
         __syncwarp();
@@ -440,7 +442,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
             }
             __syncwarp();
             const int k = s_k[warp];
-            subset_traces(w, p.A, p.nv, Dp, odd, -1, k, T, lane);
+            subset_traces(w, Ap, p.nv, Dp, odd, -1, k, T, lane);
             if (odd >= 0) fac_odd(w, order, __ldg(Dp + odd), w.ov, lane);
             else fac_even(w, order, lane);
             exp_series(w, w.cs0, order, lane);
@@ -671,7 +673,17 @@ extern "C" int wb200_lhaf_patterns_host(int device, const double* A, const doubl
 extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const double* gamma, int n_gamma,
                                               const int32_t* gamma_index, int nv, const int32_t* rpt, int64_t B,
                                               int glynn, double* out, double* kernel_ms) {
+    return wb200_lhaf_matrices_host(device, A, 1, nullptr, gamma, n_gamma, gamma_index, nv, rpt, B, glynn, out, kernel_ms);
+}
+
+extern "C" int wb200_lhaf_matrices_host(int device, const double* A, int n_A, const int32_t* A_index,
+                                        const double* gamma, int n_gamma, const int32_t* gamma_index, int nv,
+                                        const int32_t* rpt, int64_t B, int glynn, double* out, double* kernel_ms) {
     if (!A || !rpt || !out) { set_error("lhaf_patterns: null pointer"); return WB200_EINVAL; }
+    if (n_A < 1 || (n_A > 1 && !A_index)) { set_error("lhaf_patterns: n_A must be >= 1 and A_index given for n_A > 1"); return WB200_EINVAL; }
+    if (A_index)
+        for (int64_t i = 0; i < B; ++i)
+            if (A_index[i] < 0 || A_index[i] >= n_A) { set_error("lhaf_patterns: A_index[%lld] = %d outside [0, %d)", (long long)i, A_index[i], n_A); return WB200_EINVAL; }
     if (gamma && n_gamma < 1) { set_error("lhaf_patterns: n_gamma must be >= 1 when gamma is given"); return WB200_EINVAL; }
     if (gamma && n_gamma > 1 && !gamma_index) { set_error("lhaf_patterns: gamma_index is required for n_gamma > 1"); return WB200_EINVAL; }
     if (gamma && gamma_index)
@@ -683,9 +695,13 @@ extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const
     WB_CUDA(cudaSetDevice(device));
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    DevBufB dA, dD, dgi, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
-    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * nv * nv));
-    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * nv * nv, cudaMemcpyHostToDevice));
+    DevBufB dA, dai, dD, dgi, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
+    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * (size_t)n_A * nv * nv));
+    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * (size_t)n_A * nv * nv, cudaMemcpyHostToDevice));
+    if (A_index) {
+        WB_POOL(pool_alloc(&dai.p, sizeof(int32_t) * (size_t)B));
+        WB_CUDA(cudaMemcpy(dai.p, A_index, sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice));
+    }
     if (gamma) {
         WB_POOL(pool_alloc(&dD.p, sizeof(double2) * (size_t)n_gamma * nv));
         WB_CUDA(cudaMemcpy(dD.p, gamma, sizeof(double2) * (size_t)n_gamma * nv, cudaMemcpyHostToDevice));
@@ -723,7 +739,7 @@ extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const
     }
     if (nchunks > 0) {
         PatParams p;
-        p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.gidx = (const int32_t*)dgi.p; p.nv = nv; p.glynn = glynn;
+        p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.gidx = (const int32_t*)dgi.p; p.aidx = (const int32_t*)dai.p; p.nv = nv; p.glynn = glynn;
         p.smax = 2 * meta.maxE; p.T = meta.maxN / 2; p.O = meta.anyOdd ? meta.maxN : meta.maxN / 2;
         p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p;
         p.nchunks = nchunks; p.counter = (unsigned long long*)dcounter.p;

@@ -51,19 +51,23 @@ def _prefactor(mu, cov, hbar=2):
     return np.exp(-0.5 * beta @ np.linalg.inv(Q) @ beta.conj()) / np.sqrt(np.linalg.det(Q))
 
 
-def lhaf_patterns(A, gamma, rpt, glynn=True, *, gamma_index=None, group=None, device=None):
+def lhaf_patterns(A, gamma, rpt, glynn=True, *, gamma_index=None, A_index=None, group=None, device=None):
     """``[loop_hafnian(A, gamma, reps=r) for r in rpt]`` (``gamma=None``: ``hafnian_repeated(A, r)``) on the GPU.
 
-    ``rpt``: integer array ``[B, len(A)]``.  ``gamma`` may also be a table ``[G, len(A)]`` of loop vectors with
+    ``rpt``: integer array ``[B, len(A)]``.  ``A`` may be a stack ``[n_A, nv, nv]`` with ``A_index[B]`` naming the
+    matrix of each problem (the batched-matrix front end, see :func:`thewalrus_b200.hafnian_batch`).  ``gamma`` may also be a table ``[G, len(A)]`` of loop vectors with
     ``gamma_index[B]`` naming the row each pattern uses (the batched samplers' call).  With ``group`` the
     patterns are sharded over the ranks in contiguous blocks and the results all-gathered (one collective).
     """
     rpt = np.ascontiguousarray(rpt, dtype=np.int32)
-    if rpt.ndim != 2 or rpt.shape[1] != len(A):
+    nv = np.shape(A)[-1]
+    if rpt.ndim != 2 or rpt.shape[1] != nv:
         raise ValueError("rpt must have shape [batch, len(A)]")
     if gamma is not None and np.ndim(gamma) == 2 and gamma_index is None and len(gamma) != 1:
         raise ValueError("a table of loop vectors needs gamma_index")
-    return _engine.run_sharded_patterns(A, gamma, rpt, glynn, group, device, gamma_index=gamma_index)
+    if np.ndim(A) == 3 and A_index is None and len(A) != 1:
+        raise ValueError("a stack of matrices needs A_index")
+    return _engine.run_sharded_patterns(A, gamma, rpt, glynn, group, device, gamma_index=gamma_index, A_index=A_index)
 
 
 def _state(mu, cov, hbar, tol):
