@@ -236,25 +236,26 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
     """Time the oracle's C port (reference algorithm) on the host cores over a bounded sample."""
     from oracle import c_oracle as co
 
-    threads = co.max_threads()
+    # all host cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or co.max_threads())
     if kind in ("hafnian", "lhaf"):
         x = co.matched_order(X)
         Ax = np.ascontiguousarray(X[np.ix_(x, x)])
         Dx = np.ascontiguousarray(np.diag(X)[x]) if kind == "lhaf" else None
         total = 1 << (n // 2 - 1)
-        co.hafnian_range(Ax, 0, min(total, 64 * threads), Dx)  # warm-up (thread pool, page faults)
+        co.hafnian_range(Ax, 0, min(total, 64 * threads), Dx, threads)  # warm-up (thread pool, page faults)
         t0 = time.perf_counter()
-        co.hafnian_range(Ax, 0, min(total, 256 * threads), Dx)
+        co.hafnian_range(Ax, 0, min(total, 256 * threads), Dx, threads)
         rate = min(total, 256 * threads) / (time.perf_counter() - t0)
         sample = int(min(total, max(1024, rate * seconds)))
         t0 = time.perf_counter()
-        co.hafnian_range(Ax, 0, sample, Dx)
+        co.hafnian_range(Ax, 0, sample, Dx, threads)
         dt = time.perf_counter() - t0
         what = f"first {sample} of {total} Glynn subsets of the same {n}x{n} matrix, full product-chain algorithm"
     elif kind == "perm":
         sample = int(min(1 << (n - 1), 4e7 * threads * seconds / 15.0))
         t0 = time.perf_counter()
-        co.perm_range(X, 0, 0, sample)
+        co.perm_range(X, 0, 0, sample, threads)
         dt = time.perf_counter() - t0
         what = f"first {sample} of {1 << (n - 1)} Gray-code steps (the reference itself is single-threaded; the port splits the range over threads)"
     elif kind == "tor" and n <= 48:
