@@ -60,15 +60,20 @@ __global__ void haf_prep_kernel(const double* __restrict__ A, int n, int m, int 
         const int lane = idx & 31, pair = idx >> 5;
         const int tile = pair % NT, kappa = pair / NT;
         const int k = lane & 3, ncol = lane >> 2;
-        const int ek = haf_chunk_elem(kappa, k, m, TF, tp);
+        // K-packed tail chunk (one vertex pair in the tail, tp == 1): only positions 0, 1 of the chunk carry
+        // elements, so positions 2, 3 take the IMAGINARY parts of the same two elements and the step needs two
+        // DMMAs per tile for this chunk instead of four:  D_re += [yr | yi] . [Ar ; -Ai],  D_im += [yr | yi] . [Ai ; Ar]
+        const bool packk = tail && tp == 1 && kappa == 2 * TF;
+        const bool imag_slot = packk && k >= 2;
+        const int ek = haf_chunk_elem(kappa, packk ? (k & 1) : k, m, TF, tp);
         double2 v = make_double2(0.0, 0.0);
         if (ek >= 0) {
             if (tile < TF) {
                 const int in = 4 * tile + (ncol >> 1);
                 if (in < m) {
                     const int en = in + (ncol & 1) * m;
-                    v.x = A[2 * ((size_t)ek * n + en)];
-                    v.y = A[2 * ((size_t)ek * n + en) + 1];
+                    const double ar = A[2 * ((size_t)ek * n + en)], ai = A[2 * ((size_t)ek * n + en) + 1];
+                    v = imag_slot ? make_double2(-ai, ar) : make_double2(ar, ai);
                 }
             } else {
                 const int tq = ncol >> 1;
@@ -76,6 +81,7 @@ __global__ void haf_prep_kernel(const double* __restrict__ A, int n, int m, int 
                     const int en = 4 * TF + (tq >> 1) + (tq & 1) * m;
                     const double ar = A[2 * ((size_t)ek * n + en)], ai = A[2 * ((size_t)ek * n + en) + 1];
                     v = (ncol & 1) ? make_double2(ai, ar) : make_double2(ar, -ai);
+                    if (packk) v = make_double2(imag_slot ? v.y : v.x, 0.0);   // D += [yr | yi] . [F1 ; F2]
                 }
             }
         }
@@ -109,7 +115,7 @@ struct HafY {
 // W <- Y * A' on the tensor pipe
 template <int TF, bool TAIL>
 __device__ __forceinline__ void haf_step(const double2* __restrict__ sfrag, int lane, const HafY<TF, TAIL>& y,
-                                         HafRow<TF, TAIL>& w) {
+                                         HafRow<TF, TAIL>& w, bool packk) {
     constexpr int NK = 2 * TF + (TAIL ? 1 : 0), NT = TF + (TAIL ? 1 : 0);
 #pragma unroll
     for (int tp = 0; tp < TF; ++tp) {
@@ -121,6 +127,19 @@ __device__ __forceinline__ void haf_step(const double2* __restrict__ sfrag, int 
     for (int kap = 0; kap < NK; ++kap) {
         const double ar = kap < 2 * TF ? y.yr[kap < 2 * TF ? kap : 0] : y.ytr;
         const double ai = kap < 2 * TF ? y.yi[kap < 2 * TF ? kap : 0] : y.yti;
+        if (TAIL && kap == 2 * TF && packk) {   // K-packed tail chunk (see haf_prep_kernel): 2 DMMAs per tile
+            const double yi2 = __shfl_sync(0xffffffffu, y.yti, lane & ~2);
+            const double ap = (lane & 2) ? yi2 : y.ytr;
+#pragma unroll
+            for (int tp = 0; tp < TF; ++tp) {
+                const double2 b = sfrag[(kap * NT + tp) * 32 + lane];
+                dmma884(w.wr[tp][0], w.wr[tp][1], ap, b.x);
+                dmma884(w.wi[tp][0], w.wi[tp][1], ap, b.y);
+            }
+            const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
+            dmma884(w.wtr, w.wti, ap, b.x);
+            continue;
+        }
 #pragma unroll
         for (int tp = 0; tp < TF; ++tp) {
             const double2 b = sfrag[(kap * NT + tp) * 32 + lane];
@@ -294,7 +313,7 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
             }
             const int nsteps = isD ? nstepD : nprod;
             for (int k = 1; k <= nsteps; ++k) {
-                haf_step<TF, TAIL>(sfrag, lane, y, w);  // w = row of B_{k+1} (Z_k for the loop row)
+                haf_step<TF, TAIL>(sfrag, lane, y, w, TAIL && tp == 1);  // w = row of B_{k+1} (Z_k for the loop row)
                 if (!isD) {
                     // tr(M^(k+1)) share: element sigma(v) of this row
                     if (t == own_t) {
