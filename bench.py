@@ -30,6 +30,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "hafnian n=50 complex128 subsets/s"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu captures in profiles/)
+MEASURED_TRAFFIC = {"hafnian50": 5864960 + 59578624, "perm32": 79104, "tor48": 79104, "gbs16": 3444480 + 178432}
 
 
 def make_input(workload):
@@ -651,8 +653,11 @@ def main():
                                         "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
                          "flops_per_unit": my_flops, "flops_model": model,
                          "reference_algorithm_equivalent_tflops": per_gpu_units * ref_flops / (kms * 1e-3) * 1e-12,
-                         "kernel_ms": kms, "traffic": None,
-                         "traffic_note": "DRAM traffic is KB per launch (matrix in, 4 doubles per CTA out); see profiles/ for the ncu capture"},
+                         "kernel_ms": kms, "traffic": MEASURED_TRAFFIC.get(args.workload),
+                         "traffic_note": "bytes per launch of the dominant kernel, dram__bytes_read.sum + dram__bytes_write.sum from "
+                                         "the ncu captures under profiles/ (r01_ncu_traffic_hafnian50.csv, r01_ncu_*.txt); the "
+                                         "algorithmic traffic is KB (matrix in, 4 doubles per CTA out) — these paths are FP64-pipe "
+                                         "bound, DRAM sees the 4-byte spill slot and L2 write-backs over a multi-second launch"},
             "result": {"re": res.real, "im": res.imag, "e2e_re": complex(r_e2e).real},
         }
         if not args.no_cpu_baseline and world == 1:
