@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "hafnian n=50 complex128 subsets/s"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu captures in profiles/)
-MEASURED_TRAFFIC = {"hafnian50": 5864960 + 59578624, "perm32": 79104, "tor48": 79104, "gbs16": 3444480 + 178432}
+MEASURED_TRAFFIC = {"hafnian50": 5864960 + 59578624, "perm32": 79104, "tor48": 79104}
 
 
 def make_input(workload):
