@@ -113,19 +113,38 @@ template <> struct AccOf<C128> { using type = KahanC; };
 template <> struct AccOf<double> { using type = KahanR; };
 template <> struct AccOf<unsigned long long> { using type = AccI; };
 
-// product of CPL values with up to four independent chains
+// product of CPL values: WB_PERM_NC independent chains (default 4), or a balanced tree (WB_PERM_TREE)
+#ifndef WB_PERM_NC
+#define WB_PERM_NC 4
+#endif
 template <int CPL, typename S>
 __device__ __forceinline__ S product(const S (&r)[CPL]) {
-    constexpr int NC = CPL < 4 ? CPL : 4;
+#ifdef WB_PERM_TREE
+    S t[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) t[j] = r[j];
+#pragma unroll
+    for (int w = CPL; w > 1; w = (w + 1) / 2) {
+#pragma unroll
+        for (int j = 0; j < w / 2; ++j) t[j] = cmul(t[2 * j], t[2 * j + 1]);
+        if (w & 1) t[w / 2] = t[w - 1];
+    }
+    return t[0];
+#else
+    constexpr int NC = CPL < WB_PERM_NC ? CPL : WB_PERM_NC;
     S p[NC];
 #pragma unroll
     for (int j = 0; j < NC; ++j) p[j] = r[j];
 #pragma unroll
     for (int c = NC; c < CPL; ++c) p[c % NC] = cmul(p[c % NC], r[c]);
-    if constexpr (NC == 4) return cmul(cmul(p[0], p[1]), cmul(p[2], p[3]));
-    else if constexpr (NC == 3) return cmul(cmul(p[0], p[1]), p[2]);
-    else if constexpr (NC == 2) return cmul(p[0], p[1]);
-    else return p[0];
+#pragma unroll
+    for (int w = NC; w > 1; w = (w + 1) / 2) {
+#pragma unroll
+        for (int j = 0; j < w / 2; ++j) p[j] = cmul(p[2 * j], p[2 * j + 1]);
+        if (w & 1) p[w / 2] = p[w - 1];
+    }
+    return p[0];
+#endif
 }
 
 // x, -x or 0 by selects (no FP64 issue slots)
@@ -152,7 +171,10 @@ perm_kernel(const S* __restrict__ Mg, int n, int ryser, uint64_t k0, uint64_t k1
             double* __restrict__ partials, unsigned long long* __restrict__ iout) {
     using Coef = typename Traits<S>::Coef;
     constexpr int NP = CPL * SL;
-    constexpr int G = SL < 2 ? 2 : SL;
+#ifndef WB_PERM_G1
+#define WB_PERM_G1 2          // steps per group when one lane owns a stream (even)
+#endif
+    constexpr int G = SL < 2 ? WB_PERM_G1 : SL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* sM = reinterpret_cast<S*>(smem_raw);
     for (int i = threadIdx.x; i < n * NP; i += PERM_THREADS) {
@@ -246,6 +268,9 @@ perm_kernel(const S* __restrict__ Mg, int n, int ryser, uint64_t k0, uint64_t k1
                 if constexpr (SL == 1) {
                     const bool on0 = t >= tlo[s] && t < thi[s], on1 = t + 1 >= tlo[s] && t + 1 < thi[s];
                     T = cadd(weigh(P[s][0], on0, false), weigh(P[s][1], on1, true));     // t is even: + then -
+#pragma unroll
+                    for (int i = 2; i < G; ++i)
+                        T = cadd(T, weigh(P[s][i], t + i >= tlo[s] && t + i < thi[s], (i & 1) != 0));
                 } else if constexpr (SL == 2) {
                     const S mine = sub ? P[s][1] : P[s][0], give = sub ? P[s][0] : P[s][1];
                     const S got = shfl_xor_s(0xffffffffu, give, 1);
