@@ -48,7 +48,20 @@ def _worker(rank, world, port, q):
         return np.array([wo.loop_hafnian(A5, g5, [int(x) for x in r]) for r in rows], dtype=np.complex128)
 
     pats = _engine.run_sharded_patterns(A5, g5, rpt, True, True, None, local=local)
-    q.put((rank, total, table.tolist(), t2.tolist(), pats.tolist()))
+
+    # batched-matrix / multi-gamma form: the per-problem index arrays must be sliced with the shard.  The GPU
+    # evaluator of a rank is replaced by the oracle (this box has no GPU); the sharding code is what runs here.
+    def oracle_local(Ast, gam, r, glynn=True, device=None, want_ms=False, gamma_index=None, A_index=None):
+        return np.array([wo.loop_hafnian(Ast[a], gam[g], [int(x) for x in row])
+                         for row, g, a in zip(r, gamma_index, A_index)], dtype=np.complex128)
+
+    _engine.lhaf_patterns_local = oracle_local
+    Ast = np.stack([A5, 0.5 * A5, A5 * (1 + 0.1j)])
+    gam = np.stack([g5, 2 * g5])
+    gi = np.array([0, 1, 1, 0, 1, 0, 0], dtype=np.int32)
+    ai = np.array([2, 0, 1, 1, 0, 2, 1], dtype=np.int32)
+    pats2 = _engine.run_sharded_patterns(Ast, gam, rpt, True, True, None, gamma_index=gi, A_index=ai)
+    q.put((rank, total, table.tolist(), t2.tolist(), pats.tolist(), pats2.tolist()))
     dist.destroy_process_group()
 
 
@@ -72,12 +85,17 @@ def test_two_rank_gloo_sharded_sum():
     G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     A = G + G.T
     want = co.hafnian(A)
-    (r0, v0, tab0, i0, p0), (r1, v1, tab1, i1, p1) = res
+    (r0, v0, tab0, i0, p0, m0), (r1, v1, tab1, i1, p1, m1) = res
     from oracle import walrus_oracle as wo
 
     rpt = np.random.default_rng(5).integers(0, 3, (7, 5)).astype(np.int32)
     wantp = [wo.loop_hafnian(A[:5, :5], np.diag(A)[:5].copy(), [int(x) for x in r]) for r in rpt]
     assert p0 == p1 and np.allclose(np.array(p0), np.array(wantp), rtol=1e-13, atol=0)
+    A5, g5 = A[:5, :5], np.diag(A)[:5].copy()
+    Ast, gam = [A5, 0.5 * A5, A5 * (1 + 0.1j)], [g5, 2 * g5]
+    gi, ai = [0, 1, 1, 0, 1, 0, 0], [2, 0, 1, 1, 0, 2, 1]
+    wantm = [wo.loop_hafnian(Ast[a], gam[g], [int(x) for x in r]) for r, g, a in zip(rpt, gi, ai)]
+    assert m0 == m1 and np.allclose(np.array(m0), np.array(wantm), rtol=1e-13, atol=0)
     assert v0 == v1, "ranks must agree bit-for-bit"
     assert tab0 == tab1 and len(tab0) == world
     assert abs(v0 - want) / abs(want) < 1e-12
