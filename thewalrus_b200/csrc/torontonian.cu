@@ -9,10 +9,11 @@
 // each B_S, so it is as stable as the reference, but every node only touches the *remaining* modes, whose
 // matrices shrink towards the leaves where almost all of the 2^N nodes live.
 //
-// Work split: the first P = N - DC modes form a "prefix" (the C-ABI range unit).  A CTA owns G consecutive
-// prefixes, eliminates their common leading modes once, then for each prefix expands the last DC modes
-// breadth-first in shared memory (all threads busy at every level) down to 2-mode (4x4) nodes, which single
-// threads finish in registers.
+// Work split: the first P = N - DC modes form a "prefix" (the C-ABI range unit).  A CTA owns 2^g consecutive
+// prefixes: it eliminates their common leading modes once (in place), walks the g group modes depth-first (one
+// elimination per prefix), and expands the last DC modes of every prefix breadth-first in shared memory down to
+// 2-mode (4x4, loop variant 5x5) nodes, which single threads finish in registers.  Nodes are (offset, stride)
+// views of stored lower triangles, so excluding a mode copies nothing; see the comment above tor_kernel.
 #include "common.cuh"
 
 namespace wb {
