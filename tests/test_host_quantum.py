@@ -105,3 +105,12 @@ def test_hafnian_batch_host_paths():
         q.lhaf_patterns(np.zeros((2, 2, 2)), None, np.ones((2, 2), dtype=np.int32))
     with pytest.raises(ValueError, match="needs gamma_index"):
         q.lhaf_patterns(np.zeros((2, 2)), np.zeros((3, 2)), np.ones((2, 2), dtype=np.int32))
+
+
+def test_log_factorial_table_matches_gammaln():
+    from scipy.special import gammaln
+
+    pats = np.random.default_rng(2).integers(0, 9, (500, 6))
+    assert np.allclose(q._log_factorial_sums(pats), gammaln(pats + 1.0).sum(axis=1), rtol=1e-14, atol=1e-13)
+    assert np.all(q._log_factorial_sums(np.zeros((3, 4), dtype=int)) == 0)
+    assert q._log_factorial_sums(np.zeros((0, 4), dtype=int)).shape == (0,)

@@ -87,6 +87,17 @@ def density_matrix_element(mu, cov, i, j, include_prefactor=True, tol=1e-10, hba
     return haf / np.sqrt(np.prod([np.exp(lgamma(k + 1)) for k in rpt]))
 
 
+def _log_factorial_sums(patterns):
+    """sum_i log(n_i!) per row (sqrt(prod rpt!) = prod n_i! for rpt = n + n), from a table of log-factorials:
+    the photon numbers are small integers, and a table lookup is several times cheaper than 10^6 gammaln calls."""
+    patterns = np.asarray(patterns)
+    if patterns.size == 0:
+        return np.zeros(patterns.shape[0])
+    top = int(patterns.max())
+    table = np.concatenate([[0.0], np.cumsum(np.log(np.arange(1, max(top, 1) + 1, dtype=np.float64)))])
+    return table[patterns].sum(axis=1)
+
+
 def probabilities_batch(mu, cov, patterns, hbar=2, tol=1e-10, *, group=None, device=None):
     """Probabilities p(n) = <n| rho |n> of many photon-number patterns of one Gaussian state.
 
@@ -101,10 +112,7 @@ def probabilities_batch(mu, cov, patterns, hbar=2, tol=1e-10, *, group=None, dev
     rpt = np.concatenate([patterns, patterns], axis=1)
     lh = lhaf_patterns(A, gamma, rpt, group=group, device=device)
     pref = _prefactor(mu, cov, hbar=hbar)
-    from scipy.special import gammaln
-
-    logfac = gammaln(patterns + 1.0).sum(axis=1)       # sqrt(prod rpt!) = prod n!
-    return np.maximum(0.0, (lh * pref).real * np.exp(-logfac))
+    return np.maximum(0.0, (lh * pref).real * np.exp(-_log_factorial_sums(patterns)))
 
 
 def probabilities(mu, cov, cutoff, parallel=False, hbar=2.0, rtol=1e-05, atol=1e-08, *, group=None, device=None):
