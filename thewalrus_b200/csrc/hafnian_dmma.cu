@@ -385,17 +385,22 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
     block_reduce_store(acc, red, partials);
 }
 
-// Warps per CTA (one CTA per SM): 8 (<= 255 registers) or 12 (<= 168 registers, 3 warps per scheduler).
-// Chosen per call: env WB200_HAF_WARPS overrides the default picked from measurements.
-static int haf_pick_warps(int TF, int tail) {
+// Warps per CTA (one CTA per SM): 12 (<= 168 registers, 3 warps per scheduler) for full-size problems — measured on
+// B200: 12 warps beat 8 by 2-4 % at n = 40..64 (profiles/r01_hafnian_sweep.txt).  Small problems do not have 12
+// groups of four subsets per SM; one warp per scheduler already saturates the DMMA pipe (tools/fp64_peak.cu:
+// dmma884 ch4, 128 threads), so they are spread over as many SMs as possible with 4- or 8-warp CTAs instead of
+// packing 12 warps on a fraction of the SMs (n = 24: 512 groups -> 128 CTAs x 4 warps instead of 43 x 12).
+// env WB200_HAF_WARPS = 4 | 8 | 12 overrides.
+static int haf_pick_warps(uint64_t ngroups, int sms) {
     static int env = -1;
     if (env < 0) {
         const char* e = getenv("WB200_HAF_WARPS");
         env = e ? atoi(e) : 0;
     }
-    if (env == 8 || env == 12) return env;
-    (void)TF; (void)tail;
-    return 12;  // measured on B200: 12 warps beat 8 by 2-4 % at n = 40..64 (profiles/r01_hafnian_sweep.txt)
+    if (env == 4 || env == 8 || env == 12) return env;
+    if (ngroups <= 4ull * (uint64_t)sms) return 4;
+    if (ngroups <= 8ull * (uint64_t)sms) return 8;
+    return 12;
 }
 
 template <int TF, bool TAIL, int WARPS>
@@ -415,9 +420,10 @@ static int launch_haf_w(const double2* frag, const double* dA, const double* dD,
 template <int TF, bool TAIL>
 static int launch_haf(const double2* frag, const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
                       double* partials, uint64_t ngroups, int sms, int* grid_out, cudaStream_t st) {
-    if (haf_pick_warps(TF, TAIL) == 12)
-        return launch_haf_w<TF, TAIL, 12>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
-    return launch_haf_w<TF, TAIL, 8>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    const int warps = haf_pick_warps(ngroups, sms);
+    if (warps == 12) return launch_haf_w<TF, TAIL, 12>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    if (warps == 8) return launch_haf_w<TF, TAIL, 8>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    return launch_haf_w<TF, TAIL, 4>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
 }
 
 constexpr int HAF_MAX_GRID = 4096;
