@@ -391,13 +391,15 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     TorParams p;
     tor_shape(N, aug, &p.P, &p.g, &p.DC);
     p.N = N; p.p0 = p0; p.p1 = p1;
+    int dev = 0, sms = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (device_sm_count(dev, &sms)) return WB200_ECUDA;
+    // small problems (or thin multi-GPU shards): fewer prefixes per CTA so that every SM gets a group
+    while (p.g > 0 && ((p1 - p0) >> p.g) < 2ull * (uint64_t)sms) --p.g;
     const size_t shm = tor_smem_plan(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc);
     double2* dB = reinterpret_cast<double2*>(d_workspace);
     double* dpart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_workspace) + tor_ws_partials_offset(N));
     p.B = dB;
-    int dev = 0, sms = 0;
-    WB_CUDA(cudaGetDevice(&dev));
-    if (device_sm_count(dev, &sms)) return WB200_ECUDA;
     if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
     if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1, TOR_THREADS_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0, TOR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
