@@ -273,23 +273,31 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
 
         total = 1 << (n // 2 if kind in ("tor", "ltor") else n)
         j0, sample, dt = total // 3, 0, 0.0       # a window in the middle of the index space: typical subset sizes
-        step = {"tor": 2000, "ltor": 2000, "mtl": 2000, "brs": 8}[kind]
+        step = {"tor": 100000, "ltor": 2000, "mtl": 2000, "brs": 8}[kind]
         t0 = time.perf_counter()
+        used = 1
+        if kind == "ltor":
+            step, used = 20000 * threads, threads     # numba_ltor is a parallel prange in the reference: all cores
+        elif kind == "brs":
+            step = 64                                   # C port, one thread: the reference's brs loop is serial
         while dt < seconds and j0 + sample < total:
             a, b = j0 + sample, min(total, j0 + sample + step)
             if kind == "tor":
-                wo.tor_direct(X, a, b)
+                co.tor_direct(X, a, b, 1)
             elif kind == "ltor":
-                wo.ltor_direct(X[0], X[1], a, b)
+                co.ltor_direct(X[0], X[1], a, b, threads)
             elif kind == "mtl":
                 wo.montrealer(np.vstack([X[n:], X[:n]]), None, a, b)     # Xmat(n) @ A, as mtl does
             else:
-                wo.brs(X[0], X[1], a, b)
+                co.brs(X[0], X[1], a, b, 1)
             sample += b - a
             dt = time.perf_counter() - t0
-        threads = 1
-        what = (f"{sample} of {total} subsets starting at index {j0} through the NumPy restatement of the reference "
-                "(single thread, as the reference)")
+        threads = used
+        what = (f"{sample} of {total} subsets starting at index {j0} through the "
+                + ("C + OpenMP port of numba_ltor (all host cores, as the reference's prange)" if kind == "ltor" else
+                   "C port of brs (one thread, as the reference)" if kind == "brs" else
+                   "C port of numba_tor (one thread, as the reference)" if kind == "tor" else
+                   "NumPy restatement of the reference (single thread, as the reference)"))
     elif kind == "hsample":
         # the reference's chain (one sample at a time, one loop_hafnian_batch per mode) with the oracle as its kernel
         from oracle import walrus_oracle as wo

@@ -23,6 +23,9 @@ def _lib(long_double=False):
         lib.oracle_tor_recursive.restype = ctypes.c_double
         lib.oracle_tor_direct_range.argtypes = [_dp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]
         lib.oracle_tor_direct_range.restype = ctypes.c_double
+        lib.oracle_ltor_direct_range.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _dp]
+        lib.oracle_brs_range.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
+                                         ctypes.c_int, _dp]
         lib.oracle_max_threads.restype = ctypes.c_int
         _libs[key] = lib
     return _libs[key]
@@ -92,3 +95,28 @@ def tor_direct(O, j0=0, j1=None, threads=0, long_double=False):
     O, pO = _c128(O)
     N = O.shape[0] // 2
     return float(_lib(long_double).oracle_tor_direct_range(pO, N, j0, (1 << N) if j1 is None else j1, threads))
+
+
+def ltor_direct(O, gamma, j0=0, j1=None, threads=0, long_double=False):
+    """Loop torontonian over subset indices [j0, j1) (numba_ltor, thewalrus/_torontonian.py:369-412)."""
+    O, pO = _c128(O)
+    gamma, pg = _c128(gamma)
+    N = O.shape[0] // 2
+    out = np.zeros(2)
+    _lib(long_double).oracle_ltor_direct_range(pO, pg, N, j0, (1 << N) if j1 is None else j1, threads,
+                                               out.ctypes.data_as(_dp))
+    return complex(out[0], out[1])
+
+
+def brs(A, E=None, j0=0, j1=None, threads=0, long_double=False):
+    """Bristolian over row-subset labels [j0, j1) (brs / ubrs, thewalrus/_permanent.py:198-249); ``E=None`` and
+    ``j0=1`` give ubrs."""
+    A, pA = _c128(A)
+    pE = None
+    if E is not None:
+        E, pE = _c128(E)
+    m, n = A.shape
+    out = np.zeros(2)
+    _lib(long_double).oracle_brs_range(pA, pE, m, n, j0, (1 << m) if j1 is None else j1, threads,
+                                       out.ctypes.data_as(_dp))
+    return complex(out[0], out[1])

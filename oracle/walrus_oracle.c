@@ -9,6 +9,8 @@
  *   oracle_perm_range          thewalrus/_permanent.py:86-168
  *   oracle_tor_recursive       thewalrus/_torontonian.py:157-247
  *   oracle_tor_direct_range    thewalrus/_torontonian.py:123-154
+ *   oracle_ltor_direct_range   thewalrus/_torontonian.py:369-412 (numba_ltor; parallel in the reference too)
+ *   oracle_brs_range           thewalrus/_permanent.py:198-249 (brs / ubrs; the reference loop is serial)
  * Built twice by oracle/build.py: REAL = double (liboracle.so: checker + CPU baseline) and REAL = long
  * double (liboracle_ld.so: extended-precision yardstick for sampled ranges at n = 50/56).
  * Parity status: PINNED — tests/test_oracle_golden.py checks these against the committed outputs of the
@@ -353,6 +355,128 @@ double oracle_tor_direct_range(const double* O, int N, uint64_t j0, uint64_t j1,
         free(B);
     }
     return (double)tot.s;
+}
+
+/* numba_ltor (thewalrus/_torontonian.py:369-412): flat loop over subsets [j0, j1) of
+ * (-1)^(N-|S|) exp(gamma_S (I - O_S)^-1 gamma_S^* / 2) / sqrt(det(I - O_S)).  The quadratic form is evaluated
+ * through the Cholesky factor, x^H B^-1 x = |L^-1 x|^2 with x = conj(gamma_S), as rec_ltorontonian does
+ * (:338-343).  out2 = {re, 0}: real for Hermitian O. */
+void oracle_ltor_direct_range(const double* O, const double* gamma, int N, uint64_t j0, uint64_t j1, int nthreads,
+                              double* out2) {
+    kahan_t tot = {0, 0};
+    const int dimO = 2 * N;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        cplx* B = (cplx*)malloc(sizeof(cplx) * ((size_t)dimO * dimO * 2 + dimO));
+        cplx* L = B + (size_t)dimO * dimO;
+        cplx* z = L + (size_t)dimO * dimO;
+        int rows[128];
+        kahan_t acc = {0, 0};
+#pragma omp for schedule(dynamic, 64)
+        for (uint64_t j = j0; j < j1; ++j) {
+            int k = 0;
+            for (int i = 0; i < N; ++i)
+                if ((j >> (N - 1 - i)) & 1ull) { rows[k] = i; ++k; }
+            for (int i = 0; i < k; ++i) rows[k + i] = rows[i] + N;
+            const int dim = 2 * k;
+            for (int r = 0; r < dim; ++r) {
+                for (int c = 0; c < dim; ++c) {
+                    B[r * dim + c].re = (r == c ? 1 : 0) - O[2 * ((size_t)rows[r] * dimO + rows[c])];
+                    B[r * dim + c].im = -O[2 * ((size_t)rows[r] * dimO + rows[c]) + 1];
+                }
+                z[r].re = gamma[2 * rows[r]];
+                z[r].im = -gamma[2 * rows[r] + 1];          /* x = conj(gamma_S) */
+            }
+            const REAL pd = dim ? chol_from(B, L, dim, dim, 0) : 1;
+            REAL q = 0;
+            for (int r = 0; r < dim; ++r) {                 /* forward substitution L z = x */
+                cplx s = z[r];
+                for (int c = 0; c < r; ++c) {
+                    const cplx l = L[r * dim + c];
+                    s.re -= l.re * z[c].re - l.im * z[c].im;
+                    s.im -= l.re * z[c].im + l.im * z[c].re;
+                }
+                const REAL d = L[r * dim + r].re;
+                z[r].re = s.re / d; z[r].im = s.im / d;
+                q += z[r].re * z[r].re + z[r].im * z[r].im;
+            }
+#ifdef ORACLE_LONG_DOUBLE
+            const REAL ex = expl(q / 2);
+#else
+            const REAL ex = exp(q / 2);
+#endif
+            kadd(&acc, (((N - k) & 1) ? -1 : 1) * ex / pd);
+        }
+#pragma omp critical
+        { kadd(&tot, acc.s); kadd(&tot, -acc.c); }
+        free(B);
+    }
+    out2[0] = (double)tot.s; out2[1] = 0;
+}
+
+/* brs / ubrs (thewalrus/_permanent.py:198-249): sum over row-subset labels [j0, j1) of A (m x n; bit (m-1-i) of the
+ * label keeps row i) of (-1)^(m-|Y|) perm_bbfg(A_Y^H A_Y + E); E may be NULL (ubrs).  perm_bbfg includes its
+ * 2^(1-n) factor (:167).  out2 = {re, im}. */
+void oracle_brs_range(const double* A, const double* E, int m, int n, uint64_t j0, uint64_t j1, int nthreads,
+                      double* out2) {
+    kahan_t tot_r = {0, 0}, tot_i = {0, 0};
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        REAL* G = (REAL*)malloc(sizeof(REAL) * 2 * (size_t)n * n);
+        REAL rr[64], ri[64];
+        kahan_t acc_r = {0, 0}, acc_i = {0, 0};
+#pragma omp for schedule(dynamic, 1)
+        for (uint64_t j = j0; j < j1; ++j) {
+            int cnt = 0;
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) {
+                    G[2 * (a * n + b)] = E ? E[2 * ((size_t)a * n + b)] : 0;
+                    G[2 * (a * n + b) + 1] = E ? E[2 * ((size_t)a * n + b) + 1] : 0;
+                }
+            for (int i = 0; i < m; ++i) {
+                if (!((j >> (m - 1 - i)) & 1ull)) continue;
+                ++cnt;
+                for (int a = 0; a < n; ++a) {               /* G += conj(A[i, a]) A[i, b] */
+                    const REAL ar = A[2 * ((size_t)i * n + a)], ai = -A[2 * ((size_t)i * n + a) + 1];
+                    for (int b = 0; b < n; ++b) {
+                        const REAL br = A[2 * ((size_t)i * n + b)], bi = A[2 * ((size_t)i * n + b) + 1];
+                        G[2 * (a * n + b)] += ar * br - ai * bi;
+                        G[2 * (a * n + b) + 1] += ar * bi + ai * br;
+                    }
+                }
+            }
+            /* perm_bbfg(G): Gray-code Glynn over 2^(n-1) steps */
+            REAL pr_tot = 0, pi_tot = 0;
+            for (int c = 0; c < n; ++c) { rr[c] = 0; ri[c] = 0; }
+            for (int r = 0; r < n; ++r)
+                for (int c = 0; c < n; ++c) { rr[c] += G[2 * (r * n + c)]; ri[c] += G[2 * (r * n + c) + 1]; }
+            const uint64_t steps = n > 0 ? (1ull << (n - 1)) : 1;
+            for (uint64_t k = 0; k < steps; ++k) {
+                REAL pr = 1, pi = 0;
+                for (int c = 0; c < n; ++c) { const REAL t = pr * rr[c] - pi * ri[c]; pi = pr * ri[c] + pi * rr[c]; pr = t; }
+                if (k & 1ull) { pr_tot -= pr; pi_tot -= pi; } else { pr_tot += pr; pi_tot += pi; }
+                const uint64_t k1n = k + 1;
+                const int row = __builtin_ctzll(k1n);
+                if (row < n - 1 || (row < n && k1n < steps)) {
+                    const int set = (int)(((k1n ^ (k1n >> 1)) >> row) & 1ull);
+                    const REAL d = set ? -2 : 2;
+                    for (int c = 0; c < n; ++c) { rr[c] += d * G[2 * (row * n + c)]; ri[c] += d * G[2 * (row * n + c) + 1]; }
+                }
+            }
+            const REAL scale = (((m - cnt) & 1) ? -1 : 1) / (REAL)steps;
+            kadd(&acc_r, scale * pr_tot); kadd(&acc_i, scale * pi_tot);
+        }
+#pragma omp critical
+        { kadd(&tot_r, acc_r.s); kadd(&tot_r, -acc_r.c); kadd(&tot_i, acc_i.s); kadd(&tot_i, -acc_i.c); }
+        free(G);
+    }
+    out2[0] = (double)tot_r.s; out2[1] = (double)tot_i.s;
 }
 
 int oracle_max_threads(void) {
