@@ -176,13 +176,14 @@ def hafnian_sample_state(cov, samples, mean=None, hbar=2, cutoff=5, max_photons=
     del parallel
     _validate_cov(cov)
     ch = _Chain(cov, mean, hbar)
-    out = []
-    while len(out) < samples:
-        S = min(samples - len(out), 4096) if batch is None else int(batch)
+    out, have = [], 0
+    while have < samples:
+        S = min(samples - have, 4096) if batch is None else int(batch)
         det = _hafnian_chains(ch, S, cutoff, device)[:, ch.order_inv]
         keep = (det[:, -1] != cutoff) & (det.sum(axis=1) <= max_photons)
-        out.extend(det[keep][: samples - len(out)])
-    return np.vstack(out).astype(int) if out else np.zeros((0, ch.M), dtype=int)
+        out.append(det[keep][: samples - have])
+        have += len(out[-1])
+    return np.concatenate(out).astype(int) if out else np.zeros((0, ch.M), dtype=int)
 
 
 def hafnian_sample_graph(A, n_mean, samples=1, cutoff=5, max_photons=30, parallel=False, *, batch=None, device=None):
@@ -246,12 +247,13 @@ def torontonian_sample_state(cov, samples, mu=None, hbar=2, max_photons=30, fano
     del parallel
     _validate_cov(cov)
     ch = _Chain(cov, mu, hbar, scale=fanout)
-    out = []
-    while len(out) < samples:
-        S = min(samples - len(out), 1024) if batch is None else int(batch)
+    out, have = [], 0
+    while have < samples:
+        S = min(samples - have, 1024) if batch is None else int(batch)
         clicks, alive = _torontonian_chains(ch, S, fanout, cutoff, max_photons, device)
-        out.extend(clicks[alive][:, ch.order_inv][: samples - len(out)])
-    return np.vstack(out).astype(int) if out else np.zeros((0, ch.M), dtype=int)
+        out.append(clicks[alive][:, ch.order_inv][: samples - have])
+        have += len(out[-1])
+    return np.concatenate(out).astype(int) if out else np.zeros((0, ch.M), dtype=int)
 
 
 def torontonian_sample_graph(A, n_mean, samples=1, max_photons=30, fanout=10, cutoff=1, parallel=False, *, batch=None,
