@@ -18,10 +18,22 @@
 
 namespace wb {
 
-constexpr int TOR_THREADS = 512;       // torontonian: 16 warps hide the shared-memory / FP64 latency of the tree levels
+#ifndef WB_TOR_THREADS      // build-time overrides for the shape experiment (tools/gpu_tor_shape.py)
+#define WB_TOR_THREADS 256  // measured: 256 threads 1.23 ms, 512 threads 1.36 ms, 128 threads 1.42 ms at 2N = 48
+#endif
+#ifndef WB_TOR_DC
+#define WB_TOR_DC 9
+#endif
+#ifndef WB_TOR_G
+#define WB_TOR_G 5
+#endif
+#ifndef WB_TOR_SMEM_KB
+#define WB_TOR_SMEM_KB 225
+#endif
+constexpr int TOR_THREADS = WB_TOR_THREADS;  // CTA size of the torontonian (profiles/r01_tor_shape.txt)
 constexpr int TOR_THREADS_LOOP = 256;  // loop torontonian: the 5 x 5 register tail needs > 128 registers
-constexpr int TOR_DC = 9;        // modes expanded breadth-first inside a CTA
-constexpr int TOR_G = 5;         // log2(prefixes per CTA)
+constexpr int TOR_DC = WB_TOR_DC;      // modes expanded breadth-first inside a CTA
+constexpr int TOR_G = WB_TOR_G;        // log2(prefixes per CTA)
 constexpr int TOR_MAX_MODES = 32;
 
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
@@ -218,8 +230,8 @@ __host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, i
 // included children go to a pool that stays alive until the 2-mode tails have been summed in registers.
 template <int AUG, int THREADS>
 __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __restrict__ partials) {
-    constexpr int LOG_THREADS = THREADS == 512 ? 9 : 8;
-    static_assert(THREADS == 256 || THREADS == 512, "one node needs at least 4 threads at 64 nodes");
+    constexpr int LOG_THREADS = THREADS == 512 ? 9 : (THREADS == 256 ? 8 : 7);
+    static_assert(THREADS == 128 || THREADS == 256 || THREADS == 512, "power of two, at least one thread per parent node");
     extern __shared__ __align__(16) double smem_tor[];
     const int N = p.N, n2 = 2 * N + AUG, DC = p.DC, g = p.g, P = p.P;
     const int dg = 2 * (DC + g) + AUG, ldT = tor_ld(n2);
@@ -343,7 +355,7 @@ static void tor_shape(int N, int aug, int* P, int* g, int* DC) {
     *P = N - *DC;
     *g = *P < TOR_G ? *P : TOR_G;
     int a, b, c;
-    while (*g > 0 && tor_smem_plan(N, aug, *g, *DC, &a, &b, &c) > 225 * 1024) --*g;
+    while (*g > 0 && tor_smem_plan(N, aug, *g, *DC, &a, &b, &c) > (size_t)WB_TOR_SMEM_KB * 1024) --*g;
 }
 
 struct DevBufT {
@@ -404,7 +416,12 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1, TOR_THREADS_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0, TOR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
-    int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
+    int occ = 1;
+    if (aug) WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tor_kernel<1, TOR_THREADS_LOOP>, TOR_THREADS_LOOP, shm));
+    else WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tor_kernel<0, TOR_THREADS>, TOR_THREADS, shm));
+    if (occ < 1) occ = 1;
+    const uint64_t slots = (uint64_t)sms * occ;
+    int grid = (int)(groups < slots ? (groups ? groups : 1) : slots);
     if (grid > TOR_MAX_GRID) grid = TOR_MAX_GRID;
     tor_prep_kernel<<<8, 256, 0, st>>>(reinterpret_cast<const double2*>(dO), reinterpret_cast<const double2*>(dGamma), N, dB);
     if (aug) tor_kernel<1, TOR_THREADS_LOOP><<<grid, TOR_THREADS_LOOP, shm, st>>>(p, dpart);
