@@ -24,7 +24,10 @@ namespace wb {
 constexpr int BW_EMAX = 32;      // max edges per problem
 constexpr int BW_NVMAX = 64;     // max vertices of the big matrix
 constexpr int BW_WARPS = 8;      // warps per CTA
-constexpr int BW_CHUNK = 16;     // subsets per work item (patterns kernel)
+#ifndef WB_BW_CHUNK
+#define WB_BW_CHUNK 16
+#endif
+constexpr int BW_CHUNK = WB_BW_CHUNK;   // subsets per work item (patterns kernel)
 constexpr int BW_MAX_ORDER = 200;
 
 __device__ __forceinline__ void cfma(double2& acc, double2 a, double2 b) {
