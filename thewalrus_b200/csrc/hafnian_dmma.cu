@@ -22,7 +22,11 @@
 //   full tile tau < TF : w[tau][r] = element 4 tau + t + r m   (partners share a thread: swap is free)
 //   tail tile (TAIL)   : (wt_r, wt_i) = element 4 TF + (t >> 1) + (t & 1) m, partner in lane ^ 1.
 // The tail tile packs the last m mod 4 in {1, 2} vertex pairs with (re, im) interleaved so that sizes
-// like n = 50 (m = 25) waste one quarter of one tile instead of a whole tile row and column.
+// like n = 50 (m = 25) waste one quarter of one tile instead of a whole tile row and column.  With ONE pair in
+// the tail (m mod 4 = 1) the tail K-chunk is packed as well — positions 2, 3 carry the imaginary parts — and
+// costs two DMMAs per tile instead of four (haf_prep_kernel / haf_step, `packk`).
+// Launch shape: one CTA per SM, 12 warps for full-size problems, 4 or 8 warps when there are fewer groups of
+// four subsets than that, so small problems spread over all SMs (haf_pick_warps).
 #include <stdlib.h>
 #include "common.cuh"
 
