@@ -26,6 +26,8 @@ def _lib(long_double=False):
         lib.oracle_ltor_direct_range.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, _dp]
         lib.oracle_brs_range.argtypes = [_dp, _dp, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64,
                                          ctypes.c_int, _dp]
+        lib.oracle_lhaf_patterns.argtypes = [_dp, _dp, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int64,
+                                             ctypes.c_int, ctypes.c_int, _dp]
         lib.oracle_max_threads.restype = ctypes.c_int
         _libs[key] = lib
     return _libs[key]
@@ -120,3 +122,17 @@ def brs(A, E=None, j0=0, j1=None, threads=0, long_double=False):
     _lib(long_double).oracle_brs_range(pA, pE, m, n, j0, (1 << m) if j1 is None else j1, threads,
                                        out.ctypes.data_as(_dp))
     return complex(out[0], out[1])
+
+
+def lhaf_patterns(A, gamma, rpt, glynn=True, threads=0, long_double=False):
+    """``[loop_hafnian(A, gamma, reps=r) for r in rpt]`` (``gamma=None``: ``hafnian_repeated``), patterns in parallel
+    (thewalrus/_hafnian.py:581-631 per pattern, as quantum/fock_tensors.py:191-232 calls it)."""
+    A, pA = _c128(A)
+    pG = None
+    if gamma is not None:
+        gamma, pG = _c128(gamma)
+    rpt = np.ascontiguousarray(rpt, dtype=np.int32)
+    out = np.zeros(len(rpt), dtype=np.complex128)
+    _lib(long_double).oracle_lhaf_patterns(pA, pG, A.shape[0], rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                           len(rpt), 1 if glynn else 0, threads, out.view(np.float64).ctypes.data_as(_dp))
+    return out

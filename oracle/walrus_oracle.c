@@ -11,12 +11,18 @@
  *   oracle_tor_direct_range    thewalrus/_torontonian.py:123-154
  *   oracle_ltor_direct_range   thewalrus/_torontonian.py:369-412 (numba_ltor; parallel in the reference too)
  *   oracle_brs_range           thewalrus/_permanent.py:198-249 (brs / ubrs; the reference loop is serial)
+ *   oracle_lhaf_patterns       thewalrus/_hafnian.py:80-159, 162-180, 212-285, 315-356, 512-631: loop hafnians with
+ *                              repeated vertices (the per-pattern call of quantum/fock_tensors.py:191-232), one
+ *                              pattern per OpenMP task; power traces by the product chain for every order (the
+ *                              reference switches to La Budde beyond the matrix size, charpoly.py:319-326: same
+ *                              numbers)
  * Built twice by oracle/build.py: REAL = double (liboracle.so: checker + CPU baseline) and REAL = long
  * double (liboracle_ld.so: extended-precision yardstick for sampled ranges at n = 50/56).
  * Parity status: PINNED — tests/test_oracle_golden.py checks these against the committed outputs of the
  * reference itself (tests/golden/reference_outputs.json) and its known-answer tests.
  * Used only by tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference).
  */
+#include <complex.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -477,6 +483,178 @@ void oracle_brs_range(const double* A, const double* E, int m, int n, uint64_t j
         free(G);
     }
     out2[0] = (double)tot_r.s; out2[1] = (double)tot_i.s;
+}
+
+/* ---- loop hafnian with repeated vertices (general path) ------------------------------------------- */
+#ifdef ORACLE_LONG_DOUBLE
+typedef long double _Complex zc;
+#else
+typedef double _Complex zc;
+#endif
+#define ZC(re, im) ((REAL)(re) + (REAL)(im) * (zc)_Complex_I)
+
+/* matched_reps (_hafnian.py:80-159): greedy pairing by (count, index) descending.  Returns the number of edges. */
+static int lh_matched_reps(const int32_t* reps, int nv, int* ea, int* eb, int* er, int* odd) {
+    int cnt[128], live = 0, E = 0;
+    for (int i = 0; i < nv; ++i) { cnt[i] = reps[i]; live += cnt[i] > 0; }
+    for (;;) {
+        int i0 = -1, i1 = -1;
+        for (int i = nv - 1; i >= 0; --i) {       /* descending index: ties pick the larger index first */
+            if (cnt[i] <= 0) continue;
+            if (i0 < 0 || cnt[i] > cnt[i0]) { i1 = i0; i0 = i; }
+            else if (i1 < 0 || cnt[i] > cnt[i1]) i1 = i;
+        }
+        if (live == 0 || (live == 1 && cnt[i0] <= 1)) break;
+        if (live == 1 || cnt[i0] > 2 * cnt[i1]) {
+            ea[E] = i0; eb[E] = i0; er[E] = cnt[i0] / 2;
+            if (cnt[i0] & 1) cnt[i0] = 1; else { cnt[i0] = 0; --live; }
+        } else {
+            ea[E] = i0; eb[E] = i1; er[E] = cnt[i1];
+            cnt[i0] -= cnt[i1]; cnt[i1] = 0; --live;
+            if (cnt[i0] == 0) --live;
+        }
+        ++E;
+    }
+    *odd = -1;
+    for (int i = 0; i < nv; ++i) if (cnt[i] > 0) *odd = i;
+    return E;
+}
+
+static REAL lh_binom(int n, int k) {
+    REAL b = 1;
+    if (k > n - k) k = n - k;
+    for (int q = 0; q < k; ++q) b = b * (REAL)(n - q) / (REAL)(q + 1);
+    return b;
+}
+
+/* exp series of f / f_loop / f_loop_odd (`comb` loops, _hafnian.py:196-209, 228-242, 264-285) */
+static zc lh_exp_series(const zc* fac, int order, zc* comb, zc* tmp) {
+    for (int i = 0; i <= order; ++i) comb[i] = 0;
+    comb[0] = 1;
+    for (int i = 1; i <= order; ++i) {
+        for (int q = 0; q <= order; ++q) tmp[q] = comb[q];
+        zc pw = 1;
+        for (int j = 1; j <= order / i; ++j) {
+            pw = pw * fac[i] / (REAL)j;
+            for (int q = i * j; q <= order; ++q) tmp[q] += comb[q - i * j] * pw;
+        }
+        for (int q = 0; q <= order; ++q) comb[q] = tmp[q];
+    }
+    return comb[order];
+}
+
+/* one loop hafnian: A nv x nv, D nv (or NULL: hafnian_repeated), reps nv */
+static zc lh_one(const double* A, const double* D, int nv, const int32_t* reps, int glynn) {
+    int N = 0;
+    for (int i = 0; i < nv; ++i) N += reps[i];
+    if (N == 0) return 1;
+    if (!D && (N & 1)) return 0;
+    if (D && N == 1) { for (int i = 0; i < nv; ++i) if (reps[i] == 1) return ZC(D[2 * i], D[2 * i + 1]); }
+    int ea[64], eb[64], er[64], odd;
+    const int E = lh_matched_reps(reps, nv, ea, eb, er, &odd);
+    if (odd >= 0 && !D) return 0;
+    const int has_odd = odd >= 0;
+    const int order = has_odd ? N : N / 2, T = N / 2, smax = 2 * E;
+    zc* buf = (zc*)malloc(sizeof(zc) * ((size_t)3 * smax * smax + 6 * (size_t)smax + 4 * (size_t)(order + 2) + (size_t)(T + 2)));
+    zc *M = buf, *P = M + (size_t)smax * smax, *Q = P + (size_t)smax * smax;
+    zc *xd = Q + (size_t)smax * smax, *dd = xd + smax, *d2 = dd + smax, *ov = d2 + smax, *xd2 = ov + smax, *spare = xd2 + smax;
+    zc *fac = spare + smax, *comb = fac + order + 2, *tmp = comb + order + 2, *ptr = tmp + order + 2;
+    (void)spare;
+    uint64_t steps = 1;
+    for (int e = 0; e < E; ++e) steps *= (uint64_t)((e == 0 && glynn && !has_odd) ? (er[0] + 2) / 2 : er[e] + 1);
+    int kept[64], rows[128];
+    REAL delta[128];
+    zc H = 0;
+    for (uint64_t j = 0; j < steps; ++j) {
+        uint64_t num = j;
+        for (int e = E - 1; e >= 0; --e) { kept[e] = (int)(num % (uint64_t)(er[e] + 1)); num /= (uint64_t)(er[e] + 1); }
+        int k = 0, esum = 0, d0zero = 0;
+        REAL w = 1;
+        for (int e = 0; e < E; ++e) {
+            esum += kept[e];
+            w *= lh_binom(er[e], kept[e]);
+            const int d = glynn ? 2 * kept[e] - er[e] : kept[e];
+            if (e == 0) d0zero = (d == 0);
+            if (d != 0) { rows[k] = e; delta[k] = (REAL)d; ++k; }
+        }
+        for (int a = 0; a < k; ++a) { const int e = rows[a]; rows[a] = ea[e]; rows[k + a] = eb[e]; delta[k + a] = delta[a]; }
+        const int s = 2 * k;
+        /* get_submatrices (:315-356): M[:, c] = delta_c * A[rows, rows][:, swap(c)] */
+        for (int r = 0; r < s; ++r)
+            for (int c = 0; c < s; ++c) {
+                const int sc = c < k ? c + k : c - k;
+                const size_t at = 2 * ((size_t)rows[r] * nv + rows[sc]);
+                M[r * s + c] = delta[c] * ZC(A[at], A[at + 1]);
+            }
+        for (int c = 0; c < s; ++c) {
+            const int sc = c < k ? c + k : c - k;
+            if (D) { xd[c] = delta[c] * ZC(D[2 * rows[sc]], D[2 * rows[sc] + 1]); dd[c] = ZC(D[2 * rows[c]], D[2 * rows[c] + 1]); }
+            if (has_odd) { const size_t at = 2 * ((size_t)odd * nv + rows[sc]); ov[c] = delta[c] * ZC(A[at], A[at + 1]); }
+        }
+        /* power traces tr(M^i), i = 1..T, by the product chain (charpoly.py:316-318) */
+        for (int i = 0; i < s * s; ++i) P[i] = M[i];
+        for (int i = 1; i <= T; ++i) {
+            zc tr = 0;
+            for (int r = 0; r < s; ++r) tr += P[r * s + r];
+            ptr[i] = tr;
+            if (i < T) {
+                for (int r = 0; r < s; ++r)
+                    for (int c = 0; c < s; ++c) {
+                        zc a = 0;
+                        for (int q = 0; q < s; ++q) a += P[r * s + q] * M[q * s + c];
+                        Q[r * s + c] = a;
+                    }
+                zc* t2 = P; P = Q; Q = t2;
+            }
+        }
+        REAL pre = (((N / 2 - esum) & 1) ? -1 : 1) * w;
+        if (!has_odd) {                                   /* f / f_loop (:183-242) */
+            for (int c = 0; c < s; ++c) xd2[c] = D ? xd[c] : 0;
+            for (int i = 1; i <= order; ++i) {
+                zc l = 0;
+                if (D) {
+                    for (int c = 0; c < s; ++c) l += xd2[c] * dd[c];
+                    for (int c = 0; c < s; ++c) { zc a = 0; for (int q = 0; q < s; ++q) a += xd2[q] * M[q * s + c]; d2[c] = a; }
+                    for (int c = 0; c < s; ++c) xd2[c] = d2[c];
+                }
+                fac[i] = ptr[i] / (REAL)(2 * i) + l / 2;
+            }
+            if (glynn && d0zero) pre *= (REAL)0.5;
+        } else {                                          /* f_loop_odd (:246-285) */
+            for (int i = 1; i <= order; ++i) {
+                if (i == 1) fac[i] = ZC(D[2 * odd], D[2 * odd + 1]);
+                else if ((i & 1) == 0) {
+                    zc l = 0;
+                    for (int c = 0; c < s; ++c) l += xd[c] * dd[c];
+                    fac[i] = ptr[i / 2] / (REAL)i + l / 2;
+                } else {
+                    zc o = 0;
+                    for (int c = 0; c < s; ++c) o += ov[c] * dd[c];
+                    fac[i] = o;
+                    for (int r = 0; r < s; ++r) { zc a = 0; for (int q = 0; q < s; ++q) a += M[r * s + q] * dd[q]; d2[r] = a; }
+                    for (int r = 0; r < s; ++r) dd[r] = d2[r];
+                }
+            }
+        }
+        H += pre * lh_exp_series(fac, order, comb, tmp);
+    }
+    if (glynn) H *= (REAL)ldexp(1.0, -(has_odd ? N / 2 : N / 2 - 1));
+    free(buf);
+    return H;
+}
+
+/* out[b] = loop_hafnian(A, D, reps = rpt[b]) (hafnian_repeated when D is NULL) for b < B; patterns in parallel */
+void oracle_lhaf_patterns(const double* A, const double* D, int nv, const int32_t* rpt, int64_t B, int glynn,
+                          int nthreads, double* out) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t b = 0; b < B; ++b) {
+        const zc v = lh_one(A, D, nv, rpt + (size_t)b * nv, glynn);
+        out[2 * b] = (double)creall(v);
+        out[2 * b + 1] = (double)cimagl(v);
+    }
 }
 
 int oracle_max_threads(void) {
