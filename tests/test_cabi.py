@@ -54,3 +54,28 @@ def test_argument_checks_do_not_need_a_gpu():
     assert lib.wb200_tor_num_prefixes(24, ctypes.byref(cnt)) == 0 and cnt.value == 1 << 15
     assert lib.wb200_tor_num_prefixes(40, ctypes.byref(cnt)) == -3
     assert b"modes" in lib.wb200_last_error()
+
+
+def test_argument_checks_of_the_newer_entry_points():
+    import numpy as np
+
+    lib = _lib.load()
+    O = np.zeros(2 * 8 * 8)
+    out = np.zeros(4)
+    assert lib.wb200_ltor_host(0, _lib.dptr(O), None, 4, 0, 1, _lib.dptr(out), None) == -1      # gamma is required
+    assert b"gamma" in lib.wb200_last_error()
+    A = np.zeros(2 * 2 * 3 * 3)
+    rpt = np.ones((2, 3), dtype=np.int32)
+    prpt = rpt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    res = np.zeros(4)
+    # two matrices but no index / index out of range / table of loop vectors without an index
+    assert lib.wb200_lhaf_matrices_host(0, _lib.dptr(A), 2, None, None, 0, None, 3, prpt, 2, 1, _lib.dptr(res), None) == -1
+    bad = np.array([0, 2], dtype=np.int32)
+    assert lib.wb200_lhaf_matrices_host(0, _lib.dptr(A), 2, bad.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), None, 0,
+                                        None, 3, prpt, 2, 1, _lib.dptr(res), None) == -1
+    assert b"A_index" in lib.wb200_last_error()
+    g = np.zeros(2 * 2 * 3)
+    assert lib.wb200_lhaf_patterns_multi_host(0, _lib.dptr(A), _lib.dptr(g), 2, None, 3, prpt, 2, 1, _lib.dptr(res),
+                                              None) == -1
+    assert lib.wb200_lhaf_patterns_multi_host(0, _lib.dptr(A), None, 0, None, 65, prpt, 2, 1, _lib.dptr(res), None) == -3
+    assert lib.wb200_release_scratch() == 0
