@@ -229,3 +229,17 @@ def test_hafnian_batch_exact_matchings_and_checks():
         wb.hafnian_batch(np.zeros((2, 3, 4)))
     assert wb.hafnian_batch(np.zeros((0, 4, 4))).shape == (0,)
     assert np.all(wb.hafnian_batch(np.zeros((3, 0, 0))) == 1)
+
+
+# ------------------------------------------------------------------------------ remaining drop-in names
+def test_permanent_repeated_and_driver_aliases():
+    """permanent_repeated (thewalrus/_permanent.py:171-195) and the numba driver names the reference exports
+    (thewalrus/__init__.py:126-134)."""
+    rng = np.random.default_rng(71)
+    A = rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5))
+    rpt = [2, 1, 0, 3, 1]
+    rows = [i for i, r in enumerate(rpt) for _ in range(r)]
+    assert relv(wb.permanent_repeated(A, rpt), wo.perm_bbfg(A[np.ix_(rows, rows)])) < TOL
+    O, gamma = _rand_O_gamma(5, 72)
+    assert wb.numba_tor(O) == wb.tor(O) == wb.rec_torontonian(O)
+    assert wb.numba_ltor(O, gamma) == wb.ltor(O, gamma) == wb.rec_ltorontonian(O, gamma)

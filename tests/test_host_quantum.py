@@ -114,3 +114,22 @@ def test_log_factorial_table_matches_gammaln():
     assert np.allclose(q._log_factorial_sums(pats), gammaln(pats + 1.0).sum(axis=1), rtol=1e-14, atol=1e-13)
     assert np.all(q._log_factorial_sums(np.zeros((3, 4), dtype=int)) == 0)
     assert q._log_factorial_sums(np.zeros((0, 4), dtype=int)).shape == (0,)
+
+
+def test_permanent_repeated_host_logic(monkeypatch):
+    """permanent_repeated builds [[0, A], [A^T, 0]] with (rpt, rpt) (thewalrus/_permanent.py:171-195).  The subset
+    sum is replaced by the oracle here (no GPU on this box); the front-end bookkeeping is what runs."""
+    from thewalrus_b200 import _hafnian
+
+    def oracle_sum(Ax, Dx, edge_reps, oddloop, oddV, glynn, group, device):
+        return wo.calc_hafnian(Ax, edge_reps, glynn) if Dx is None else wo.calc_loop_hafnian(Ax, Dx, edge_reps, oddloop, oddV, glynn)
+
+    monkeypatch.setattr(_hafnian, "_subset_sum", oracle_sum)
+    rng = np.random.default_rng(21)
+    A = rng.standard_normal((3, 3)) + 1j * rng.standard_normal((3, 3))
+    rpt = [2, 0, 1]
+    rows = [0, 0, 2]
+    want = wo.perm_bbfg(A[np.ix_(rows, rows)])
+    got = wb.permanent_repeated(A, rpt)
+    assert abs(got - want) < 1e-12 * max(1.0, abs(want))
+    assert wb.version() == wb.__version__

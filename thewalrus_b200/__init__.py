@@ -17,10 +17,34 @@ from ._hafnian import (  # noqa: F401
 )
 from .loop_hafnian_batch import loop_hafnian_batch  # noqa: F401
 from .loop_hafnian_batch_gamma import loop_hafnian_batch_gamma  # noqa: F401
-from ._permanent import brs, fock_prob, fock_threshold_prob, perm, perm_bbfg, perm_ryser, ubrs  # noqa: F401
-from ._torontonian import ltor, numba_vac_prob, threshold_detection_prob, tor, tor_input_checks  # noqa: F401
+from ._permanent import (  # noqa: F401
+    brs,
+    fock_prob,
+    fock_threshold_prob,
+    perm,
+    perm_bbfg,
+    perm_ryser,
+    permanent_repeated,
+    ubrs,
+)
+from ._torontonian import (  # noqa: F401
+    ltor,
+    numba_ltor,
+    numba_tor,
+    numba_vac_prob,
+    rec_ltorontonian,
+    rec_torontonian,
+    threshold_detection_prob,
+    tor,
+    tor_input_checks,
+)
 from ._montrealer import lmtl, mtl  # noqa: F401
 from . import quantum, samples  # noqa: F401
 from .quantum import density_matrix_element, probabilities, probabilities_batch  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def version():
+    """Version string (thewalrus/__init__.py:166-175)."""
+    return __version__

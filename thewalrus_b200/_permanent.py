@@ -3,7 +3,7 @@ import numpy as np
 
 from . import _engine
 
-__all__ = ["perm", "perm_bbfg", "perm_ryser", "brs", "ubrs", "fock_prob", "fock_threshold_prob"]
+__all__ = ["perm", "perm_bbfg", "perm_ryser", "permanent_repeated", "brs", "ubrs", "fock_prob", "fock_threshold_prob"]
 
 
 def _steps(n, ryser):
@@ -84,6 +84,18 @@ def perm(A, method="bbfg", *, group=None, device=None):
     if method == "ryser":
         return perm_ryser(A, group=group, device=device)
     raise ValueError("method must be 'bbfg', 'glynn' or 'ryser'")
+
+
+def permanent_repeated(A, rpt, *, group=None, device=None):
+    """Permanent of ``A`` with row/column ``i`` repeated ``rpt[i]`` times (thewalrus/_permanent.py:171-195):
+    ``perm(A_rpt) = haf([[0, A], [A^T, 0]]_(rpt, rpt))``, evaluated by the repeated-edge hafnian kernel."""
+    from ._hafnian import hafnian_repeated
+
+    A = np.asarray(A)
+    n = A.shape[0]
+    Z = np.zeros((n, n), dtype=A.dtype)
+    B = np.vstack([np.hstack([Z, A]), np.hstack([A.T, Z])])
+    return hafnian_repeated(B, list(rpt) * 2, loop=False, group=group, device=device)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -5,7 +5,8 @@ import numpy as np
 from . import _engine
 from ._prep import dd_sum
 
-__all__ = ["tor", "ltor", "threshold_detection_prob", "numba_vac_prob", "tor_input_checks"]
+__all__ = ["tor", "ltor", "threshold_detection_prob", "numba_vac_prob", "tor_input_checks", "numba_tor", "rec_torontonian",
+           "numba_ltor", "rec_ltorontonian"]
 
 
 def tor_input_checks(A, loops=None):
@@ -111,3 +112,25 @@ def threshold_detection_prob(mu, cov, det_pattern, hbar=2, atol=1e-10, rtol=1e-1
     gamma = (inv_sigma @ alpha).conj()
     O_red = np.ascontiguousarray(O[np.ix_(rows, rows)])
     return numba_vac_prob(alpha, sigma) * ltor(O_red, gamma[rows], group=group, device=device).real
+
+
+# The reference exports its four numba drivers as well (thewalrus/__init__.py:126-134); callers that use them
+# directly (threshold_detection_prob does, _torontonian.py:120) get the same GPU evaluation.
+def numba_tor(O, **kw):
+    """thewalrus/_torontonian.py:123-154."""
+    return tor(np.asarray(O), recursive=False, **kw)
+
+
+def rec_torontonian(A, **kw):
+    """thewalrus/_torontonian.py:227-247."""
+    return tor(np.asarray(A), recursive=True, **kw)
+
+
+def numba_ltor(O, gamma, **kw):
+    """thewalrus/_torontonian.py:369-412."""
+    return ltor(np.asarray(O), np.asarray(gamma), recursive=False, **kw)
+
+
+def rec_ltorontonian(A, gamma, **kw):
+    """thewalrus/_torontonian.py:320-345."""
+    return ltor(np.asarray(A), np.asarray(gamma), recursive=True, **kw)
