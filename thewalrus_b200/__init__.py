@@ -40,7 +40,14 @@ from ._torontonian import (  # noqa: F401
 )
 from ._montrealer import lmtl, mtl  # noqa: F401
 from . import quantum, samples  # noqa: F401
-from .quantum import density_matrix_element, probabilities, probabilities_batch  # noqa: F401
+from .quantum import (  # noqa: F401
+    density_matrix,
+    density_matrix_element,
+    probabilities,
+    probabilities_batch,
+    pure_state_amplitude,
+    state_vector,
+)
 
 __version__ = "0.1.0"
 

@@ -14,6 +14,7 @@ import numpy as np
 from . import _engine
 
 __all__ = ["Qmat", "Amat", "Covmat", "Xmat", "sympmat", "complex_to_real_displacements", "density_matrix_element",
+           "density_matrix", "pure_state_amplitude", "state_vector", "is_pure_cov",
            "probabilities", "probabilities_batch", "lhaf_patterns", "photon_number_mean_vector", "adj_scaling",
            "adj_to_qmat", "gen_Qmat_from_graph", "is_valid_cov", "is_classical_cov", "williamson"]
 
@@ -123,6 +124,108 @@ def probabilities(mu, cov, cutoff, parallel=False, hbar=2.0, rtol=1e-05, atol=1e
     M = len(mu) // 2
     pats = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(-1, M)
     return probabilities_batch(mu, cov, pats, hbar=hbar, group=group, device=device).reshape([cutoff] * M)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fock-space tensors: every element is one loop hafnian, all of them in ONE batched GPU call
+# ---------------------------------------------------------------------------------------------------
+def is_pure_cov(cov, hbar=2, rtol=1e-05, atol=1e-08):
+    """Valid covariance with purity 1 / sqrt(det(2 cov / hbar)) = 1 (quantum/gaussian_checks.py:60-76)."""
+    if not is_valid_cov(cov, hbar=hbar, rtol=rtol, atol=atol):
+        return False
+    purity = 1 / np.sqrt(np.linalg.det(2 * np.asarray(cov) / hbar))
+    return bool(np.allclose(purity, 1.0, rtol=rtol, atol=atol))
+
+
+def _pure_parts(mu, cov, hbar, tol):
+    """(B*, gamma or None, alpha, det Q) of a pure state (fock_tensors.py:66-76): the amplitude of |i> is
+    lhaf(B*, gamma, reps = i) with gamma = alpha - B* alpha*."""
+    N = len(cov) // 2
+    beta = complex_to_real_displacements(mu, hbar=hbar)
+    Bc = np.ascontiguousarray(Amat(cov, hbar=hbar)[:N, :N].conj())
+    alpha = beta[:N]
+    gamma = None if np.linalg.norm(alpha) < tol else alpha - Bc @ alpha.conj()
+    return Bc, gamma, alpha, np.linalg.det(Qmat(cov, hbar=hbar))
+
+
+def _amplitudes(Bc, gamma, patterns, detQ, group, device):
+    """lhaf(B*, gamma, i) / sqrt(prod i! sqrt(det Q)) for every row i of ``patterns`` (one GPU call)."""
+    patterns = np.ascontiguousarray(patterns, dtype=np.int32)
+    lh = lhaf_patterns(Bc, gamma, patterns, group=group, device=device)
+    return lh * np.exp(-0.5 * _log_factorial_sums(patterns)) / np.sqrt(np.sqrt(detQ))
+
+
+def pure_state_amplitude(mu, cov, i, include_prefactor=True, tol=1e-10, hbar=2, check_purity=True, *, device=None):
+    """<i|psi> of a pure Gaussian state (fock_tensors.py:45-105)."""
+    if check_purity and not is_pure_cov(cov, hbar=hbar, rtol=1e-05, atol=1e-08):
+        raise ValueError("The covariance matrix does not correspond to a pure state")
+    Bc, gamma, alpha, detQ = _pure_parts(mu, cov, hbar, tol)
+    amp = complex(_amplitudes(Bc, gamma, np.array([list(i)]), detQ, None, device)[0])
+    if include_prefactor:
+        amp *= np.exp(-0.5 * (np.linalg.norm(alpha) ** 2 - alpha.conj() @ Bc @ alpha.conj()))
+    return amp
+
+
+def _insert_post_selected(free, N, post_select):
+    """Full photon-number patterns [len(free), N] from the free-mode indices, post-selected modes filled in."""
+    free = np.asarray(free, dtype=np.int32)
+    full = np.zeros((len(free), N), dtype=np.int32)
+    cols = [m for m in range(N) if m not in post_select]
+    full[:, cols] = free
+    for m, v in post_select.items():
+        full[:, m] = v
+    return full
+
+
+def state_vector(mu, cov, post_select=None, normalize=False, cutoff=5, hbar=2, check_purity=True, *, group=None,
+                 device=None, **kwargs):
+    """State vector of a (PNR post-selected) pure Gaussian state, shape ``[cutoff] * M`` (fock_tensors.py:108-190).
+    The reference takes the multidimensional-Hermite route without post-selection and one hafnian per element with
+    it; here both are the same batched loop-hafnian call.  ``choi_r`` (the rescaling :func:`fock_tensor` asks for,
+    :162-169) is honoured."""
+    if check_purity and not is_pure_cov(cov, hbar=hbar, rtol=1e-05, atol=1e-08):
+        raise ValueError("The covariance matrix does not correspond to a pure state")
+    N = len(cov) // 2
+    Bc, gamma, alpha, detQ = _pure_parts(mu, cov, hbar, 0.0)        # the reference never drops gamma here
+    pref = np.exp(-0.5 * (np.linalg.norm(alpha) ** 2 - alpha.conj() @ Bc @ alpha.conj()))
+    post_select = dict(post_select or {})
+    choi_r = kwargs.get("choi_r", None)
+    if choi_r is not None and not post_select:
+        resc = np.concatenate([np.ones(N // 2), np.ones(N // 2) / np.tanh(choi_r)])
+        Bc = np.ascontiguousarray(resc[:, None] * Bc * resc[None, :])
+        gamma = resc * gamma
+        detQ = np.linalg.det(Qmat(cov, hbar=hbar) / np.cosh(choi_r))
+    M = N - len(post_select)
+    free = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(-1, M)
+    pats = _insert_post_selected(free, N, post_select)
+    psi = (pref * _amplitudes(Bc, gamma, pats, detQ.real if not post_select else detQ, group, device)).reshape([cutoff] * M)
+    if normalize:
+        psi = psi / np.sqrt(np.sum(np.abs(psi) ** 2))
+    return psi
+
+
+def density_matrix(mu, cov, post_select=None, normalize=False, cutoff=5, hbar=2, *, group=None, device=None):
+    """Density matrix of a (PNR post-selected) Gaussian state in the Strawberry Fields index order
+    (ket_1, bra_1, ket_2, bra_2, ...), shape ``[cutoff] * 2M`` (fock_tensors.py:235-300).  Every element is
+    ``density_matrix_element``; all ``cutoff^(2M)`` of them go through one batched GPU call."""
+    N = len(mu) // 2
+    post_select = dict(post_select or {})
+    M = N - len(post_select)
+    A, gamma = _state(mu, cov, hbar, 1e-10)
+    free = np.array(list(product(range(cutoff), repeat=2 * M)), dtype=np.int32).reshape(-1, 2 * M)
+    el0 = _insert_post_selected(free[:, :M], N, post_select)
+    el1 = _insert_post_selected(free[:, M:], N, post_select)
+    rpt = np.concatenate([el0, el1], axis=1)
+    vals = lhaf_patterns(A, gamma, rpt, group=group, device=device) * np.exp(-0.5 * _log_factorial_sums(rpt))
+    vals = vals * _prefactor(mu, cov, hbar=hbar)
+    # the reference stores element (i, j) at index (j_1, i_1, j_2, i_2, ...) (:283-285)
+    rho = vals.reshape([cutoff] * (2 * M))                    # axes (i_1..i_M, j_1..j_M)
+    order = [ax for m in range(M) for ax in (M + m, m)]
+    rho = np.ascontiguousarray(rho.transpose(order))
+    if normalize:
+        back = np.arange(2 * M).reshape([M, 2]).T.flatten()
+        rho = rho / np.trace(rho.transpose(back).reshape([cutoff**M, cutoff**M])).real
+    return rho
 
 
 # ---------------------------------------------------------------------------------------------------
