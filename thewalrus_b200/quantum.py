@@ -347,3 +347,22 @@ def williamson(V, rtol=1e-05, atol=1e-08):
     nu = 1.0 / np.abs(beta)
     dd = np.concatenate([nu, nu])
     return np.diag(dd), (root @ O) / np.sqrt(dd)
+
+
+# photon-number / click statistics live in thewalrus_b200.moments; the reference exposes them from
+# thewalrus.quantum, so they are re-exported here (imported last: moments imports this module)
+from .moments import (  # noqa: E402,F401
+    click_cumulant,
+    mean_clicks,
+    normal_ordered_expectation,
+    photon_number_covar,
+    photon_number_covmat,
+    photon_number_cumulant,
+    photon_number_expectation,
+    photon_number_mean,
+    photon_number_moment,
+    photon_number_squared_expectation,
+    reduced_gaussian,
+    s_ordered_expectation,
+    variance_clicks,
+)
