@@ -39,7 +39,8 @@ from ._torontonian import (  # noqa: F401
     tor_input_checks,
 )
 from ._montrealer import lmtl, mtl  # noqa: F401
-from . import moments, quantum, samples  # noqa: F401
+from . import quantum  # noqa: F401  (first: quantum re-exports moments at its end, moments imports quantum)
+from . import moments, samples  # noqa: F401
 from .quantum import (  # noqa: F401
     density_matrix,
     density_matrix_element,
