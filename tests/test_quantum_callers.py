@@ -85,3 +85,43 @@ def test_gpu_pure_state_callers_vs_reference(gold):
 @pytest.mark.gpu
 def test_gpu_density_matrix_vs_reference(gold):
     _check_mixed(gold)
+
+
+# ------------------------------------------------------------------------------------------- fock_tensor, loss, noise
+@pytest.fixture(scope="module")
+def gold_ft():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_fock_tensor.json")) as fh:
+        return json.load(fh)
+
+
+def _check_fock_tensor(gold_ft):
+    for c in gold_ft["fock_tensor"]:
+        got = q.fock_tensor(np.array(c["S"]), dec(c["alpha"]), c["cutoff"], sf_order=c["sf_order"])
+        want = dec(c["value"])
+        assert got.shape == want.shape and _close(got, want, tol=1e-9)
+
+
+def test_fock_tensor_vs_reference(gold_ft, cpu_kernel):
+    _check_fock_tensor(gold_ft)
+    with pytest.raises(ValueError, match="not symplectic"):
+        q.fock_tensor(2 * np.identity(2), np.zeros(1), 3)
+    with pytest.raises(ValueError, match="compatible dimensions"):
+        q.fock_tensor(np.identity(2), np.zeros(2), 3)
+
+
+def test_loss_and_noise_updates_vs_reference(gold_ft):
+    for c in gold_ft["loss"]:
+        p = np.array(c["probs"])
+        assert np.allclose(q.update_probabilities_with_loss(c["etas"], p), c["lossy"], rtol=1e-12, atol=1e-15)
+        assert np.allclose(q.update_probabilities_with_noise([np.array(n) for n in c["noise"]], p), c["noisy"], rtol=1e-12, atol=1e-15)
+        assert np.allclose(q.loss_mat(0.3, 5), c["loss_mat"], rtol=1e-12, atol=1e-15)
+    assert np.array_equal(q.loss_mat(1.0, 4), np.identity(4))
+    with pytest.raises(ValueError, match="between 0 and 1"):
+        q.loss_mat(1.5, 3)
+    with pytest.raises(ValueError, match="incompatible dimensions"):
+        q.update_probabilities_with_loss([0.5], np.ones((2, 2)))
+
+
+@pytest.mark.gpu
+def test_gpu_fock_tensor_vs_reference(gold_ft):
+    _check_fock_tensor(gold_ft)

@@ -14,7 +14,8 @@ import numpy as np
 from . import _engine
 
 __all__ = ["Qmat", "Amat", "Covmat", "Xmat", "sympmat", "complex_to_real_displacements", "density_matrix_element",
-           "density_matrix", "pure_state_amplitude", "state_vector", "is_pure_cov",
+           "density_matrix", "pure_state_amplitude", "state_vector", "fock_tensor", "is_pure_cov", "is_symplectic",
+           "loss_mat", "update_probabilities_with_loss", "update_probabilities_with_noise",
            "probabilities", "probabilities_batch", "lhaf_patterns", "photon_number_mean_vector", "adj_scaling",
            "adj_to_qmat", "gen_Qmat_from_graph", "is_valid_cov", "is_classical_cov", "williamson"]
 
@@ -226,6 +227,86 @@ def density_matrix(mu, cov, post_select=None, normalize=False, cutoff=5, hbar=2,
         back = np.arange(2 * M).reshape([M, 2]).T.flatten()
         rho = rho / np.trace(rho.transpose(back).reshape([cutoff**M, cutoff**M])).real
     return rho
+
+
+def is_symplectic(S, rtol=1e-05, atol=1e-08):
+    """S^T Omega S = Omega (thewalrus/symplectic.py is_symplectic)."""
+    S = np.asarray(S)
+    if S.ndim != 2 or S.shape[0] != S.shape[1] or S.shape[0] % 2:
+        return False
+    Om = sympmat(S.shape[0] // 2)
+    return bool(np.allclose(S.T @ Om @ S, Om, rtol=rtol, atol=atol))
+
+
+def fock_tensor(S, alpha, cutoff, choi_r=np.arcsinh(1.0), check_symplectic=True, sf_order=False, rtol=1e-05,
+                atol=1e-08, *, group=None, device=None):
+    """Fock representation of the Gaussian unitary (S, alpha) up to ``cutoff``, shape ``[cutoff] * 2l``
+    (fock_tensors.py:303-389) by the Choi-Jamiolkowski trick: the unitary acts on one half of l two-mode squeezed
+    vacua (squeezing ``choi_r``) and the tensor is that 2l-mode pure state's vector with the ancilla amplitudes
+    rescaled — ``state_vector(..., choi_r=choi_r)``, i.e. ``cutoff^(2l)`` loop hafnians in one batched call.
+    (The reference special-cases passive S through its Hermite-polynomial routine; the same path serves both here.)"""
+    S = np.asarray(S)
+    if check_symplectic and not is_symplectic(S, rtol=rtol, atol=atol):
+        raise ValueError("The matrix S is not symplectic")
+    l = S.shape[0] // 2
+    if l != len(alpha):
+        raise ValueError("The matrix S and the vector alpha do not have compatible dimensions")
+    ch, sh, zh = np.cosh(choi_r) * np.identity(l), np.sinh(choi_r) * np.identity(l), np.zeros((l, l))
+    S_choi = np.block([[ch, sh, zh, zh], [sh, ch, zh, zh], [zh, zh, ch, -sh], [zh, zh, -sh, ch]])
+    S_big = np.identity(4 * l)                       # S acting on modes 0..l-1 of 2l modes
+    w = np.arange(l)
+    for (r0, c0), blk in (((0, 0), S[:l, :l]), ((0, 2 * l), S[:l, l:]), ((2 * l, 0), S[l:, :l]), ((2 * l, 2 * l), S[l:, l:])):
+        S_big[np.ix_(w + r0, w + c0)] = blk
+    S_exp = S_big @ S_choi
+    alphat = np.concatenate([np.asarray(alpha, dtype=np.complex128), np.zeros(l)])
+    mu = np.concatenate([2 * alphat.real, 2 * alphat.imag])
+    tensor = state_vector(mu, S_exp @ S_exp.T, normalize=False, cutoff=cutoff, hbar=2, check_purity=False,
+                          choi_r=choi_r, group=group, device=device)
+    if sf_order:
+        return tensor.transpose([ax for i in range(l) for ax in (i, i + l)])
+    return tensor
+
+
+def loss_mat(eta, cutoff):
+    """Binomial loss matrix L[n, k] = C(n, k) eta^k (1 - eta)^(n - k) (fock_tensors.py:432-458)."""
+    from scipy.special import comb
+
+    if eta < 0.0 or eta > 1.0:
+        raise ValueError("The transmission parameter eta should be a number between 0 and 1.")
+    if eta == 1.0:
+        return np.identity(cutoff)
+    n, k = np.arange(cutoff)[:, None], np.arange(cutoff)[None, :]
+    return np.where(k <= n, comb(n, k) * eta ** k * (1.0 - eta) ** np.maximum(n - k, 0), 0.0)
+
+
+def update_probabilities_with_loss(etas, probs):
+    """Photon-number distribution after per-mode loss (fock_tensors.py:461-486): contract every axis with its
+    loss matrix."""
+    probs = np.asarray(probs)
+    if probs.ndim != len(etas):
+        raise ValueError("The list of transmission etas and the tensor of probabilities probs have incompatible dimensions.")
+    cutoff = probs.shape[0]
+    for axis, eta in enumerate(etas):
+        probs = np.moveaxis(np.tensordot(loss_mat(eta, cutoff), probs, axes=([0], [axis])), 0, axis)
+    return probs
+
+
+def update_probabilities_with_noise(probs_noise, probs):
+    """Photon-number distribution after adding independent per-mode noise counts (fock_tensors.py:508-538): a
+    truncated convolution along every axis."""
+    probs = np.asarray(probs)
+    if probs.ndim != len(probs_noise):
+        raise ValueError("The list of probability distributions probs_noise and the tensor of probabilities probs have incompatible dimensions.")
+    cutoff = probs.shape[0]
+    for axis, noise in enumerate(probs_noise):
+        noise = np.asarray(noise)
+        moved = np.moveaxis(probs, axis, 0)
+        out = np.zeros_like(moved)
+        for i in range(cutoff):
+            for j in range(min(i + 1, len(noise))):
+                out[i] += moved[i - j] * noise[j]
+        probs = np.moveaxis(out, 0, axis)
+    return probs
 
 
 # ---------------------------------------------------------------------------------------------------
