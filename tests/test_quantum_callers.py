@@ -125,3 +125,37 @@ def test_loss_and_noise_updates_vs_reference(gold_ft):
 @pytest.mark.gpu
 def test_gpu_fock_tensor_vs_reference(gold_ft):
     _check_fock_tensor(gold_ft)
+
+
+# ------------------------------------------------------------------------------------------- marginals, tvd bounds
+@pytest.fixture(scope="module")
+def gold_marg():
+    with open(os.path.join(ROOT, "tests", "golden", "reference_marginals.json")) as fh:
+        return json.load(fh)
+
+
+def _check_marginals(gold_marg):
+    for c in gold_marg:
+        mu, cov = np.array(c["mu"]), np.array(c["cov"])
+        assert np.allclose(q.tvd_cutoff_bounds(mu, cov, 5), c["tvd"], rtol=1e-9, atol=1e-12)
+        got = q.n_body_marginals(mu, cov, 3, 2)
+        assert len(got) == 2
+        for g, w in zip(got, c["marginals"]):
+            assert g.shape == np.array(w).shape and np.allclose(g, w, rtol=1e-9, atol=1e-12)
+
+
+def test_marginals_and_tvd_bounds_vs_reference(gold_marg, cpu_kernel):
+    _check_marginals(gold_marg)
+    for c in gold_marg:
+        mu, cov = np.array(c["mu"]), np.array(c["cov"])
+        assert q.find_classical_subsystem(cov) == c["classical"]
+        assert np.allclose(q.real_to_complex_displacements(q.complex_to_real_displacements(mu)), c["r2c"])
+    with pytest.raises(ValueError, match="higher than the number of modes"):
+        q.n_body_marginals(np.zeros(2), np.identity(2), 3, 2)
+    with pytest.raises(ValueError, match="violates the uncertainty relation"):
+        q.tvd_cutoff_bounds(np.zeros(2), 0.1 * np.identity(2), 3)
+
+
+@pytest.mark.gpu
+def test_gpu_marginals_and_tvd_bounds_vs_reference(gold_marg):
+    _check_marginals(gold_marg)

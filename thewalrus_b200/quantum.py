@@ -15,7 +15,8 @@ from . import _engine
 
 __all__ = ["Qmat", "Amat", "Covmat", "Xmat", "sympmat", "complex_to_real_displacements", "density_matrix_element",
            "density_matrix", "pure_state_amplitude", "state_vector", "fock_tensor", "is_pure_cov", "is_symplectic",
-           "loss_mat", "update_probabilities_with_loss", "update_probabilities_with_noise",
+           "loss_mat", "update_probabilities_with_loss", "update_probabilities_with_noise", "tvd_cutoff_bounds",
+           "n_body_marginals", "find_classical_subsystem", "real_to_complex_displacements",
            "probabilities", "probabilities_batch", "lhaf_patterns", "photon_number_mean_vector", "adj_scaling",
            "adj_to_qmat", "gen_Qmat_from_graph", "is_valid_cov", "is_classical_cov", "williamson"]
 
@@ -265,6 +266,73 @@ def fock_tensor(S, alpha, cutoff, choi_r=np.arcsinh(1.0), check_symplectic=True,
     if sf_order:
         return tensor.transpose([ax for i in range(l) for ax in (i, i + l)])
     return tensor
+
+
+def real_to_complex_displacements(beta, hbar=2):
+    """xp means from (alpha, alpha^*), the inverse of complex_to_real_displacements (conversions.py:172-190)."""
+    beta = np.asarray(beta)
+    N = len(beta) // 2
+    alpha = beta[:N]
+    return np.sqrt(2 * hbar) * np.concatenate([alpha.real, alpha.imag])
+
+
+def tvd_cutoff_bounds(mu, cov, cutoff, hbar=2, check_is_valid_cov=True, rtol=1e-05, atol=1e-08, *, device=None):
+    """Upper bounds on the total variation distance between the exact GBS distribution and its truncations at local
+    Fock dimensions 1..cutoff (fock_tensors.py:584-612): sum over modes of the single-mode tail probabilities
+    ``1 - cumsum(p_k)``.  The single-mode distributions come from the batched probability call."""
+    from .moments import reduced_gaussian
+
+    mu, cov = np.asarray(mu), np.asarray(cov)
+    if check_is_valid_cov and not is_valid_cov(cov, hbar=hbar, rtol=rtol, atol=atol):
+        raise ValueError("The input covariance matrix violates the uncertainty relation.")
+    bounds = np.zeros(cutoff)
+    for k in range(len(cov) // 2):
+        mu_k, cov_k = reduced_gaussian(mu, cov, [k])
+        bounds += 1 - np.cumsum(probabilities(mu_k, cov_k, cutoff, hbar=hbar, device=device))
+    return bounds
+
+
+def n_body_marginals(mean, cov, cutoff, n, hbar=2, *, device=None):
+    """Marginal photon-number distributions of all groups of up to ``n`` modes (fock_tensors.py:615-668): a list whose
+    entry ``k - 1`` has shape ``[M] * k + [cutoff] * k``; entry ``[m_1..m_k]`` is the joint distribution of those modes
+    (zero where indices repeat).  Each sorted group of distinct modes is ONE batched probability call on the reduced
+    state; permuted index tuples are filled by transposition."""
+    from .moments import reduced_gaussian
+
+    mean, cov = np.asarray(mean), np.asarray(cov)
+    if (len(mean), len(mean)) != cov.shape:
+        raise ValueError("The covariance matrix and vector of means have incompatible dimensions")
+    if len(mean) % 2 != 0:
+        raise ValueError("The vector of means is not of even dimensions")
+    M = len(mean) // 2
+    if M < n:
+        raise ValueError("The order of the correlations is higher than the number of modes")
+    marginal = [np.zeros([M] * k + [cutoff] * k) for k in range(1, n + 1)]
+    for ind in product(range(M), repeat=n):
+        distinct_sorted = sorted(set(ind))
+        k = len(distinct_sorted)
+        if list(ind) == sorted(ind):
+            sub_mean, sub_cov = reduced_gaussian(mean, cov, distinct_sorted)
+            marginal[k - 1][tuple(distinct_sorted)] = probabilities(sub_mean, sub_cov, cutoff, hbar=hbar, device=device)
+        else:
+            first_seen = list(dict.fromkeys(ind))
+            marginal[k - 1][tuple(first_seen)] = marginal[k - 1][tuple(distinct_sorted)].transpose(np.argsort(first_seen))
+    return marginal
+
+
+def find_classical_subsystem(cov, hbar=2, atol=1e-08):
+    """Largest k such that modes 0..k-1 are in a classical state (fock_tensors.py:541-563)."""
+    from .moments import reduced_gaussian
+
+    cov = np.asarray(cov)
+    N = len(cov) // 2
+    if is_classical_cov(cov, hbar=hbar, atol=atol):
+        return N
+    zero = np.zeros(2 * N)
+    k = 0
+    while k < N and is_classical_cov(reduced_gaussian(zero, cov, list(range(k + 1)))[1], hbar=hbar, atol=atol):
+        k += 1
+    return k
 
 
 def loss_mat(eta, cutoff):
