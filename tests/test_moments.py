@@ -77,7 +77,3 @@ def test_host_only_pieces():
         moments.reduced_gaussian(np.zeros(4), np.identity(4), [5])
     assert abs(moments._coeff_normal_ordered(3, 2) - 3.0) < 1e-12                                  # n^3 = :n: + 3 :n^2: + :n^3:
 
-
-@pytest.mark.gpu
-def test_gpu_moments_vs_reference(gold):
-    _check(gold)

@@ -77,14 +77,6 @@ def test_purity_check():
     assert q.is_pure_cov(np.identity(4)) and not q.is_pure_cov(2 * np.identity(4))
 
 
-@pytest.mark.gpu
-def test_gpu_pure_state_callers_vs_reference(gold):
-    _check_pure(gold)
-
-
-@pytest.mark.gpu
-def test_gpu_density_matrix_vs_reference(gold):
-    _check_mixed(gold)
 
 
 # ------------------------------------------------------------------------------------------- fock_tensor, loss, noise
@@ -122,10 +114,6 @@ def test_loss_and_noise_updates_vs_reference(gold_ft):
         q.update_probabilities_with_loss([0.5], np.ones((2, 2)))
 
 
-@pytest.mark.gpu
-def test_gpu_fock_tensor_vs_reference(gold_ft):
-    _check_fock_tensor(gold_ft)
-
 
 # ------------------------------------------------------------------------------------------- marginals, tvd bounds
 @pytest.fixture(scope="module")
@@ -155,7 +143,3 @@ def test_marginals_and_tvd_bounds_vs_reference(gold_marg, cpu_kernel):
     with pytest.raises(ValueError, match="violates the uncertainty relation"):
         q.tvd_cutoff_bounds(np.zeros(2), 0.1 * np.identity(2), 3)
 
-
-@pytest.mark.gpu
-def test_gpu_marginals_and_tvd_bounds_vs_reference(gold_marg):
-    _check_marginals(gold_marg)
