@@ -6,32 +6,48 @@ One "step" = one complete hafnian of a random 50x50 complex128 symmetric matrix 
 seed 1000*1+50 as in SURVEY.md 8d).  With N GPUs the subset index is sharded in contiguous ranges (strong
 scaling: total work fixed) and the partial sums are combined by one all-reduce inside the timed region.
 
-  python bench.py --gpus N --steps K --warmup W                 # GPU arm (torchrun for N > 1)
-  python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the oracle port on host cores
+  python bench.py --gpus N --steps K --warmup W                   # GPU arm (torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm: the reference's numba path from
+                                                                  # baseline/_ref on the host cores (C port if absent)
 
-Other workloads (the remaining BASELINE configs and the north-star targets):
---workload hafnian24|hafnian56|lhaf50|perm32|perm40|tor48|gbs16
-and the SURVEY 8(f) components: ltor48 (loop torontonian), mtl14 (montrealer, 14 modes), brs12 (Bristolian of a
-12 x 12 block), hsample8 (batched chain-rule photon-number sampler, 8 modes; unit: samples/s).
+The default N = 1 run also measures the other BASELINE configs (hafnian24, perm32, tor48, gbs16) and prints them in a
+"secondary" object of the same JSON line, each with value / e2e / roofline / clocks / cpu_baseline and the error of
+the complete result against the offline golden (tests/golden/reference_fullsize.json).
+
+Other workloads: --workload hafnian24|hafnian56|lhaf50|perm32|perm40|tor48|gbs16 and the SURVEY 8(f) components
+ltor48, mtl14, brs12, hsample8 (batched chain-rule photon-number sampler; unit samples/s).
 """
-import argparse
-import ctypes
-import json
 import os
-import statistics
-import subprocess
 import sys
-import threading
-import time
 
-import numpy as np
+if "reference" in sys.argv:   # the numba reference: one BLAS thread per prange worker (SURVEY 6: 6x cliff otherwise);
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")   # must be set before numpy loads OpenBLAS
+    os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache_wb200")
+
+import argparse  # noqa: E402
+import ctypes  # noqa: E402
+import json  # noqa: E402
+import math  # noqa: E402
+import statistics  # noqa: E402
+import subprocess  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "hafnian n=50 complex128 subsets/s"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel (ncu captures in profiles/)
-MEASURED_TRAFFIC = {"hafnian50": 5864960 + 59578624, "perm32": 79104, "tor48": 79104}
+SECONDARY = ["hafnian24", "perm32", "tor48", "gbs16"]
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the `ncu --set full` captures
+# under profiles/ (file named next to each number)
+MEASURED_TRAFFIC = {
+    "hafnian50": (5864960 + 59578624, "profiles/r01_ncu_traffic_hafnian50.csv"),
+    "perm32": (79104, "profiles/r01_ncu_perm32_v3.txt"),
+    "tor48": (73216, "profiles/r01_ncu_tor48_v3b.txt"),
+}
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_fullsize.json")
 
 
 def make_input(workload):
@@ -171,13 +187,13 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, period_ms=200):
+        self.rows, self.proc, self.index, self.period = [], None, index, int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -200,12 +216,37 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
 
 
+# ---------------------------------------------------------------------------------------------------------------------------------
+# flop models of the batched workloads
+# ---------------------------------------------------------------------------------------------------------------------------------
 def gbs_reference_flops(pats):
     """Reference-algorithm flops for the GBS patterns workload: a pattern with N_p photons is a loop hafnian of
     the reduction-expanded 2N_p x 2N_p matrix: 2^(N_p-1) Glynn subsets x 8 (2N_p)^3 (N_p - 1)."""
     Np = pats.sum(axis=1).astype(np.float64)
     Np = Np[Np >= 2]
     return float(np.sum(2.0 ** (Np - 1) * 8.0 * (2 * Np) ** 3 * (Np - 1)))
+
+
+def gbs_executed_flops(rpt):
+    """Flops the batched kernels EXECUTE for the repetition patterns ``rpt[B, nv]`` (even totals, loops): per pattern
+    `steps` mixed-radix subsets of the UN-expanded pairing (matched_reps), each a pairing power-trace chain on the
+    s = 2E matrix: floor((T-1)/2) products (8 s^3 each) for the traces up to T = N/2, plus the loop row's floor(T/2)
+    row-times-matrix products (8 s^2) and the trace / pairing inner products (8 s^2 per needed trace).  Padding of the
+    DMMA tiles is NOT counted (useful flops only)."""
+    from thewalrus_b200._prep import glynn_steps, matched_reps
+
+    uniq, counts = np.unique(np.asarray(rpt), axis=0, return_counts=True)
+    total = 0.0
+    for row, cnt in zip(uniq, counts):
+        N = int(row.sum())
+        if N < 2:
+            continue
+        _, er, odd = matched_reps([int(x) for x in row])
+        s, T = 2 * len(er), N // 2
+        steps = glynn_steps(er, True, odd is not None)
+        nprod = (T - 1) // 2 if odd is None else max(T - 1, 0)
+        total += cnt * steps * (8.0 * s**3 * nprod + 8.0 * s * s * (T // 2) + 8.0 * s * s * T)
+    return total
 
 
 def sampler_reference_flops(det, cutoff):
@@ -234,12 +275,202 @@ def sampler_reference_flops(det, cutoff):
     return total
 
 
-def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
+# ---------------------------------------------------------------------------------------------------------------------------------
+# what both arms agree on: metric, units, config
+# ---------------------------------------------------------------------------------------------------------------------------------
+def metric_name(workload):
+    if workload == "hafnian50":
+        return METRIC
+    if workload.startswith("gbs"):
+        return f"{workload} GBS pattern probabilities/s"
+    if workload.startswith("hsample"):
+        return f"{workload} GBS photon-number samples/s"
+    return f"{workload} subsets/s"
+
+
+def gbs_inputs(workload, batch):
+    import thewalrus_b200 as wb
+
+    M = int(workload[3:])
+    mu, cov, pats = make_gbs_state(M, batch, seed=1000 * 3 + M)
+    A, gamma = wb.quantum._state(mu, cov, 2, 1e-10)
+    rpt = np.ascontiguousarray(np.concatenate([pats, pats], axis=1))
+    return M, mu, cov, pats, A, gamma, rpt
+
+
+INPUT_TEXT = {
+    "hafnian": "random complex symmetric G+G^T, seed 1000*config+n", "lhaf": "random complex symmetric G+G^T, loops = diagonal",
+    "perm": "n x n block of a 2n Haar unitary",
+    "tor": "O = I - Q^-1 of an N-mode GBS state (Haar interferometer, r=1.5, eta=0.8), all detectors click",
+    "ltor": "O = I - sigma^-1, gamma = (sigma^-1 alpha)^* of the displaced N-mode GBS state, all detectors click",
+    "mtl": "random complex symmetric 2n x 2n matrix / sqrt(8n)", "brs": "n x n block A of a 2n-mode Haar unitary, E = I - A^H A"}
+
+
+def describe(workload, args):
+    """(kind, n, units per step, unit, config dict) — identical for the GPU arm and the reference arm."""
+    kind = workload.rstrip("0123456789")
+    n = int(workload[len(kind):])
+    world = max(1, args.gpus)
+    if kind == "gbs":
+        units, unit, what = args.batch, "patterns/s", "photon-number patterns"
+        inp = (f"{n}-mode Gaussian state (Haar interferometer, r=0.5, eta=0.8, displaced), {units} Poisson(0.45) "
+               "patterns with <= 10 photons")
+        par = f"pattern shards x{world}, one all-gather"
+        n = 2 * n
+    elif kind == "hsample":
+        units, unit, what = min(args.batch, 2048), "samples/s", "photon-number samples (accepted or not)"
+        inp = (f"{n}-mode Gaussian state (Haar interferometer, r=0.4, eta=0.8, displaced), {units} chains per step "
+               f"advanced together, cutoff {args.cutoff}")
+        par = f"independent chains x{world} (replicas only, no collective)"
+    else:
+        units, unit, what = units_and_flops(kind, n)[0], "subsets/s", "subsets (reference `steps`)"
+        inp = INPUT_TEXT[kind]
+        par = f"subset-index shards x{world}, one all-reduce"
+    cfg = {"workload": workload, "n": n, "units_per_step": units, "units": what, "input": inp, "parallelism": par,
+           "l2_flush": True,
+           "l2_note": "256 MiB fill between timed iterations; inputs are KB-sized, the path is FP64-pipe bound"}
+    return kind, n, units, unit, cfg
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# CPU arms: the reference itself (numba, baseline/_ref) and the C port (oracle/)
+# ---------------------------------------------------------------------------------------------------------------------------------
+def host_threads():
+    # all host cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+_REF = {}
+
+
+def load_reference():
+    """Import the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build()) with the dask stand-in.
+    Returns (module, None) or (None, reason)."""
+    if "mod" in _REF:
+        return _REF["mod"], _REF.get("why")
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    why = None
+    mod = None
+    if not os.path.isdir(os.path.join(ref_dir, "thewalrus")):
+        why = "baseline/_ref/thewalrus missing (run __graft_entry__.build() where /root/reference exists)"
+    else:
+        try:
+            import numba  # noqa: F401
+
+            for p in (os.path.join(ROOT, "baseline", "dask_shim"), ref_dir):
+                if p not in sys.path:
+                    sys.path.insert(0, p)
+            import thewalrus as mod
+        except Exception as exc:  # numba / llvmlite missing on the box, or the import fails
+            mod, why = None, f"reference import failed: {type(exc).__name__}: {exc}"
+    _REF["mod"], _REF["why"] = mod, why
+    return mod, why
+
+
+def _reference_range_harness():
+    """the reference's own per-subset functions (find_kept_edges -> get_AX_S -> f, and the loop variants)
+    in a numba prange with the scalar `H +=` reduction of _calc_hafnian (_hafnian.py:443-462), over a RANGE of subset
+    indices so that n = 50 / 56 can be sampled; all reps 1, Glynn."""
+    if "harness" in _REF:
+        return _REF["harness"]
+    import numba
+    from thewalrus._hafnian import f, f_loop, find_kept_edges, get_AX_S, get_submatrices
+
+    @numba.jit(nopython=True, parallel=True)
+    def haf_range(A, edge_reps, j0, j1):
+        N = 2 * edge_reps.sum()
+        H = np.complex128(0)
+        for j in numba.prange(j0, j1):
+            kept = find_kept_edges(j, edge_reps)
+            edge_sum = kept.sum()
+            kept = 2 * kept - edge_reps
+            AX_S = get_AX_S(kept, A)
+            H += (-1.0) ** (N // 2 - edge_sum) * f(AX_S, N)[N // 2]
+        return H
+
+    @numba.jit(nopython=True, parallel=True)
+    def lhaf_range(A, D, edge_reps, j0, j1):
+        N = 2 * edge_reps.sum()
+        H = np.complex128(0)
+        for j in numba.prange(j0, j1):
+            kept = find_kept_edges(j, edge_reps)
+            edge_sum = kept.sum()
+            kept = 2 * kept - edge_reps
+            AX_S, XD_S, D_S, _ = get_submatrices(kept, A, D, np.zeros(len(D), dtype=np.complex128))
+            H += (-1.0) ** (N // 2 - edge_sum) * f_loop(AX_S, XD_S, D_S, N)[N // 2]
+        return H
+
+    _REF["harness"] = (haf_range, lhaf_range)
+    return _REF["harness"]
+
+
+def cpu_reference(kind, n, X, seconds):
+    """Time the reference's numba path on the host cores (bounded sample).  None if it does not apply / import."""
+    tw, why = load_reference()
+    if tw is None:
+        return None, why
+    import numba
+
+    threads = numba.get_num_threads()
+    if kind in ("hafnian", "lhaf"):
+        loop = kind == "lhaf"
+        total = 1 << (n // 2 - 1)
+        if n <= 30:   # the whole call fits: thewalrus.hafnian itself
+            tw.hafnian(X, loop=loop)                       # JIT / cache warm-up
+            reps, t0 = 0, time.perf_counter()
+            while True:
+                tw.hafnian(X, loop=loop)
+                reps += 1
+                dt = time.perf_counter() - t0
+                if dt >= seconds or reps >= 200:
+                    break
+            return {"value": reps * total / dt, "unit": "subsets/s", "cores": threads, "kind": "reference", "seconds": dt,
+                    "sample": f"{reps} complete calls of the reference's thewalrus.hafnian(A{', loop=True' if loop else ''}) "
+                              f"(numba prange over {threads} threads, OPENBLAS_NUM_THREADS=1)"}, None
+        haf_range, lhaf_range = _reference_range_harness()
+        from thewalrus._hafnian import matched_reps
+
+        x, er, _ = matched_reps(np.ones(n, dtype=np.int64))
+        Ax = np.ascontiguousarray(X[np.ix_(x, x)].astype(np.complex128))
+        Dx = np.ascontiguousarray(np.diag(X)[x].astype(np.complex128))
+        er = np.asarray(er, dtype=np.int64)
+        run = (lambda a, b: lhaf_range(Ax, Dx, er, a, b)) if loop else (lambda a, b: haf_range(Ax, er, a, b))
+        run(0, 4 * threads)                                 # JIT compile + thread pool
+        t0 = time.perf_counter()
+        run(0, 64 * threads)
+        rate = 64 * threads / (time.perf_counter() - t0)
+        sample = int(min(total, max(64 * threads, rate * seconds)))
+        j0 = (total - sample) // 2                           # a window in the middle of the index space
+        t0 = time.perf_counter()
+        run(j0, j0 + sample)
+        dt = time.perf_counter() - t0
+        return {"value": sample / dt, "unit": "subsets/s", "cores": threads, "kind": "reference", "seconds": dt,
+                "sample": f"{sample} of {total} subset indices from {j0} through the reference's own find_kept_edges -> "
+                          f"get_AX_S -> f{'_loop' if loop else ''} (thewalrus/_hafnian.py) in a numba prange with its scalar H += "
+                          f"reduction, {threads} threads, OPENBLAS_NUM_THREADS=1; extrapolated to the full sum"}, None
+    if kind == "gbs":
+        from thewalrus.quantum import density_matrix_element
+
+        mu, cov, pats = X[3], X[4], X[5]
+        density_matrix_element(mu, cov, list(pats[0]), list(pats[0]))    # JIT / cache warm-up
+        order = np.random.default_rng(0).permutation(len(pats))          # a random sample of the batch: typical photon numbers
+        done, t0 = 0, time.perf_counter()
+        while done < len(order) and time.perf_counter() - t0 < seconds:
+            p = [int(v) for v in pats[order[done]]]
+            density_matrix_element(mu, cov, p, p)
+            done += 1
+        dt = time.perf_counter() - t0
+        return {"value": done / dt, "unit": "patterns/s", "cores": threads, "kind": "reference", "seconds": dt,
+                "sample": f"{done} randomly chosen patterns of the {len(pats)}, one reference density_matrix_element call each "
+                          f"(quantum/fock_tensors.py:191-232; numba prange inside, {threads} threads)"}, None
+    return None, f"no bounded-sample harness of the reference for '{kind}' (its loop has no range argument and the full call takes minutes); C port used"
+
+
+def cpu_port(kind, n, X, seconds=15.0, cutoff=6):
     """Time the oracle's C port (reference algorithm) on the host cores over a bounded sample."""
     from oracle import c_oracle as co
 
-    # all host cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
-    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or co.max_threads())
+    threads = host_threads()
     if kind in ("hafnian", "lhaf"):
         x = co.matched_order(X)
         Ax = np.ascontiguousarray(X[np.ix_(x, x)])
@@ -260,7 +491,7 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
         co.perm_range(X, 0, 0, sample, threads)
         dt = time.perf_counter() - t0
         what = f"first {sample} of {1 << (n - 1)} Gray-code steps (the reference itself is single-threaded; the port splits the range over threads)"
-    elif kind == "tor" and n <= 48:
+    elif kind == "tor" and n <= 48 and seconds >= 14.0:
         N = n // 2
         sample = 1 << N
         t0 = time.perf_counter()
@@ -268,7 +499,7 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
         dt = time.perf_counter() - t0
         threads = 1
         what = "full recursive torontonian (single thread, as the reference)"
-    elif kind in ("tor", "ltor", "mtl", "brs"):   # tor: only beyond 24 modes, where the full recursion takes > 10 min
+    elif kind in ("tor", "ltor", "mtl", "brs"):   # tor: beyond 24 modes (full recursion > 10 min) or a short budget
         from oracle import walrus_oracle as wo
 
         total = 1 << (n // 2 if kind in ("tor", "ltor") else n)
@@ -322,8 +553,8 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
         return {"value": sample / dt, "unit": "samples/s", "cores": threads, "kind": "port", "seconds": dt,
                 "sample": f"{sample} chains, one at a time as the reference walks them, the cutoff + 1 loop hafnians of a "
                           "mode step through the C port (OpenMP over the outcomes)"}
-    else:  # gbs: X = (A, gamma, rpt); the C port of the reference's per-pattern loop hafnian, patterns over all cores
-        A, gamma, rpt = X
+    else:  # gbs: X = (A, gamma, rpt, ...); the C port of the reference's per-pattern loop hafnian, patterns over all cores
+        A, gamma, rpt = X[0], X[1], X[2]
         block, sample = 256 * threads, 0
         co.lhaf_patterns(A, gamma, rpt[:threads], True, threads)       # warm-up (thread pool)
         t0 = time.perf_counter()
@@ -333,115 +564,144 @@ def cpu_baseline(kind, n, X, seconds=15.0, cutoff=6):
         dt = time.perf_counter() - t0
         what = (f"first {sample} of {len(rpt)} patterns, one loop hafnian per pattern through the C port of the reference "
                 "algorithm, patterns spread over all host cores (the reference makes one Python call per pattern, numba "
-                "prange inside; it measured 177 patterns/s on 8 cores)")
+                "prange inside)")
         return {"value": sample / dt, "unit": "patterns/s", "cores": threads, "kind": "port", "sample": what, "seconds": dt}
     return {"value": sample / dt, "unit": "subsets/s", "cores": threads, "kind": "port", "sample": what,
             "seconds": dt}
 
 
-def metric_name(workload):
-    if workload == "hafnian50":
-        return METRIC
-    if workload.startswith("gbs"):
-        return f"{workload} GBS pattern probabilities/s"
-    if workload.startswith("hsample"):
-        return f"{workload} GBS photon-number samples/s"
-    return f"{workload} subsets/s"
-
-
-def gbs_inputs(workload, batch):
-    import thewalrus_b200 as wb
-
-    M = int(workload[3:])
-    mu, cov, pats = make_gbs_state(M, batch, seed=1000 * 3 + M)
-    A, gamma = wb.quantum._state(mu, cov, 2, 1e-10)
-    rpt = np.ascontiguousarray(np.concatenate([pats, pats], axis=1))
-    return M, mu, cov, pats, A, gamma, rpt
+def workload_inputs(workload, args):
+    kind = workload.rstrip("0123456789")
+    if kind == "gbs":
+        M, mu, cov, pats, A, gamma, rpt = gbs_inputs(workload, args.batch)
+        return "gbs", 2 * M, (A, gamma, rpt, mu, cov, pats)
+    return make_input(workload)
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import __graft_entry__ as ge  # noqa: F401  (builds the oracle if needed; CPU only)
-
     from oracle import build as obuild
 
     obuild.ensure()
-    per = max(2.0, 60.0 / max(1, args.warmup + args.steps))
-    if args.workload.startswith("gbs"):
-        M, mu, cov, pats, A, gamma, rpt = gbs_inputs(args.workload, args.batch)
-        kind, n, X, units, ref_flops, unit = "gbs", 2 * M, (A, gamma, rpt), len(rpt), gbs_reference_flops(pats) / len(rpt), "patterns/s"
-    elif args.workload.startswith("hsample"):
-        kind, n, X = make_input(args.workload)
-        units, ref_flops, unit = min(args.batch, 2048), 0.0, "samples/s"
-    else:
-        kind, n, X = make_input(args.workload)
-        units, _, ref_flops, _, _ = units_and_flops(kind, n)
-        unit = "subsets/s"
-    vals = []
+    kind, n, units, unit, cfg = describe(args.workload, args)
+    _, _, X = workload_inputs(args.workload, args)
+    per = args.seconds if args.seconds > 0 else max(2.0, 60.0 / max(1, args.warmup + args.steps))
+    vals, ports = [], []
+    why = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(kind, n, X, seconds=per, cutoff=args.cutoff)
+        cb, why = (None, "forced: --cpu-kind port") if args.cpu_kind == "port" else cpu_reference(kind, n, X, per)
+        if cb is None:
+            cb = cpu_port(kind, n, X, seconds=per, cutoff=args.cutoff)
         if i >= args.warmup:
             vals.append(cb)
+    if args.cpu_kind == "both" and vals[-1]["kind"] == "reference":
+        ports.append(cpu_port(kind, n, X, seconds=per, cutoff=args.cutoff))
     v = statistics.mean(c["value"] for c in vals)
+    cfg = dict(cfg)
+    cfg["note"] = "reference arm: each step is a bounded sample of the workload; ms_per_step is extrapolated to the full step"
+    cbase = {"value": v, "unit": unit, "cores": vals[-1]["cores"], "kind": vals[-1]["kind"], "sample": vals[-1]["sample"],
+             "host_cpus": host_threads()}
+    if why:
+        cbase["reference_unavailable"] = why
+    if ports:
+        cbase["port"] = ports[-1]
     line = {"impl": "reference", "metric": metric_name(args.workload),
             "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": units / v * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "n": n, "units_per_step": units,
-                       "note": "each step is a bounded sample of the workload; ms_per_step is extrapolated to the full step"},
-            "cpu_baseline": {"value": v, "unit": unit, "cores": vals[-1]["cores"], "kind": "port",
-                             "sample": vals[-1]["sample"], "gflops_reference_algorithm": v * ref_flops * 1e-9},
+            "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": cbase,
             "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="hafnian50")
-    ap.add_argument("--batch", type=int, default=100000, help="patterns per step of the gbs workload")
-    ap.add_argument("--cutoff", type=int, default=6, help="per-mode photon cutoff of the hsample workload")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
+def cpu_baseline_subprocess(workload, args, seconds):
+    """Run the reference arm of this file in a fresh process (numba threading and OPENBLAS_NUM_THREADS=1 must be set
+    before numpy loads; torchrun's OMP_NUM_THREADS=1 must not leak into the OpenMP port) and return its cpu_baseline."""
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "1",
+           "--warmup", "0", "--seconds", str(seconds), "--batch", str(args.batch), "--cutoff", str(args.cutoff),
+           "--cpu-kind", "both"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (out.stderr or out.stdout)[-400:]}
+    except Exception as exc:  # noqa: BLE001
+        return {"error": f"{type(exc).__name__}: {exc}"}
 
-    import torch
-    import torch.distributed as dist
 
+# ---------------------------------------------------------------------------------------------------------------------------------
+# goldens: the error of the complete result, printed in the line
+# ---------------------------------------------------------------------------------------------------------------------------------
+def golden_error(workload, res, extra=None):
+    """Relative error of the full result of this run against tests/golden/reference_fullsize.json (None if the golden
+    has no entry for the workload)."""
+    try:
+        with open(GOLDEN) as fh:
+            g = json.load(fh)
+    except OSError:
+        return None
+
+    def cz(d):
+        return complex(d["re"], d["im"]) if isinstance(d, dict) else complex(d)
+
+    def rel(a, b):
+        return abs(a - b) / max(abs(b), 1e-300)
+
+    out = {}
+    if workload in ("hafnian50", "hafnian24") and workload in g:
+        e = g[workload]
+        for key, name in (("oracle_ld", "long-double C oracle"), ("oracle_double", "double C oracle (full product chain, Kahan)"),
+                          ("reference", "reference numba thewalrus.hafnian")):
+            if key in e:
+                out[name] = rel(res, cz(e[key]))
+    elif workload == "perm32" and "perm32" in g:
+        e = g["perm32"]
+        out["long-double C oracle (2^31 steps)"] = rel(res, cz(e["oracle_ld"]))
+        if "reference_bbfg" in e:
+            out["reference perm(bbfg)"] = rel(res, cz(e["reference_bbfg"]))
+    elif workload == "tor48" and "tor48" in g:
+        e = g["tor48"]
+        out["long-double C oracle"] = rel(res.real, e["oracle_ld"])
+        out["reference rec_torontonian"] = rel(res.real, cz(e["reference_rec"]).real)
+    elif workload == "gbs16" and "gbs16" in g and extra is not None and len(extra) == g["gbs16"]["B"]:
+        npy = os.path.join(os.path.dirname(GOLDEN), "gbs16_probabilities_ld.npy")
+        if os.path.exists(npy):
+            want = np.maximum(np.load(npy), 0.0)       # probabilities() clips at 0 (fock_tensors.py:424-428)
+            out["sum of all probabilities vs long-double C oracle"] = rel(float(np.sum(np.sort(extra))), float(np.sum(np.sort(want))))
+            out["worst single probability (scaled by max(p, 1e-3 max p)) vs long-double C oracle"] = float(
+                np.max(np.abs(extra - want) / np.maximum(want, 1e-3 * want.max())))
+    return out or None
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------------------
+def gpu_arm(workload, args, env, steps, warmup, min_seconds=0.0):
+    """Measure one workload on the GPU(s).  ``min_seconds``: repeat steps until the timed region has run at least this
+    long (short workloads: the nvidia-smi sampler needs time to see the clocks)."""
+    torch, dist, lib, dev = env["torch"], env["dist"], env["lib"], env["dev"]
+    world, rank, local = env["world"], env["rank"], env["local"]
     import thewalrus_b200 as wb
     from thewalrus_b200 import _engine, _lib
     from thewalrus_b200._prep import shard_range
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-    is_gbs = args.workload.startswith("gbs")
+    kind, n, units, unit, cfg = describe(workload, args)
+    is_gbs = kind == "gbs"
     if is_gbs:
-        M, mu, cov, pats, A, gamma, rpt = gbs_inputs(args.workload, args.batch)
-        kind, n, X = "gbs", 2 * M, (A, gamma, rpt)
-        units = len(rpt)
+        _, _, X = workload_inputs(workload, args)
+        A, gamma, rpt, mu, cov, pats = X
         ref_flops = gbs_reference_flops(pats) / units
-        my_flops = ref_flops
-        model = ("reference-algorithm flops of the reduction-expanded Glynn loop hafnians, sum_p 2^(N_p-1) 8 (2N_p)^3 (N_p-1); "
-                 "the kernel works on the un-expanded matrices with mixed-radix subsets, so this is an equivalent, not an executed count")
-        pipe = "FP64 DFMA (vector pipe), warp per subset, operands in shared memory"
-        unit = "patterns/s"
+        my_flops = gbs_executed_flops(rpt) / units
+        model = ("EXECUTED useful flops of the batched kernels (bench.gbs_executed_flops): per pattern prod(edge_reps+1) "
+                 "mixed-radix subsets of the un-expanded pairing, each floor((T-1)/2) products 8 s^3 + loop row + pairing "
+                 "inner products on the s = 2E matrix; DMMA tile padding not counted")
+        pipe = "FP64 DMMA.8x8x4 (tensor pipe) for even patterns; FP64 DFMA warp-per-subset kernel for odd ones"
         lo, hi = shard_range(units, rank, world)
-    elif args.workload.startswith("hsample"):
-        kind, n, X = make_input(args.workload)
-        units = min(args.batch, 2048)          # chains per step, split over the ranks
-        unit = "samples/s"
+    elif kind == "hsample":
+        _, _, X = make_input(workload)
         lo, hi = shard_range(units, rank, world)
         from thewalrus_b200 import samples as wsamples
 
@@ -452,9 +712,8 @@ def main():
                  "s = 2 #edges reduced matrix; these are small problems, the step is launch/latency bound")
         pipe = "FP64 DFMA (vector pipe), warp per subset, operands in shared memory"
     else:
-        kind, n, X = make_input(args.workload)
-        units, my_flops, ref_flops, model, pipe = units_and_flops(kind, n)
-        unit = "subsets/s"
+        _, _, X = make_input(workload)
+        _, my_flops, ref_flops, model, pipe = units_and_flops(kind, n)
         lo, hi = shard_range(units if kind not in ("tor", "ltor") else _engine.tor_num_prefixes(n // 2), rank, world)
 
     # ---- device-resident inputs for the kernel-only number
@@ -487,15 +746,16 @@ def main():
     elif kind == "hsample":
         launches_per_step = 4 * n  # one patterns call (prep, scan, main, final) per mode
     else:
-        launches_per_step = 4      # pat_prep, scan, pat_main, pat_final
+        launches_per_step = 4      # pat_prep, scan, pat_main (one per size class), pat_final
     host_entry = kind in ("gbs", "mtl", "brs", "hsample")   # *_host entry points: they time their own launches
     drawn = []
     ws = torch.empty((wsb + 7) // 8, dtype=torch.float64, device=dev)
     out = torch.zeros(4, dtype=torch.float64, device=dev)
     table = torch.zeros((world, 4), dtype=torch.float64, device=dev)
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    flush = env["flush"]
     stream = torch.cuda.current_stream(dev)
     inner_ms = []   # kernel time reported by the *_host entry points (CUDA events around the launches only)
+    gbs_out = [None]
 
     def kernel_step():
         if kind in ("hafnian", "lhaf"):
@@ -522,7 +782,7 @@ def main():
             _engine.kernel_ms_log = None
             rc = 0
         else:
-            _, ms = _engine.lhaf_patterns_local(A, gamma, rpt[lo:hi], True, dev, want_ms=True)
+            gbs_out[0], ms = _engine.lhaf_patterns_local(A, gamma, rpt[lo:hi], True, dev, want_ms=True)
             inner_ms.append(ms)
             rc = 0
         _lib.check(rc, "kernel step")
@@ -536,15 +796,23 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         kernel_step()
     sync_all()
-    sampler = ClockSampler(local)
+    if min_seconds > 0:       # size the timed region from one timed warm step
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        kernel_step()
+        e1.record(stream)
+        sync_all()
+        one = max(inner_ms[-1] if inner_ms else e0.elapsed_time(e1), 0.02) * 1e-3
+        steps = int(min(4000, max(steps, math.ceil(min_seconds / one))))
+    sampler = ClockSampler(local, period_ms=50 if min_seconds > 0 else 200)
     if rank == 0:
         sampler.start()
     total_ms = 0.0
     kern_ms = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         flush.fill_(1.0)  # L2 flush between timed iterations (inputs are KB-sized, far below L2)
         sync_all()
         inner_ms.clear()
@@ -560,13 +828,19 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
-    value = units * args.steps / (total_ms * 1e-3)
+    value = units * steps / (total_ms * 1e-3)
     if host_entry:
         res = 0j
     elif world > 1:
         res = _engine.combine4(table.cpu().numpy())
     else:
         res = _engine.combine4([out.cpu().numpy()])
+    if kind in ("hafnian", "lhaf"):
+        res_scaled = res * 0.5 ** (n // 2 - 1)
+    elif kind == "perm":
+        res_scaled = res / float(1 << (n - 1))
+    else:
+        res_scaled = res
 
     # ---- end to end through the public API with host buffers
     grp = True if world > 1 else None
@@ -589,12 +863,13 @@ def main():
         if kind == "hsample":   # every rank draws its share of the samples (independent chains, no collective)
             got = wsamples.hafnian_sample_state(X[1], hi - lo, mean=X[0], cutoff=args.cutoff, max_photons=10 ** 6)
             return float(got.sum())
-        return float(np.sum(wb.probabilities_batch(mu, cov, pats, group=grp)))
+        return wb.probabilities_batch(mu, cov, pats, group=grp)
 
-    e2e_step()
+    r_e2e = e2e_step()
     sync_all()
+    e2e_steps = steps if min_seconds <= 0 else int(min(4000, max(3, math.ceil(0.5 * min_seconds / max(1e-5, total_ms * 1e-3 / steps)))))
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         r_e2e = e2e_step()
     sync_all()
     e2e_s = time.perf_counter() - t0
@@ -603,72 +878,119 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        return None
 
+    peak = ctypes.c_double(0)
+    dmma = kind in ("hafnian", "lhaf", "gbs")
+    lib.wb200_fp64_peak(local, 1 if dmma else 0, ctypes.byref(peak))
+    per_gpu_units = (hi - lo) if kind not in ("tor", "ltor") else units / world
+    if kind == "hsample":
+        my_flops = ref_flops = sampler_reference_flops(np.concatenate(drawn), args.cutoff) / max(1, len(drawn) * (hi - lo))
+    kms = statistics.mean(kern_ms)
+    achieved = per_gpu_units * my_flops / (kms * 1e-3) * 1e-12
+    if is_gbs:
+        h2d, d2h = int(mu.nbytes + cov.nbytes + pats.nbytes), int(8 * len(pats))
+        api = "thewalrus_b200.probabilities_batch(mu, cov, patterns) with host NumPy arrays"
+    elif kind == "hsample":
+        K = args.cutoff + 1  # per mode step: B block + one gamma row per chain + patterns in, lhafs out
+        h2d = int(sum(16 * m * m + (hi - lo) * (16 * m + 4 * m * K + 4 * K) for m in range(1, n + 1)))
+        d2h = int(n * (hi - lo) * K * 16)
+        api = "thewalrus_b200.samples.hafnian_sample_state(cov, S, mean=mu, cutoff) with host NumPy arrays"
+    else:
+        Xs = X if isinstance(X, tuple) else (X,)
+        h2d, d2h = int(sum(np.asarray(x).nbytes for x in Xs)), 32
+        api = {"hafnian": "thewalrus_b200.hafnian(A)", "lhaf": "thewalrus_b200.hafnian(A, loop=True)",
+               "perm": "thewalrus_b200.perm(A, method='glynn')", "tor": "thewalrus_b200.tor(O)",
+               "ltor": "thewalrus_b200.ltor(O, gamma)", "mtl": "thewalrus_b200.mtl(A)",
+               "brs": "thewalrus_b200.brs(A, E)"}[kind] + " with a host NumPy array"
+    traffic = MEASURED_TRAFFIC.get(workload)
+    if is_gbs:
+        full_res, extra = None, np.asarray(r_e2e)
+        r_e2e_val = float(np.sum(extra))
+    else:
+        full_res, extra, r_e2e_val = res_scaled, None, complex(r_e2e)
+    line = {
+        "metric": metric_name(workload),
+        "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "e2e": {"value": units * e2e_steps / e2e_s, "unit": unit, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps, "api": api},
+        "gpu_launches": launches_per_step * steps * world,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor" if dmma else "fp64", "pipe": pipe,
+                     "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
+                     "peak_source": "measured live by wb200_fp64_peak (dependent-chain micro-benchmark on the same pipe: "
+                                    "DMMA for the hafnian kernels, DFMA otherwise); MEASURED_PEAKS.json has no FP64 entry; "
+                                    "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
+                     "flops_per_unit": my_flops, "flops_model": model,
+                     "reference_algorithm_equivalent_tflops": per_gpu_units * ref_flops / (kms * 1e-3) * 1e-12,
+                     "kernel_ms": kms, "traffic": traffic[0] if traffic else None,
+                     "traffic_source": traffic[1] if traffic else None,
+                     "traffic_note": "bytes per launch of the dominant kernel, dram__bytes_read.sum + dram__bytes_write.sum from "
+                                     "the named ncu capture; the algorithmic traffic is KB (matrix in, 4 doubles per CTA out) — these "
+                                     "paths are FP64-pipe bound"},
+        "result": ({"sum_of_probabilities": r_e2e_val} if is_gbs else
+                   {"re": complex(full_res).real, "im": complex(full_res).imag, "e2e_re": r_e2e_val.real, "e2e_im": r_e2e_val.imag}),
+    }
+    if not host_entry or is_gbs:
+        err = golden_error(workload, full_res, extra)
+        if err is not None:
+            line["result_rel_err"] = max(err.values()) if is_gbs else min(err.values())
+            line["result_rel_err_vs"] = err
+            line["result_golden"] = "tests/golden/reference_fullsize.json (tests/golden/make_golden_fullsize.py)"
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="hafnian50")
+    ap.add_argument("--batch", type=int, default=100000, help="patterns per step of the gbs workload")
+    ap.add_argument("--cutoff", type=int, default=6, help="per-mode photon cutoff of the hsample workload")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the other BASELINE configs in the default run")
+    ap.add_argument("--seconds", type=float, default=0.0, help="reference arm: CPU seconds per step (default 60 / steps)")
+    ap.add_argument("--cpu-kind", default="auto", choices=["auto", "port", "both"],
+                    help="reference arm: numba reference when available (auto), the C port, or both")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from thewalrus_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    env = {"torch": torch, "dist": dist, "lib": _lib.load(), "dev": dev, "world": world, "rank": rank, "local": local,
+           "flush": torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)}  # > 126 MB L2
+    args.gpus = world
+    line = gpu_arm(args.workload, args, env, args.steps, args.warmup)
     if rank == 0:
-        peak = ctypes.c_double(0)
-        lib.wb200_fp64_peak(local, 1 if kind in ("hafnian", "lhaf") else 0, ctypes.byref(peak))
-        per_gpu_units = (hi - lo) if kind not in ("tor", "ltor") else units / world
-        if kind == "hsample":
-            my_flops = ref_flops = sampler_reference_flops(np.concatenate(drawn), args.cutoff) / max(1, len(drawn) * (hi - lo))
-        kms = statistics.mean(kern_ms)
-        achieved = per_gpu_units * my_flops / (kms * 1e-3) * 1e-12
-        if is_gbs:
-            h2d, d2h = int(mu.nbytes + cov.nbytes + pats.nbytes), int(8 * len(pats))
-            cfg_in = (f"{M}-mode Gaussian state (Haar interferometer, r=0.5, eta=0.8, displaced), {units} Poisson(0.45) "
-                      "patterns with <= 10 photons")
-            api = "thewalrus_b200.probabilities_batch(mu, cov, patterns) with host NumPy arrays"
-        elif kind == "hsample":
-            # per mode step: B block + one gamma row per chain + patterns in, lhafs out
-            K = args.cutoff + 1
-            h2d = int(sum(16 * m * m + (hi - lo) * (16 * m + 4 * m * K + 4 * K) for m in range(1, n + 1)))
-            d2h = int(n * (hi - lo) * K * 16)
-            cfg_in = (f"{n}-mode Gaussian state (Haar interferometer, r=0.4, eta=0.8, displaced), {units} chains per step "
-                      f"advanced together, cutoff {args.cutoff}")
-            api = "thewalrus_b200.samples.hafnian_sample_state(cov, S, mean=mu, cutoff) with host NumPy arrays"
-        else:
-            Xs = X if isinstance(X, tuple) else (X,)
-            h2d, d2h = int(sum(np.asarray(x).nbytes for x in Xs)), 32
-            cfg_in = {"hafnian": "random complex symmetric G+G^T, seed 1000*config+n", "lhaf": "random complex symmetric G+G^T, loops = diagonal",
-                      "perm": "n x n block of a 2n Haar unitary", "tor": "O = I - Q^-1 of an N-mode GBS state (Haar interferometer, r=1.5, eta=0.8), all detectors click",
-                      "ltor": "O = I - sigma^-1, gamma = (sigma^-1 alpha)^* of the displaced N-mode GBS state, all detectors click",
-                      "mtl": "random complex symmetric 2n x 2n matrix / sqrt(8n)",
-                      "brs": "n x n block A of a 2n-mode Haar unitary, E = I - A^H A"}[kind]
-            api = {"hafnian": "thewalrus_b200.hafnian(A)", "lhaf": "thewalrus_b200.hafnian(A, loop=True)",
-                   "perm": "thewalrus_b200.perm(A, method='glynn')", "tor": "thewalrus_b200.tor(O)",
-                   "ltor": "thewalrus_b200.ltor(O, gamma)", "mtl": "thewalrus_b200.mtl(A)",
-                   "brs": "thewalrus_b200.brs(A, E)"}[kind] + " with a host NumPy array"
-        line = {
-            "metric": metric_name(args.workload),
-            "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "n": n, "units_per_step": units,
-                       "units": ("photon-number patterns" if is_gbs else "photon-number samples (accepted or not)"
-                                 if kind == "hsample" else "subsets (reference `steps`)"),
-                       "input": cfg_in,
-                       "parallelism": (f"pattern shards x{world}, one all-gather" if is_gbs else f"subset-index shards x{world}, one all-reduce"),
-                       "l2_flush": True,
-                       "l2_note": "256 MiB fill between timed iterations; inputs are KB-sized, the path is FP64-pipe bound"},
-            "e2e": {"value": units * args.steps / e2e_s, "unit": unit, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3, "api": api},
-            "gpu_launches": launches_per_step * args.steps * world,
-            "clocks": clocks,
-            "roofline": {"bound": "tensor", "pipe": pipe,
-                         "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-                         "peak_source": "measured live by wb200_fp64_peak (dependent-chain micro-benchmark on the same pipe: "
-                                        "DMMA for the hafnian kernels, DFMA otherwise); MEASURED_PEAKS.json has no FP64 entry; "
-                                        "nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2",
-                         "flops_per_unit": my_flops, "flops_model": model,
-                         "reference_algorithm_equivalent_tflops": per_gpu_units * ref_flops / (kms * 1e-3) * 1e-12,
-                         "kernel_ms": kms, "traffic": MEASURED_TRAFFIC.get(args.workload),
-                         "traffic_note": "bytes per launch of the dominant kernel, dram__bytes_read.sum + dram__bytes_write.sum from "
-                                         "the ncu captures under profiles/ (r01_ncu_traffic_hafnian50.csv, r01_ncu_*.txt); the "
-                                         "algorithmic traffic is KB (matrix in, 4 doubles per CTA out) — these paths are FP64-pipe "
-                                         "bound, DRAM sees the 4-byte spill slot and L2 write-backs over a multi-second launch"},
-            "result": {"re": res.real, "im": res.imag, "e2e_re": complex(r_e2e).real},
-        }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(kind, n, X, cutoff=args.cutoff)
+            line["cpu_baseline"] = cpu_baseline_subprocess(args.workload, args, 15.0)
+        if world == 1 and args.workload == "hafnian50" and not args.no_secondary:
+            sec = {}
+            for w in SECONDARY:
+                try:
+                    s = gpu_arm(w, args, env, 5, 3, min_seconds=2.0)
+                    if not args.no_cpu_baseline:
+                        s["cpu_baseline"] = cpu_baseline_subprocess(w, args, 5.0)
+                    sec[w] = s
+                except Exception as exc:  # noqa: BLE001  (a secondary config must never cost the headline line)
+                    sec[w] = {"error": f"{type(exc).__name__}: {exc}"}
+            line["secondary"] = sec
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

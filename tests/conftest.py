@@ -14,6 +14,25 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
 
 
+def _have_cuda():
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests are skipped (not failed) on a box without CUDA; `-m gpu` on the B200 box runs them all."""
+    if _have_cuda():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (run on the B200 box: pytest -m gpu)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def golden():
     with open(os.path.join(ROOT, "tests", "golden", "reference_outputs.json")) as fh:
@@ -30,9 +49,16 @@ def golden_next():
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """Make sure the CUDA library and the oracle are built (nvcc cross-compiles without a GPU)."""
+    import shutil
+
     import __graft_entry__ as ge
 
-    ge.build()
+    if shutil.which(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")) or os.path.exists(ge.LIB):
+        ge.build()
+    else:   # no CUDA toolchain and no prebuilt library: the oracle / host-logic tests still run
+        from oracle import build as obuild
+
+        obuild.ensure()
 
 
 def dec(d):

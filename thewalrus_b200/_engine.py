@@ -27,9 +27,12 @@ def require_cuda(device=None):
     _lib.load()
     if not torch.cuda.is_available():
         raise RuntimeError("walrus_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
-    if device is None:
-        return torch.device("cuda", torch.cuda.current_device())
-    return torch.device(device)
+    dev = torch.device("cuda") if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"walrus_b200 runs on CUDA devices only (got {dev}); there is no CPU fallback.")
+    if dev.index is None:   # 'cuda' without an ordinal means the CURRENT device for every entry point
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
 
 
 def _workspace(dev, nbytes):
@@ -146,7 +149,7 @@ def perm_range(M, method, k0, k1, device=None):
 
 
 def _dev_index(device):
-    return require_cuda(device).index or 0
+    return require_cuda(device).index
 
 
 def perm_f64_range(M, method, k0, k1, device=None):

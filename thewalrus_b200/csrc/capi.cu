@@ -50,6 +50,17 @@ struct PoolBlock {
 struct Pool {
     PoolBlock blk[64];
     int n = 0;
+    ~Pool() {                                  // thread exit: give idle blocks back (busy ones belong to a live call)
+        for (int i = 0; i < n; ++i)
+            if (blk[i].p && !blk[i].busy) {
+                int cur = 0;
+                if (cudaGetDevice(&cur) != cudaSuccess) break;      // runtime already torn down
+                if (blk[i].device != cur) cudaSetDevice(blk[i].device);
+                cudaFree(blk[i].p);
+                if (blk[i].device != cur) cudaSetDevice(cur);
+                blk[i] = PoolBlock{nullptr, 0, -1, false};
+            }
+    }
 };
 thread_local Pool g_pool;
 }  // namespace
@@ -62,7 +73,7 @@ int pool_alloc(void** p, size_t bytes) {
     int best = -1;
     for (int i = 0; i < pl.n; ++i) {
         const PoolBlock& b = pl.blk[i];
-        if (b.busy || b.device != dev || b.bytes < bytes) continue;
+        if (b.busy || !b.p || b.device != dev || b.bytes < bytes) continue;
         if (best < 0 || b.bytes < pl.blk[best].bytes) best = i;
     }
     if (best >= 0 && pl.blk[best].bytes <= 4 * bytes + (1u << 20)) {   // do not pin a huge block under a tiny request
@@ -75,8 +86,13 @@ int pool_alloc(void** p, size_t bytes) {
     while (want < bytes) want <<= 1;
     if (want > (64u << 20)) want = (bytes + (16u << 20) - 1) / (16u << 20) * (16u << 20);
     int slot = -1;
-    if (pl.n < 64) slot = pl.n++;
-    else {
+    for (int i = 0; i < pl.n && slot < 0; ++i)                             // an invalidated entry (failed cudaMalloc earlier)
+        if (!pl.blk[i].p) slot = i;
+    if (slot >= 0) {
+    } else if (pl.n < 64) {
+        slot = pl.n++;
+        pl.blk[slot] = PoolBlock{nullptr, 0, -1, false};
+    } else {
         for (int i = 0; i < pl.n; ++i)                                     // table full: recycle the smallest idle block
             if (!pl.blk[i].busy && (slot < 0 || pl.blk[i].bytes < pl.blk[slot].bytes)) slot = i;
         if (slot >= 0) {
@@ -84,6 +100,7 @@ int pool_alloc(void** p, size_t bytes) {
             if (pl.blk[slot].device != cur) cudaSetDevice(pl.blk[slot].device);
             cudaFree(pl.blk[slot].p);
             if (pl.blk[slot].device != cur) cudaSetDevice(cur);
+            pl.blk[slot] = PoolBlock{nullptr, 0, -1, false};             // never leave a freed pointer in the table
         }
     }
     void* q = nullptr;
@@ -281,9 +298,11 @@ extern "C" int wb200_release_scratch(void) {
     int kept = 0;
     for (int i = 0; i < pl.n; ++i) {
         if (pl.blk[i].busy) { pl.blk[kept++] = pl.blk[i]; continue; }
+        if (!pl.blk[i].p) continue;
         cudaSetDevice(pl.blk[i].device);
         cudaFree(pl.blk[i].p);
     }
+    for (int i = kept; i < pl.n; ++i) pl.blk[i] = PoolBlock{nullptr, 0, -1, false};   // no freed pointers in the tail
     pl.n = kept;
     cudaSetDevice(cur);
     return WB200_OK;

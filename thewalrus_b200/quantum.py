@@ -124,7 +124,7 @@ def probabilities(mu, cov, cutoff, parallel=False, hbar=2.0, rtol=1e-05, atol=1e
     ``state_vector`` returns the same numbers)."""
     del parallel, rtol, atol
     M = len(mu) // 2
-    pats = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(-1, M)
+    pats = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(cutoff ** M, M)
     return probabilities_batch(mu, cov, pats, hbar=hbar, group=group, device=device).reshape([cutoff] * M)
 
 
@@ -198,7 +198,7 @@ def state_vector(mu, cov, post_select=None, normalize=False, cutoff=5, hbar=2, c
         gamma = resc * gamma
         detQ = np.linalg.det(Qmat(cov, hbar=hbar) / np.cosh(choi_r))
     M = N - len(post_select)
-    free = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(-1, M)
+    free = np.array(list(product(range(cutoff), repeat=M)), dtype=np.int32).reshape(cutoff ** M, M)
     pats = _insert_post_selected(free, N, post_select)
     psi = (pref * _amplitudes(Bc, gamma, pats, detQ.real if not post_select else detQ, group, device)).reshape([cutoff] * M)
     if normalize:
@@ -214,7 +214,7 @@ def density_matrix(mu, cov, post_select=None, normalize=False, cutoff=5, hbar=2,
     post_select = dict(post_select or {})
     M = N - len(post_select)
     A, gamma = _state(mu, cov, hbar, 1e-10)
-    free = np.array(list(product(range(cutoff), repeat=2 * M)), dtype=np.int32).reshape(-1, 2 * M)
+    free = np.array(list(product(range(cutoff), repeat=2 * M)), dtype=np.int32).reshape(cutoff ** (2 * M), 2 * M)
     el0 = _insert_post_selected(free[:, :M], N, post_select)
     el1 = _insert_post_selected(free[:, M:], N, post_select)
     rpt = np.concatenate([el0, el1], axis=1)

@@ -125,7 +125,11 @@ def _lhaf_table(B, gammas, gidx, fixed, cutoff, device):
 def _draw_outcomes(probs):
     """One outcome per row of ``probs[R, K]`` (unnormalised) by inverse CDF with one uniform per row — the draw
     ``numpy.random.choice(K, p=probs / probs.sum())`` makes (one ``random_sample``, ``searchsorted`` right)."""
-    p = probs / probs.sum(axis=1, keepdims=True)
+    tot = probs.sum(axis=1, keepdims=True)
+    if not (np.isfinite(probs).all() and (probs >= 0).all() and (tot > 0).all()):
+        # numpy.random.choice(p=...) raises in the reference (samples.py:245-249) instead of drawing from garbage
+        raise ValueError("probabilities contain NaN, are negative or do not sum to a positive number")
+    p = probs / tot
     cdf = np.cumsum(p, axis=1)
     cdf /= cdf[:, -1:]
     u = np.random.random_sample(len(probs))
@@ -175,6 +179,8 @@ def hafnian_sample_state(cov, samples, mean=None, hbar=2, cutoff=5, max_photons=
     compatibility — the batch is the parallelism."""
     del parallel
     _validate_cov(cov)
+    if batch is not None and int(batch) < 1:
+        raise ValueError("batch must be >= 1")
     ch = _Chain(cov, mean, hbar)
     out, have = [], 0
     while have < samples:
@@ -246,6 +252,8 @@ def torontonian_sample_state(cov, samples, mu=None, hbar=2, max_photons=30, fano
     (samples.py:484-588).  Batching as in :func:`hafnian_sample_state`."""
     del parallel
     _validate_cov(cov)
+    if batch is not None and int(batch) < 1:
+        raise ValueError("batch must be >= 1")
     ch = _Chain(cov, mu, hbar, scale=fanout)
     out, have = [], 0
     while have < samples:
