@@ -112,40 +112,32 @@ def run_sharded(total, runner, group=None, width=4):
 # kernel runners (single device, range of the subset index)
 # ---------------------------------------------------------------------------------------------------
 def hafnian_range(Ax, Dx, j0, j1, device=None):
-    """Partial Glynn (loop) hafnian sum over subset indices [j0, j1) -> 4 doubles (no final scale)."""
-    torch = _torch()
-    dev = require_cuda(device)
+    """Partial Glynn (loop) hafnian sum over subset indices [j0, j1) -> 4 doubles (no final scale).
+    Host arrays in, host result out through ``wb200_hafnian_host`` (one H2D copy, the kernel, one 32-byte D2H)."""
     lib = _lib.load()
+    idx = _dev_index(device)
     n = Ax.shape[0]
-    with torch.cuda.device(dev):
-        dA = _to_dev(Ax, dev)
-        dD = _to_dev(Dx, dev) if Dx is not None else None
-        nbytes = lib.wb200_hafnian_workspace_bytes(n)
-        if nbytes == 0:
-            raise NotImplementedError(f"hafnian DMMA kernel supports even n in [2, 64], got {n}")
-        ws = _workspace(dev, nbytes)
-        out = torch.empty(4, dtype=torch.float64, device=dev)
-        rc = lib.wb200_hafnian_dev(dA.data_ptr(), dD.data_ptr() if dD is not None else None, n, j0, j1,
-                                   out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                                   torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(rc, "wb200_hafnian_dev")
-        return out.cpu().numpy()
+    if lib.wb200_hafnian_workspace_bytes(n) == 0:
+        raise NotImplementedError(f"hafnian DMMA kernel supports even n in [2, 64], got {n}")
+    Ax, pA = _lib.as_c128(Ax)
+    pD = None
+    if Dx is not None:
+        Dx, pD = _lib.as_c128(Dx)
+    out = np.empty(4)
+    rc = lib.wb200_hafnian_host(idx, pA, pD, n, j0, j1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_hafnian_host")
+    return out
 
 
 def perm_range(M, method, k0, k1, device=None):
     """Partial permanent sum over Gray-code steps [k0, k1) -> 4 doubles (complex kernel)."""
-    torch = _torch()
-    dev = require_cuda(device)
     lib = _lib.load()
-    n = M.shape[0]
-    with torch.cuda.device(dev):
-        dM = _to_dev(M, dev)
-        ws = _workspace(dev, lib.wb200_perm_workspace_bytes(n))
-        out = torch.empty(4, dtype=torch.float64, device=dev)
-        rc = lib.wb200_perm_dev(dM.data_ptr(), n, method, k0, k1, out.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                                torch.cuda.current_stream(dev).cuda_stream)
-        _lib.check(rc, "wb200_perm_dev")
-        return out.cpu().numpy()
+    idx = _dev_index(device)
+    M, pM = _lib.as_c128(M)
+    out = np.empty(4)
+    rc = lib.wb200_perm_host(idx, pM, M.shape[0], method, k0, k1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_perm_host")
+    return out
 
 
 def _dev_index(device):
@@ -196,26 +188,20 @@ def lhaf_general_range(Ax, Dx, oddV, oddloop, edge_reps, glynn, j0, j1, device=N
 
 def tor_range(O, p0, p1, device=None, gamma=None):
     """Partial (loop) torontonian sum over prefixes [p0, p1) -> (hi, lo); ``gamma`` selects the loop variant."""
-    torch = _torch()
-    dev = require_cuda(device)
     lib = _lib.load()
+    idx = _dev_index(device)
     N = O.shape[0] // 2
-    nbytes = lib.wb200_tor_workspace_bytes(N)
-    if nbytes == 0:
+    if lib.wb200_tor_workspace_bytes(N) == 0:
         raise NotImplementedError(f"torontonian kernel supports 2..32 modes, got {N}")
-    with torch.cuda.device(dev):
-        dO = _to_dev(O, dev)
-        ws = _workspace(dev, nbytes)
-        out = torch.empty(4, dtype=torch.float64, device=dev)
-        st = torch.cuda.current_stream(dev).cuda_stream
-        if gamma is None:
-            rc = lib.wb200_tor_dev(dO.data_ptr(), N, p0, p1, out.data_ptr(), ws.data_ptr(), ws.numel() * 8, st)
-        else:
-            dG = _to_dev(gamma, dev)
-            rc = lib.wb200_ltor_dev(dO.data_ptr(), dG.data_ptr(), N, p0, p1, out.data_ptr(), ws.data_ptr(),
-                                    ws.numel() * 8, st)
-        _lib.check(rc, "wb200_tor_dev" if gamma is None else "wb200_ltor_dev")
-        return out.cpu().numpy()[:2]
+    O, pO = _lib.as_c128(O)
+    out = np.empty(2)
+    if gamma is None:
+        rc = lib.wb200_tor_host(idx, pO, N, p0, p1, _lib.dptr(out), None)
+    else:
+        gamma, pG = _lib.as_c128(gamma)
+        rc = lib.wb200_ltor_host(idx, pO, pG, N, p0, p1, _lib.dptr(out), None)
+    _lib.check(rc, "wb200_tor_host" if gamma is None else "wb200_ltor_host")
+    return out
 
 
 def tor_num_prefixes(n_modes):

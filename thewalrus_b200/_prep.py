@@ -18,6 +18,11 @@ def matched_reps(reps):
     n = len(reps)
     if sum(reps) == 0:
         return np.array([], dtype=np.int64), np.array([], dtype=np.int64), None
+    if n > 1 and all(r == 1 for r in reps):
+        # closed form of the greedy rule for all-ones repetitions (the plain hafnian / loop hafnian call):
+        # vertices n-1, n-3, ... are paired with n-2, n-4, ...; an odd n leaves vertex 0 over
+        first = np.arange(n - 1, 0, -2, dtype=np.int64)
+        return np.concatenate([first, first - 1]), np.ones(len(first), dtype=np.int64), (0 if n % 2 else None)
 
     pool = [(int(r), i) for i, r in zip(range(n), reps) if r > 0]
     first, second, counts = [], [], []

@@ -17,6 +17,7 @@
 // to La Budde + Newton (thewalrus/charpoly.py:319-326; same numbers) — loop terms XD M^(t-1) D and
 // oddVX M^(t-1) D from one mat-vec chain, and the series c_t = (1/t) sum_i i a_i c_(t-i) of f_loop /
 // f_loop_odd (_hafnian.py:212-285).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace wb {
@@ -286,16 +287,21 @@ struct __align__(16) PatDesc {
     unsigned long long steps;
     unsigned int nchunks;
     short E, N, odd, kind;  // kind: 0 subset sum, 1 -> 1.0, 2 -> 0.0, 3 -> D[odd]
+    short cls;              // tile-shape class of the DMMA path (pat_dmma.cuh), PD_NCLS = warp-per-subset DFMA kernel
     unsigned short r[BW_EMAX];
     unsigned char u[BW_EMAX], v[BW_EMAX];
 };
 
-struct PatMeta {  // maxima over the batch + error flag, filled by the prep kernel
+struct PatMeta {  // maxima over the patterns of the fallback class + error flag, filled by the prep kernel
     int maxE, maxN, anyOdd, err;
 };
 
-__global__ void pat_prep_kernel(const int32_t* __restrict__ rpt, long long B, int nv, int loops, int glynn,
-                                PatDesc* __restrict__ desc, unsigned int* __restrict__ nchunks, PatMeta* meta) {
+constexpr int PAT_NCLS = 8;      // 7 DMMA tile classes + the fallback class (== PD_NCLS + 1, checked below)
+__host__ __device__ inline int pat_class_of(int E, int N, int odd);
+
+__global__ void pat_prep_kernel(const int32_t* __restrict__ rpt, long long B, int nv, int loops, int glynn, int force_fallback,
+                                PatDesc* __restrict__ desc, unsigned int* __restrict__ nchunks,
+                                unsigned char* __restrict__ cls_out, PatMeta* meta) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     int cnt[BW_NVMAX];
@@ -309,7 +315,8 @@ __global__ void pat_prep_kernel(const int32_t* __restrict__ rpt, long long B, in
         npool += cnt[i] > 0;
     }
     PatDesc d;
-    d.steps = 0; d.nchunks = 0; d.E = 0; d.N = (short)N; d.odd = -1; d.kind = 0;
+    d.steps = 0; d.nchunks = 0; d.E = 0; d.N = (short)N; d.odd = -1; d.kind = 0; d.cls = PAT_NCLS - 1;
+    cls_out[p] = (unsigned char)(PAT_NCLS - 1);
     if (bad || N > 32000) { atomicExch(&meta->err, 1); d.kind = 2; desc[p] = d; nchunks[p] = 0; return; }
     if (N == 0) d.kind = 1;
     else if (!loops && (N & 1)) d.kind = 2;
@@ -358,22 +365,30 @@ __global__ void pat_prep_kernel(const int32_t* __restrict__ rpt, long long B, in
     }
     d.E = (short)E; d.steps = steps;
     d.nchunks = (unsigned int)((steps + BW_CHUNK - 1) / BW_CHUNK);
+    d.cls = (short)(force_fallback ? PAT_NCLS - 1 : pat_class_of(E, N, d.odd));
+    cls_out[p] = (unsigned char)d.cls;
     desc[p] = d;
     nchunks[p] = d.nchunks;
-    atomicMax(&meta->maxE, E);
-    atomicMax(&meta->maxN, N);
-    if (d.odd >= 0) atomicMax(&meta->anyOdd, 1);
+    if (d.cls == PAT_NCLS - 1) {
+        atomicMax(&meta->maxE, E);
+        atomicMax(&meta->maxN, N);
+        if (d.odd >= 0) atomicMax(&meta->anyOdd, 1);
+    }
 }
 
-// exclusive scan of n unsigned ints into 64-bit offsets (off[n] = total); one CTA of 1024 threads
-__global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restrict__ in, long long n,
-                                                    unsigned long long* __restrict__ off) {
+// Exclusive scans of the per-pattern chunk counts, one per class (blockIdx.x = class c, one CTA of 1024 threads each):
+// off[c][i] = chunks of the class-c patterns before pattern i, off[c][n] = totals[c] = all chunks of class c.
+__global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restrict__ in_all, const unsigned char* __restrict__ cls,
+                                                    long long n, unsigned long long* __restrict__ off_all,
+                                                    unsigned long long* __restrict__ totals) {
     __shared__ unsigned long long part[1024];
     const int tid = threadIdx.x;
+    const int c = blockIdx.x;
+    unsigned long long* off = off_all + (size_t)c * (n + 1);
     const long long per = (n + 1023) / 1024;
     const long long lo = tid * per, hi = lo + per < n ? lo + per : n;
     unsigned long long s = 0;
-    for (long long i = lo; i < hi; ++i) s += in[i];
+    for (long long i = lo; i < hi; ++i) s += cls[i] == c ? in_all[i] : 0u;
     part[tid] = s;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
@@ -383,8 +398,8 @@ __global__ void __launch_bounds__(1024) scan_kernel(const unsigned int* __restri
         __syncthreads();
     }
     unsigned long long run = tid ? part[tid - 1] : 0ull;
-    for (long long i = lo; i < hi; ++i) { off[i] = run; run += in[i]; }
-    if (tid == 1023) off[n] = part[1023];
+    for (long long i = lo; i < hi; ++i) { off[i] = run; run += cls[i] == c ? in_all[i] : 0u; }
+    if (tid == 1023) { off[n] = part[1023]; totals[c] = part[1023]; }
 }
 
 struct PatParams {
@@ -400,6 +415,16 @@ struct PatParams {
     unsigned long long* counter;
     double* partial;  // nchunks * 4
 };
+
+}  // namespace wb
+#include "pat_dmma.cuh"
+namespace wb {
+
+static_assert(PAT_NCLS == PD_NCLS + 1, "class table out of sync");
+__host__ __device__ inline int pat_class_of(int E, int N, int odd) {
+    if (odd >= 0 || N / 2 > PD_TMAX) return PD_NCLS;
+    return pd_class(E);
+}
 
 __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
     extern __shared__ __align__(16) unsigned char smem_bw[];
@@ -465,8 +490,12 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
     }
 }
 
-__global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigned long long* __restrict__ coff,
-                                 const double* __restrict__ partial, const double2* __restrict__ D,
+struct PatBases {
+    unsigned long long base[PAT_NCLS];   // first slot of class c in the partial table
+};
+
+__global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigned long long* __restrict__ coff_all, PatBases cb,
+                                 const double* __restrict__ partial_all, const double2* __restrict__ D,
                                  const int32_t* __restrict__ gidx, int nv, int glynn, long long B,
                                  double2* __restrict__ out) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -476,6 +505,8 @@ __global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigne
     if (d->kind == 2) { out[p] = make_double2(0.0, 0.0); return; }
     if (d->kind == 3) { out[p] = D[(gidx ? (size_t)gidx[p] * nv : 0) + d->odd]; return; }
     dd re = {0.0, 0.0}, im = {0.0, 0.0};
+    const unsigned long long* coff = coff_all + (size_t)d->cls * (B + 1);
+    const double* partial = partial_all + 4 * cb.base[d->cls];
     for (unsigned long long c = coff[p]; c < coff[p + 1]; ++c) {
         dd_add_dd(re, dd{partial[c * 4 + 0], partial[c * 4 + 1]});
         dd_add_dd(im, dd{partial[c * 4 + 2], partial[c * 4 + 3]});
@@ -664,6 +695,87 @@ static int bw_pick_warps(size_t per_warp, int* ctas) {
     return best_w;
 }
 
+// Device-side driver of the batched front end: everything between "inputs are in HBM" and "results are in HBM" on the
+// caller's stream.  Scratch comes from the caching pool.  ONE host synchronisation in the middle (the class totals and
+// shared-memory maxima decide the launch shapes) and one at the end (the scratch is released on return).
+// env WB200_PAT_DFMA=1 forces every pattern onto the warp-per-subset DFMA kernel (A/B measurements, tests).
+static int lhaf_matrices_device(const double2* dA, const int32_t* dai, const double2* dD, const int32_t* dgi, int nv,
+                                const int32_t* drpt, int64_t B, int glynn, double2* dout, int sms, cudaStream_t st,
+                                double* kernel_ms) {
+    const char* env_dfma = getenv("WB200_PAT_DFMA");      // read per call: the tests toggle it
+    const int force_fallback = (env_dfma && atoi(env_dfma)) ? 1 : 0;
+    DevBufB ddesc, dnch, dcls, dcoff, dmeta, dcounter, dpartial;
+    WB_POOL(pool_alloc(&ddesc.p, sizeof(PatDesc) * (size_t)B));
+    WB_POOL(pool_alloc(&dnch.p, sizeof(unsigned int) * (size_t)B));
+    WB_POOL(pool_alloc(&dcls.p, (size_t)B));
+    WB_POOL(pool_alloc(&dcoff.p, sizeof(unsigned long long) * ((size_t)B + 1) * PAT_NCLS));
+    // meta block: PatMeta | totals[PAT_NCLS] | counters[PAT_NCLS]
+    const size_t meta_bytes = 64 + 2 * sizeof(unsigned long long) * PAT_NCLS;
+    WB_POOL(pool_alloc(&dmeta.p, meta_bytes));
+    WB_CUDA(cudaMemsetAsync(dmeta.p, 0, meta_bytes, st));
+    PatMeta* d_meta = (PatMeta*)dmeta.p;
+    unsigned long long* d_totals = (unsigned long long*)((char*)dmeta.p + 64);
+    unsigned long long* d_counters = d_totals + PAT_NCLS;
+    EvPair ev;
+    WB_CUDA(cudaEventCreate(&ev.e0));
+    WB_CUDA(cudaEventCreate(&ev.e1));
+    WB_CUDA(cudaEventRecord(ev.e0, st));
+    pat_prep_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(drpt, B, nv, dD != nullptr, glynn, force_fallback, (PatDesc*)ddesc.p,
+                                                                 (unsigned int*)dnch.p, (unsigned char*)dcls.p, d_meta);
+    scan_kernel<<<PAT_NCLS, 1024, 0, st>>>((const unsigned int*)dnch.p, (const unsigned char*)dcls.p, B,
+                                           (unsigned long long*)dcoff.p, d_totals);
+    WB_CUDA(cudaGetLastError());
+    struct { PatMeta meta; char pad[64 - sizeof(PatMeta)]; unsigned long long totals[PAT_NCLS]; } h;
+    WB_CUDA(cudaMemcpyAsync(&h, dmeta.p, 64 + sizeof(unsigned long long) * PAT_NCLS, cudaMemcpyDeviceToHost, st));
+    WB_CUDA(cudaStreamSynchronize(st));
+    if (h.meta.err) {
+        set_error(h.meta.err == 1 ? "lhaf_patterns: repetition counts must be in [0, 65535] with total <= 32000"
+                                  : "lhaf_patterns: a pattern exceeds the kernel limits (edges <= %d, series order <= %d, steps <= 1e12) or has an odd total without loops", BW_EMAX, BW_MAX_ORDER);
+        return h.meta.err == 1 ? WB200_EINVAL : WB200_ENOSUP;
+    }
+    PatBases cb;
+    unsigned long long nchunks = 0;
+    for (int c = 0; c < PAT_NCLS; ++c) { cb.base[c] = nchunks; nchunks += h.totals[c]; }
+    if (nchunks > 0) {
+        WB_POOL(pool_alloc(&dpartial.p, sizeof(double) * 4 * (size_t)nchunks));
+        // largest classes first: the small ones fill the tail of the big ones' last wave
+        for (int c = PAT_NCLS - 1; c >= 0; --c) {
+            if (!h.totals[c]) continue;
+            PatParams p;
+            p.A = dA; p.D = dD; p.gidx = dgi; p.aidx = dai; p.nv = nv; p.glynn = glynn;
+            p.smax = 2 * h.meta.maxE; p.T = h.meta.maxN / 2; p.O = h.meta.anyOdd ? h.meta.maxN : h.meta.maxN / 2;
+            p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p + (size_t)c * (B + 1);
+            p.nchunks = h.totals[c]; p.counter = d_counters + c;
+            p.partial = (double*)dpartial.p + 4 * cb.base[c];
+            if (c < PAT_NCLS - 1) {
+                int rc = launch_pat_class(c, p, sms, st);
+                if (rc) return rc;
+                continue;
+            }
+            const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
+            int ctas = 1;
+            const int wpc = bw_pick_warps(per_warp, &ctas);
+            if (wpc < 1) { set_error("lhaf_patterns: pattern too large for shared memory (%zu bytes per warp)", per_warp); return WB200_ENOSUP; }
+            const size_t shm = per_warp * wpc;
+            WB_CUDA(cudaFuncSetAttribute(pat_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            int grid = sms * ctas;
+            const unsigned long long want = (p.nchunks + wpc - 1) / wpc;
+            if ((unsigned long long)grid > want) grid = (int)want;
+            pat_main_kernel<<<grid, 32 * wpc, shm, st>>>(p);
+            WB_CUDA(cudaGetLastError());
+        }
+    }
+    pat_final_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const PatDesc*)ddesc.p, (const unsigned long long*)dcoff.p, cb,
+                                                                  (const double*)dpartial.p, dD, dgi, nv, glynn, B, dout);
+    WB_CUDA(cudaEventRecord(ev.e1, st));
+    WB_CUDA(cudaEventSynchronize(ev.e1));
+    WB_CUDA(cudaGetLastError());
+    float ms = 0;
+    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+    if (kernel_ms) *kernel_ms = ms;
+    return WB200_OK;
+}
+
 }  // namespace wb
 
 using namespace wb;
@@ -698,7 +810,7 @@ extern "C" int wb200_lhaf_matrices_host(int device, const double* A, int n_A, co
     WB_CUDA(cudaSetDevice(device));
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    DevBufB dA, dai, dD, dgi, drpt, ddesc, dnch, dcoff, dmeta, dcounter, dpartial, dout;
+    DevBufB dA, dai, dD, dgi, drpt, ddesc, dnch, dcls, dcoff, dmeta, dtotals, dcounter, dpartial, dout;
     WB_POOL(pool_alloc(&dA.p, sizeof(double2) * (size_t)n_A * nv * nv));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * (size_t)n_A * nv * nv, cudaMemcpyHostToDevice));
     if (A_index) {
@@ -715,60 +827,10 @@ extern "C" int wb200_lhaf_matrices_host(int device, const double* A, int n_A, co
     }
     WB_POOL(pool_alloc(&drpt.p, sizeof(int32_t) * (size_t)B * nv));
     WB_CUDA(cudaMemcpy(drpt.p, rpt, sizeof(int32_t) * (size_t)B * nv, cudaMemcpyHostToDevice));
-    WB_POOL(pool_alloc(&ddesc.p, sizeof(PatDesc) * (size_t)B));
-    WB_POOL(pool_alloc(&dnch.p, sizeof(unsigned int) * (size_t)B));
-    WB_POOL(pool_alloc(&dcoff.p, sizeof(unsigned long long) * ((size_t)B + 1)));
-    WB_POOL(pool_alloc(&dmeta.p, sizeof(PatMeta)));
-    WB_POOL(pool_alloc(&dcounter.p, sizeof(unsigned long long)));
     WB_POOL(pool_alloc(&dout.p, sizeof(double2) * (size_t)B));
-    WB_CUDA(cudaMemset(dmeta.p, 0, sizeof(PatMeta)));
-    WB_CUDA(cudaMemset(dcounter.p, 0, sizeof(unsigned long long)));
-    EvPair ev;
-    WB_CUDA(cudaEventCreate(&ev.e0));
-    WB_CUDA(cudaEventCreate(&ev.e1));
-    WB_CUDA(cudaEventRecord(ev.e0, 0));
-    pat_prep_kernel<<<(unsigned)((B + 127) / 128), 128>>>((const int32_t*)drpt.p, B, nv, gamma != nullptr, glynn,
-                                                          (PatDesc*)ddesc.p, (unsigned int*)dnch.p, (PatMeta*)dmeta.p);
-    scan_kernel<<<1, 1024>>>((const unsigned int*)dnch.p, B, (unsigned long long*)dcoff.p);
-    WB_CUDA(cudaGetLastError());
-    PatMeta meta;
-    unsigned long long nchunks = 0;
-    WB_CUDA(cudaMemcpy(&meta, dmeta.p, sizeof(meta), cudaMemcpyDeviceToHost));
-    WB_CUDA(cudaMemcpy(&nchunks, (unsigned long long*)dcoff.p + B, sizeof(nchunks), cudaMemcpyDeviceToHost));
-    if (meta.err) {
-        set_error(meta.err == 1 ? "lhaf_patterns: repetition counts must be in [0, 65535] with total <= 32000"
-                                : "lhaf_patterns: a pattern exceeds the kernel limits (edges <= %d, series order <= %d, steps <= 1e12) or has an odd total without loops", BW_EMAX, BW_MAX_ORDER);
-        return meta.err == 1 ? WB200_EINVAL : WB200_ENOSUP;
-    }
-    if (nchunks > 0) {
-        PatParams p;
-        p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.gidx = (const int32_t*)dgi.p; p.aidx = (const int32_t*)dai.p; p.nv = nv; p.glynn = glynn;
-        p.smax = 2 * meta.maxE; p.T = meta.maxN / 2; p.O = meta.anyOdd ? meta.maxN : meta.maxN / 2;
-        p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p;
-        p.nchunks = nchunks; p.counter = (unsigned long long*)dcounter.p;
-        WB_POOL(pool_alloc(&dpartial.p, sizeof(double) * 4 * (size_t)nchunks));
-        p.partial = (double*)dpartial.p;
-        const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
-        int ctas = 1;
-        const int wpc = bw_pick_warps(per_warp, &ctas);
-        if (wpc < 1) { set_error("lhaf_patterns: pattern too large for shared memory (%zu bytes per warp)", per_warp); return WB200_ENOSUP; }
-        const size_t shm = per_warp * wpc;
-        WB_CUDA(cudaFuncSetAttribute(pat_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-        int grid = sms * ctas;
-        const unsigned long long want = (nchunks + wpc - 1) / wpc;
-        if ((unsigned long long)grid > want) grid = (int)want;
-        pat_main_kernel<<<grid, 32 * wpc, shm>>>(p);
-        WB_CUDA(cudaGetLastError());
-    }
-    pat_final_kernel<<<(unsigned)((B + 127) / 128), 128>>>((const PatDesc*)ddesc.p, (const unsigned long long*)dcoff.p,
-                                                           (const double*)dpartial.p, (const double2*)dD.p,
-                                                           (const int32_t*)dgi.p, nv, glynn, B, (double2*)dout.p);
-    WB_CUDA(cudaEventRecord(ev.e1, 0));
-    WB_CUDA(cudaEventSynchronize(ev.e1));
-    WB_CUDA(cudaGetLastError());
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
-    if (kernel_ms) *kernel_ms = ms;
+    int rc = lhaf_matrices_device((const double2*)dA.p, (const int32_t*)dai.p, (const double2*)dD.p, (const int32_t*)dgi.p, nv,
+                                  (const int32_t*)drpt.p, B, glynn, (double2*)dout.p, sms, (cudaStream_t)0, kernel_ms);
+    if (rc) return rc;
     WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double2) * (size_t)B, cudaMemcpyDeviceToHost));
     return WB200_OK;
 }

@@ -29,38 +29,22 @@
 // four subsets than that, so small problems spread over all SMs (haf_pick_warps).
 #include <stdlib.h>
 #include "common.cuh"
+#include "haf_dmma.cuh"
 
 namespace wb {
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-        : "+d"(c0), "+d"(c1)
-        : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ double flipsign(double x, unsigned mask) {
-    return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
-}
-
-// element held at K-chunk kappa, position k (or -1 for padding)
-__device__ __forceinline__ int haf_chunk_elem(int kappa, int k, int m, int TF, int tp) {
-    if (kappa < 2 * TF) {
-        const int iv = 4 * (kappa >> 1) + k;
-        return iv < m ? iv + (kappa & 1) * m : -1;
-    }
-    return (k >> 1) < tp ? 4 * TF + (k >> 1) + (k & 1) * m : -1;
-}
 
 // Fragment table, (kappa * NT + tile) * 32 + lane:
 //   standard tile taup: (Ar, Ai)[e_k, e_n], e_n = 4 taup + (ncol >> 1) + (ncol & 1) m
 //   tail tile        : (F1, F2) with column ncol <-> vertex u(ncol >> 1), output part ncol & 1:
 //                      re: (Ar, -Ai), im: (Ai, Ar)   so that  D += yr * F1 + yi * F2
-__global__ void haf_prep_kernel(const double* __restrict__ A, int n, int m, int TF, int tail,
-                                double2* __restrict__ frag) {
+// Every CTA builds the table straight into its shared memory (it costs what copying a prebuilt table would, and
+// saves the separate prep launch of round 1: 3 us + a launch gap on a 40 us n = 24 call).
+__device__ __forceinline__ void haf_build_frag(const double* __restrict__ A, int n, int m, int TF, int tail,
+                                               double2* __restrict__ frag, int tid, int nthreads) {
     const int tp = tail ? m - 4 * TF : 0;
     const int NK = 2 * TF + (tail ? 1 : 0), NT = TF + (tail ? 1 : 0);
     const int total = NK * NT * 32;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    for (int idx = tid; idx < total; idx += nthreads) {
         const int lane = idx & 31, pair = idx >> 5;
         const int tile = pair % NT, kappa = pair / NT;
         const int k = lane & 3, ncol = lane >> 2;
@@ -76,14 +60,14 @@ __global__ void haf_prep_kernel(const double* __restrict__ A, int n, int m, int 
                 const int in = 4 * tile + (ncol >> 1);
                 if (in < m) {
                     const int en = in + (ncol & 1) * m;
-                    const double ar = A[2 * ((size_t)ek * n + en)], ai = A[2 * ((size_t)ek * n + en) + 1];
+                    const double ar = __ldg(A + 2 * ((size_t)ek * n + en)), ai = __ldg(A + 2 * ((size_t)ek * n + en) + 1);
                     v = imag_slot ? make_double2(-ai, ar) : make_double2(ar, ai);
                 }
             } else {
                 const int tq = ncol >> 1;
                 if ((tq >> 1) < tp) {
                     const int en = 4 * TF + (tq >> 1) + (tq & 1) * m;
-                    const double ar = A[2 * ((size_t)ek * n + en)], ai = A[2 * ((size_t)ek * n + en) + 1];
+                    const double ar = __ldg(A + 2 * ((size_t)ek * n + en)), ai = __ldg(A + 2 * ((size_t)ek * n + en) + 1);
                     v = (ncol & 1) ? make_double2(ai, ar) : make_double2(ar, -ai);
                     if (packk) v = make_double2(imag_slot ? v.y : v.x, 0.0);   // D += [yr | yi] . [F1 ; F2]
                 }
@@ -105,121 +89,19 @@ struct HafCfg {
     static constexpr size_t BYTES = sizeof(double) * (FRAG_D + WARPS * WARP_D);
 };
 
-template <int TF, bool TAIL>
-struct HafRow {  // one 8-row panel slice held by a thread
-    double wr[TF > 0 ? TF : 1][2], wi[TF > 0 ? TF : 1][2];
-    double wtr, wti;
-};
-template <int TF, bool TAIL>
-struct HafY {
-    double yr[TF > 0 ? 2 * TF : 1], yi[TF > 0 ? 2 * TF : 1];
-    double ytr, yti;
-};
-
-// W <- Y * A' on the tensor pipe
-template <int TF, bool TAIL>
-__device__ __forceinline__ void haf_step(const double2* __restrict__ sfrag, int lane, const HafY<TF, TAIL>& y,
-                                         HafRow<TF, TAIL>& w, bool packk) {
-    constexpr int NK = 2 * TF + (TAIL ? 1 : 0), NT = TF + (TAIL ? 1 : 0);
-#pragma unroll
-    for (int tp = 0; tp < TF; ++tp) {
-        w.wr[tp][0] = w.wr[tp][1] = 0.0;
-        w.wi[tp][0] = w.wi[tp][1] = 0.0;
-    }
-    w.wtr = w.wti = 0.0;
-#pragma unroll
-    for (int kap = 0; kap < NK; ++kap) {
-        const double ar = kap < 2 * TF ? y.yr[kap < 2 * TF ? kap : 0] : y.ytr;
-        const double ai = kap < 2 * TF ? y.yi[kap < 2 * TF ? kap : 0] : y.yti;
-        if (TAIL && kap == 2 * TF && packk) {   // K-packed tail chunk (see haf_prep_kernel): 2 DMMAs per tile
-            const double yi2 = __shfl_sync(0xffffffffu, y.yti, lane & ~2);
-            const double ap = (lane & 2) ? yi2 : y.ytr;
-#pragma unroll
-            for (int tp = 0; tp < TF; ++tp) {
-                const double2 b = sfrag[(kap * NT + tp) * 32 + lane];
-                dmma884(w.wr[tp][0], w.wr[tp][1], ap, b.x);
-                dmma884(w.wi[tp][0], w.wi[tp][1], ap, b.y);
-            }
-            const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
-            dmma884(w.wtr, w.wti, ap, b.x);
-            continue;
-        }
-#pragma unroll
-        for (int tp = 0; tp < TF; ++tp) {
-            const double2 b = sfrag[(kap * NT + tp) * 32 + lane];
-            const double nbi = -b.y;
-            dmma884(w.wr[tp][0], w.wr[tp][1], ar, b.x);
-            dmma884(w.wi[tp][0], w.wi[tp][1], ar, b.y);
-            dmma884(w.wr[tp][0], w.wr[tp][1], ai, nbi);
-            dmma884(w.wi[tp][0], w.wi[tp][1], ai, b.x);
-        }
-        if (TAIL) {
-            const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
-            dmma884(w.wtr, w.wti, ar, b.x);
-            dmma884(w.wtr, w.wti, ai, b.y);
-        }
-    }
-}
-
-#define WB_CFMA(sr, si, xr_, xi_, yr_, yi_)                  \
-    do {                                                       \
-        sr = fma(xr_, yr_, sr); sr = fma(-(xi_), yi_, sr);     \
-        si = fma(xr_, yi_, si); si = fma(xi_, yr_, si);        \
-    } while (0)
-
-// Y <- S_j W (swap partners, sign delta).  If IP: also odd = <X, Y_old>, even = <X, Y_new> over this
-// thread's slots, X = W of the partner row (lane ^ 16) or W itself (SELF, the loop row).
-template <int TF, bool TAIL, bool IP, bool SELF>
-__device__ __forceinline__ void haf_advance(const HafRow<TF, TAIL>& w, HafY<TF, TAIL>& y, const unsigned* sm,
-                                            unsigned smt, double& orr, double& oi, double& er, double& ei) {
-    double o2r = 0.0, o2i = 0.0, e2r = 0.0, e2i = 0.0;  // second chains for ILP
-    orr = oi = er = ei = 0.0;
-#pragma unroll
-    for (int tau = 0; tau < TF; ++tau) {
-        double x0r = 0, x0i = 0, x1r = 0, x1i = 0;
-        if (IP) {
-            x0r = SELF ? w.wr[tau][0] : shfl_xor_d(w.wr[tau][0], 16);
-            x0i = SELF ? w.wi[tau][0] : shfl_xor_d(w.wi[tau][0], 16);
-            x1r = SELF ? w.wr[tau][1] : shfl_xor_d(w.wr[tau][1], 16);
-            x1i = SELF ? w.wi[tau][1] : shfl_xor_d(w.wi[tau][1], 16);
-            WB_CFMA(orr, oi, x0r, x0i, y.yr[2 * tau], y.yi[2 * tau]);
-            WB_CFMA(o2r, o2i, x1r, x1i, y.yr[2 * tau + 1], y.yi[2 * tau + 1]);
-        }
-        y.yr[2 * tau + 0] = flipsign(w.wr[tau][1], sm[tau]);
-        y.yr[2 * tau + 1] = flipsign(w.wr[tau][0], sm[tau]);
-        y.yi[2 * tau + 0] = flipsign(w.wi[tau][1], sm[tau]);
-        y.yi[2 * tau + 1] = flipsign(w.wi[tau][0], sm[tau]);
-        if (IP) {
-            WB_CFMA(er, ei, x0r, x0i, y.yr[2 * tau], y.yi[2 * tau]);
-            WB_CFMA(e2r, e2i, x1r, x1i, y.yr[2 * tau + 1], y.yi[2 * tau + 1]);
-        }
-    }
-    if (TAIL) {
-        double xr = 0, xi = 0;
-        if (IP) {
-            xr = SELF ? w.wtr : shfl_xor_d(w.wtr, 16);
-            xi = SELF ? w.wti : shfl_xor_d(w.wti, 16);
-            WB_CFMA(orr, oi, xr, xi, y.ytr, y.yti);
-        }
-        y.ytr = flipsign(shfl_xor_d(w.wtr, 1), smt);
-        y.yti = flipsign(shfl_xor_d(w.wti, 1), smt);
-        if (IP) WB_CFMA(er, ei, xr, xi, y.ytr, y.yti);
-    }
-    if (IP) {
-        orr += o2r; oi += o2i; er += e2r; ei += e2i;
-        orr += shfl_xor_d(orr, 1); oi += shfl_xor_d(oi, 1); er += shfl_xor_d(er, 1); ei += shfl_xor_d(ei, 1);
-        orr += shfl_xor_d(orr, 2); oi += shfl_xor_d(oi, 2); er += shfl_xor_d(er, 2); ei += shfl_xor_d(ei, 2);
-    }
-}
-
-template <int TF, bool TAIL, int WARPS>
+// PS = panel split: the row panels of one group of four subsets are dealt round-robin to a TEAM of PS warps (on
+// different schedulers), whose per-panel trace shares are combined in fixed warp order by the team's first warp.
+// PS = 1 (one warp walks all panels) is the full-size shape; PS = 3 serves small problems (n <= 30), where there are
+// too few groups to give every scheduler three independent warps (n = 24: 512 groups for 592 schedulers).
+template <int TF, bool TAIL, int WARPS, int PS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
-haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A, const double* __restrict__ D, int n,
+haf_dmma_kernel(const double* __restrict__ A, const double* __restrict__ D, int n,
                 int m, uint64_t j0, uint64_t j1, double* __restrict__ partials) {
     using C = HafCfg<TF, TAIL, WARPS>;
+    static_assert(WARPS % PS == 0, "teams must tile the CTA");
     extern __shared__ __align__(16) double smem[];
     double2* sfrag = reinterpret_cast<double2*>(smem);
-    for (int i = threadIdx.x; i < C::FRAG_D / 2; i += 32 * WARPS) sfrag[i] = frag_g[i];
+    haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * WARPS);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -235,13 +117,18 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
     const int K = nprod + 1;                          // tr(M^j), j <= K, come from single elements
     const int nstepD = m >> 1;                        // products of the loop row (l_1..l_m)
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
-    const uint64_t gstride = (uint64_t)gridDim.x * WARPS;
+    constexpr int TEAMS = WARPS / PS;
+    const int team = warp / PS, pw = warp - team * PS;       // warp pw of its team takes panels pw, pw + PS, ...
+    const uint64_t gstride = (uint64_t)gridDim.x * TEAMS;
+    auto team_barrier = [&]() {
+        if constexpr (PS > 1) asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(32 * PS) : "memory");
+    };
 
     cdd acc;
     acc.re = {0.0, 0.0};
     acc.im = {0.0, 0.0};
 
-    for (uint64_t G = (uint64_t)blockIdx.x * WARPS + warp; G < ngroups; G += gstride) {
+    for (uint64_t G = (uint64_t)blockIdx.x * TEAMS + team; G < ngroups; G += gstride) {
         const uint64_t jq = j0 + 4 * G + q;
         const bool valid = jq < j1;
         unsigned sm[TF > 0 ? TF : 1];
@@ -257,7 +144,7 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
         __syncwarp();
 
         const int npanels = m + (loop ? 1 : 0);
-        for (int i = 0; i < npanels; ++i) {
+        for (int i = pw; i < npanels; i += PS) {
             const bool isD = (i == m);
             HafRow<TF, TAIL> w;
             HafY<TF, TAIL> y = {};
@@ -354,12 +241,25 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
             }
             __syncwarp();  // part[] slots are updated by different lanes in the next panel
         }
-        // ---- combine the two rows (vertex i and i + m) of each subset q
+        // ---- combine the two rows (vertex i and i + m) of each subset q (and, for PS > 1, the team's warps in order)
+        team_barrier();                                             // (A) every panel of the group is done
+        if (PS > 1 && pw != 0) { team_barrier(); continue; }       // (B) below; the team's first warp finishes the group
         for (int s = lane; s < (m + 1) * 4; s += 32) {
             const int j = s >> 2, qq = s & 3;
-            const double2 a = part[j * 8 + qq], b = part[j * 8 + qq + 4];
-            Pk[(j * 4 + qq) * 2] = a.x + b.x; Pk[(j * 4 + qq) * 2 + 1] = a.y + b.y;
+            double pr = 0.0, pi = 0.0;
+#pragma unroll
+            for (int tw = 0; tw < PS; ++tw) {
+                const double2* pt = reinterpret_cast<const double2*>(wsm + tw * C::WARP_D);
+                const double2 a = pt[j * 8 + qq], b = pt[j * 8 + qq + 4];
+                pr += a.x + b.x; pi += a.y + b.y;
+            }
+            Pk[(j * 4 + qq) * 2] = pr; Pk[(j * 4 + qq) * 2 + 1] = pi;
         }
+        if (PS > 1 && loop && (m % PS) != 0) {                      // loop terms live with the warp that walked the loop row
+            const double* Lsrc = wsm + (m % PS) * C::WARP_D + C::PART_D + C::P_D;
+            for (int s = lane; s < (m + 2) * 8; s += 32) Lk[s] = Lsrc[s];
+        }
+        team_barrier();                                             // (B) the other warps may reuse their slices
         __syncwarp();
         // ---- coefficient [eta^m] of exp(sum_i a_i eta^i), a_i = p_i/(2i) (+ l_i/2): c_t = (1/t) sum_i i a_i c_{t-i}
         if (t == 0 && half == 0) {
@@ -389,54 +289,52 @@ haf_dmma_kernel(const double2* __restrict__ frag_g, const double* __restrict__ A
     block_reduce_store(acc, red, partials);
 }
 
-// Warps per CTA (one CTA per SM): 12 (<= 168 registers, 3 warps per scheduler) for full-size problems — measured on
-// B200: 12 warps beat 8 by 2-4 % at n = 40..64 (profiles/r01_hafnian_sweep.txt).  Small problems do not have 12
-// groups of four subsets per SM; one warp per scheduler already saturates the DMMA pipe (tools/fp64_peak.cu:
-// dmma884 ch4, 128 threads), so they are spread over as many SMs as possible with 4- or 8-warp CTAs instead of
-// packing 12 warps on a fraction of the SMs (n = 24: 512 groups -> 128 CTAs x 4 warps instead of 43 x 12).
-// env WB200_HAF_WARPS = 4 | 8 | 12 overrides.
-static int haf_pick_warps(uint64_t ngroups, int sms) {
-    static int env = -1;
-    if (env < 0) {
-        const char* e = getenv("WB200_HAF_WARPS");
-        env = e ? atoi(e) : 0;
-    }
-    if (env == 4 || env == 8 || env == 12) return env;
-    if (ngroups <= 4ull * (uint64_t)sms) return 4;
-    if (ngroups <= 8ull * (uint64_t)sms) return 8;
-    return 12;
+// Launch shape (one CTA per SM).  Full-size problems: 12 warps (<= 168 registers, 3 warps per scheduler), each warp
+// walks all row panels of its group — measured on B200: 12 warps beat 8 by 2-4 % at n = 40..64
+// (profiles/r01_hafnian_sweep.txt).  Small problems (n <= 30, i.e. at most 4096 groups of four subsets) do not have
+// three independent groups per scheduler: there the panels of a group are split over a team of 3 warps
+// (PS = 3; 4 teams per CTA, or one team per CTA when there are fewer groups than SMs), so that every scheduler
+// still interleaves 3 warps and the launch takes ceil(groups / (4 * SMs)) short rounds instead of one or two long ones.
+// env WB200_HAF_WARPS = 4 | 8 | 12 forces the round-1 shapes (PS = 1) for A/B measurements.
+static int haf_env_warps() {
+    const char* e = getenv("WB200_HAF_WARPS");
+    const int v = e ? atoi(e) : 0;
+    return (v == 4 || v == 8 || v == 12) ? v : 0;
 }
 
-template <int TF, bool TAIL, int WARPS>
-static int launch_haf_w(const double2* frag, const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
+template <int TF, bool TAIL, int WARPS, int PS>
+static int launch_haf_w(const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
                         double* partials, uint64_t ngroups, int sms, int* grid_out, cudaStream_t st) {
     using C = HafCfg<TF, TAIL, WARPS>;
-    auto kern = haf_dmma_kernel<TF, TAIL, WARPS>;
-    uint64_t want = (ngroups + WARPS - 1) / WARPS;
+    auto kern = haf_dmma_kernel<TF, TAIL, WARPS, PS>;
+    constexpr int TEAMS = WARPS / PS;
+    uint64_t want = (ngroups + TEAMS - 1) / TEAMS;
     const int grid = (int)(want < (uint64_t)sms ? (want ? want : 1) : (uint64_t)sms);
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
-    kern<<<grid, 32 * WARPS, C::BYTES, st>>>(frag, dA, dD, n, m, j0, j1, partials);
+    kern<<<grid, 32 * WARPS, C::BYTES, st>>>(dA, dD, n, m, j0, j1, partials);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
 }
 
 template <int TF, bool TAIL>
-static int launch_haf(const double2* frag, const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
+static int launch_haf(const double* dA, const double* dD, int n, int m, uint64_t j0, uint64_t j1,
                       double* partials, uint64_t ngroups, int sms, int* grid_out, cudaStream_t st) {
-    const int warps = haf_pick_warps(ngroups, sms);
-    if (warps == 12) return launch_haf_w<TF, TAIL, 12>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
-    if (warps == 8) return launch_haf_w<TF, TAIL, 8>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
-    return launch_haf_w<TF, TAIL, 4>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    const int env = haf_env_warps();
+    if constexpr (TF <= 4) {      // n <= 32: the panel-split shapes exist
+        if (!env && m <= 15) {
+            if (ngroups <= (uint64_t)sms) return launch_haf_w<TF, TAIL, 3, 3>(dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+            return launch_haf_w<TF, TAIL, 12, 3>(dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+        }
+    }
+    int warps = env;
+    if (!warps) warps = ngroups <= 4ull * (uint64_t)sms ? 4 : (ngroups <= 8ull * (uint64_t)sms ? 8 : 12);
+    if (warps == 12) return launch_haf_w<TF, TAIL, 12, 1>(dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    if (warps == 8) return launch_haf_w<TF, TAIL, 8, 1>(dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
+    return launch_haf_w<TF, TAIL, 4, 1>(dA, dD, n, m, j0, j1, partials, ngroups, sms, grid_out, st);
 }
 
 constexpr int HAF_MAX_GRID = 4096;
-
-static void haf_shape(int m, int* TF, int* tail) {
-    const int r = m & 3;
-    if (m >= 5 && (r == 1 || r == 2)) { *TF = m >> 2; *tail = 1; }
-    else { *TF = (m + 3) >> 2; *tail = 0; }
-}
 
 }  // namespace wb
 
@@ -463,14 +361,11 @@ extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint
     (void)cudaGetLastError();  // drop any stale non-sticky error from earlier calls
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
-    double2* frag = reinterpret_cast<double2*>(d_workspace);
-    double* partials = reinterpret_cast<double*>(d_workspace) + (size_t)17 * 9 * 64;
-    haf_prep_kernel<<<8, 256, 0, st>>>(dA, n, m, TF, tail, frag);
-    WB_CUDA(cudaGetLastError());
+    double* partials = reinterpret_cast<double*>(d_workspace) + (size_t)17 * 9 * 64;   // (the table slot of round 1 is unused)
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
     int grid = 1;
     int rc = WB200_ENOSUP;
-#define WB_HAF_CASE(tf, tl) case (tf) * 2 + (tl): rc = launch_haf<tf, (tl) != 0>(frag, dA, dD, n, m, j0, j1, partials, ngroups, sms, &grid, st); break;
+#define WB_HAF_CASE(tf, tl) case (tf) * 2 + (tl): rc = launch_haf<tf, (tl) != 0>(dA, dD, n, m, j0, j1, partials, ngroups, sms, &grid, st); break;
     switch (TF * 2 + tail) {
         WB_HAF_CASE(1, 0) WB_HAF_CASE(2, 0) WB_HAF_CASE(3, 0) WB_HAF_CASE(4, 0)
         WB_HAF_CASE(5, 0) WB_HAF_CASE(6, 0) WB_HAF_CASE(7, 0) WB_HAF_CASE(8, 0)

@@ -460,19 +460,23 @@ static int tor_host_impl(int device, const double* O, const double* gamma, int n
         WB_POOL(pool_alloc(&dG.p, sizeof(double) * 2 * n2));
         WB_CUDA(cudaMemcpy(dG.p, gamma, sizeof(double) * 2 * n2, cudaMemcpyHostToDevice));
     }
-    cudaEvent_t e0, e1;
-    WB_CUDA(cudaEventCreate(&e0));
-    WB_CUDA(cudaEventCreate(&e1));
-    WB_CUDA(cudaEventRecord(e0, 0));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) {        // events only when the caller wants the kernel time (the end-to-end path does not)
+        WB_CUDA(cudaEventCreate(&e0));
+        WB_CUDA(cudaEventCreate(&e1));
+        WB_CUDA(cudaEventRecord(e0, 0));
+    }
     rc = tor_launch((const double*)dO.p, (const double*)dG.p, n_modes, p0, p1, (double*)dout.p, dws.p, wsb, nullptr);
-    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
-    WB_CUDA(cudaEventRecord(e1, 0));
-    WB_CUDA(cudaEventSynchronize(e1));
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (kernel_ms) *kernel_ms = ms;
+    if (rc) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return rc; }
+    if (kernel_ms) {
+        WB_CUDA(cudaEventRecord(e1, 0));
+        WB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *kernel_ms = ms;
+    }
     double o4[4];
     WB_CUDA(cudaMemcpy(o4, dout.p, 4 * sizeof(double), cudaMemcpyDeviceToHost));
     out2[0] = o4[0]; out2[1] = o4[1];
