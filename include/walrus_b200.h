@@ -61,6 +61,10 @@ int wb200_hafnian_host(int device, const double* A, const double* D, int n, uint
 int wb200_lhaf_general_host(int device, const double* A, const double* D, const double* oddV,
                             const double* oddloop, int n, const int32_t* edge_reps, int glynn,
                             uint64_t j0, uint64_t j1, double out4[4], double* kernel_ms);
+/* Device-pointer twin: dA, dD, doddV live on the current device; oddloop (2 doubles) and edge_reps are small HOST
+ * arrays (launch metadata).  Asynchronous on `stream`; scratch is stream-ordered (cudaMallocAsync). */
+int wb200_lhaf_general_dev(const double* dA, const double* dD, const double* doddV, const double* oddloop, int n,
+                           const int32_t* edge_reps, int glynn, uint64_t j0, uint64_t j1, double* d_out4, void* stream);
 /* total number of subset indices for these arguments (reference `steps`, _hafnian.py:432-435, 535-538) */
 int wb200_lhaf_general_steps(const int32_t* edge_reps, int n_edges, int glynn, int has_odd, uint64_t* steps);
 
@@ -89,6 +93,14 @@ int wb200_lhaf_matrices_host(int device, const double* A, int n_A, const int32_t
                              int n_gamma, const int32_t* gamma_index, int nv, const int32_t* rpt, int64_t B, int glynn,
                              double* out, double* kernel_ms);
 
+/* Device-pointer twin of the batched front end: every array (dA, dA_index, dgamma, dgamma_index, drpt, d_out) lives on
+ * the current device.  The launches go to `stream`; the call synchronises that stream ONCE in the middle (the per-class
+ * work totals computed by the prep kernel decide the launch shapes) and returns without waiting for the kernels.
+ * Index tables are validated on the device (WB200_EINVAL if an entry is outside its table). */
+int wb200_lhaf_matrices_dev(const double* dA, int n_A, const int32_t* dA_index, const double* dgamma, int n_gamma,
+                            const int32_t* dgamma_index, int nv, const int32_t* drpt, int64_t B, int glynn,
+                            double* d_out, void* stream);
+
 /* ---- loop_hafnian_batch sweep -------------------------------------------------------------------------
  * Replaces _calc_loop_hafnian_batch_even / _odd (thewalrus/loop_hafnian_batch.py:51-208).  Ax (n x n, n = 2E),
  * Dx: already edge-ordered by add_batch_edges_even/odd (:211-257); edge_reps = [batch_max, fixed...] (even
@@ -108,6 +120,11 @@ int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, 
                                 const int32_t* edge_reps, int odd_variant, int cutoff_extra, int glynn,
                                 uint64_t j0, uint64_t j1, double* out, int length, double* kernel_ms);
 
+/* Device-pointer twin (dAx, dDx, d_out on the current device; edge_reps on the host); asynchronous on `stream`. */
+int wb200_lhaf_batch_gamma_dev(const double* dAx, const double* dDx, int n, int n_D, const int32_t* edge_reps,
+                               int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* d_out,
+                               int length, void* stream);
+
 /* ---- montrealer ---------------------------------------------------------------------------------------
  * Replaces montrealer / lmontrealer (thewalrus/_montrealer.py:37-102) as called by mtl / lmtl (:105-135):
  * A: 2n x 2n complex (the matrix passed to mtl, NOT pre-multiplied by Xmat), zeta: 2n complex or NULL.
@@ -116,6 +133,9 @@ int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, 
  * W = sum_p (-1)^(|p|+1) conj(zeta_p) Sigma_p^(n-1) zeta_p; the caller forms (-1)^(n+1) (V / 2n + W / 2). */
 int wb200_mtl_host(int device, const double* A, const double* zeta, int n_modes, uint64_t p0, uint64_t p1,
                    double out8[8], double* kernel_ms);
+/* Device-pointer twin; asynchronous on `stream`. */
+int wb200_mtl_dev(const double* dA, const double* dzeta, int n_modes, uint64_t p0, uint64_t p1, double* d_out8,
+                  void* stream);
 
 /* ---- permanent --------------------------------------------------------------------------------------
  * Replaces perm_bbfg (thewalrus/_permanent.py:130-168; method 0, steps k in [0, 2^(n-1)), final scale
@@ -142,6 +162,9 @@ int wb200_perm_int64_host(int device, const int64_t* M, int n, int method, uint6
  * perm_bbfg (:167), which the caller applies.  m <= 40, n <= 32. */
 int wb200_brs_host(int device, const double* A, const double* E, int m, int n, uint64_t j0, uint64_t j1,
                    double out4[4], double* kernel_ms);
+/* Device-pointer twin; asynchronous on `stream`. */
+int wb200_brs_dev(const double* dA, const double* dE, int m, int n, uint64_t j0, uint64_t j1, double* d_out4,
+                  void* stream);
 
 /* ---- torontonian ------------------------------------------------------------------------------------
  * Replaces rec_torontonian / numba_tor (thewalrus/_torontonian.py:123-154, 189-247):

@@ -1,0 +1,139 @@
+"""Device-pointer / stream entry points (`*_dev`) of the general, batched, montrealer and Bristolian kernel families
+(VERDICT r01 missing 4): device buffers owned by torch, a NON-default stream, results compared with the `*_host` twins
+(bit-identical: same kernels, same launch shapes) and with the oracle."""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(a, dev):
+    import torch
+
+    a = np.ascontiguousarray(a)
+    if np.iscomplexobj(a):
+        a = a.view(np.float64)
+    return torch.from_numpy(a.reshape(-1).copy()).to(dev)
+
+
+@pytest.fixture()
+def ctx():
+    import torch
+
+    from thewalrus_b200 import _lib
+
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(dev)
+    return torch, _lib.load(), _lib, dev, st
+
+
+def test_lhaf_matrices_dev_matches_host_and_oracle(ctx):
+    torch, lib, _lib, dev, st = ctx
+    from oracle import c_oracle as co
+    from thewalrus_b200 import _engine
+
+    rng = np.random.default_rng(5)
+    nv, B = 10, 700
+    G = rng.standard_normal((nv, nv)) + 1j * rng.standard_normal((nv, nv))
+    A = (G + G.T) / 4
+    gam = (rng.standard_normal((3, nv)) + 1j * rng.standard_normal((3, nv))) / 3
+    rpt = rng.integers(0, 3, (B, nv)).astype(np.int32)
+    gi = rng.integers(0, 3, B).astype(np.int32)
+    want = _engine.lhaf_patterns_local(A, gam, rpt, True, dev, gamma_index=gi)
+    with torch.cuda.stream(st):
+        dA, dG, dR, dI = _dev(A, dev), _dev(gam, dev), torch.from_numpy(rpt.reshape(-1)).to(dev), torch.from_numpy(gi).to(dev)
+        out = torch.zeros(2 * B, dtype=torch.float64, device=dev)
+        rc = lib.wb200_lhaf_matrices_dev(dA.data_ptr(), 1, None, dG.data_ptr(), 3, dI.data_ptr(), nv, dR.data_ptr(), B, 1,
+                                         out.data_ptr(), st.cuda_stream)
+        _lib.check(rc, "wb200_lhaf_matrices_dev")
+    st.synchronize()
+    got = out.cpu().numpy().view(np.complex128)
+    assert np.array_equal(got, want)
+    ref = np.array([co.lhaf_patterns(A, gam[g], r[None, :])[0] for g, r in zip(gi[:60], rpt[:60])])
+    assert np.max(np.abs(got[:60] - ref) / np.maximum(np.abs(ref), 1e-9)) < 1e-10
+    # an index outside its table is reported, not dereferenced
+    bad = gi.copy()
+    bad[17] = 3
+    dB = torch.from_numpy(bad).to(dev)
+    rc = lib.wb200_lhaf_matrices_dev(dA.data_ptr(), 1, None, dG.data_ptr(), 3, dB.data_ptr(), nv, dR.data_ptr(), B, 1,
+                                     out.data_ptr(), st.cuda_stream)
+    assert rc == -1
+
+
+def test_lhaf_general_dev_matches_host(ctx):
+    torch, lib, _lib, dev, st = ctx
+    from thewalrus_b200 import _engine
+
+    rng = np.random.default_rng(6)
+    E = 5
+    n = 2 * E
+    G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = (G + G.T) / 3
+    D = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    V = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    er = np.array([2, 1, 3, 1, 2], dtype=np.int32)
+    for odd in (False, True):
+        steps = ctypes.c_uint64(0)
+        lib.wb200_lhaf_general_steps(er.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), E, 1, int(odd), ctypes.byref(steps))
+        want = _engine.lhaf_general_range(A, D, V if odd else None, 0.3 - 0.2j if odd else None, er, True, 0, steps.value, dev)
+        ol = np.array([0.3, -0.2])
+        with torch.cuda.stream(st):
+            dA, dD, dV = _dev(A, dev), _dev(D, dev), _dev(V, dev)
+            out = torch.zeros(4, dtype=torch.float64, device=dev)
+            rc = lib.wb200_lhaf_general_dev(dA.data_ptr(), dD.data_ptr(), dV.data_ptr() if odd else None,
+                                            ol.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if odd else None, n,
+                                            er.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), 1, 0, steps.value,
+                                            out.data_ptr(), st.cuda_stream)
+            _lib.check(rc, "wb200_lhaf_general_dev")
+        st.synchronize()
+        assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_batch_gamma_mtl_brs_dev_match_host(ctx):
+    torch, lib, _lib, dev, st = ctx
+    from thewalrus_b200 import _engine
+
+    rng = np.random.default_rng(7)
+    # loop_hafnian_batch_gamma sweep
+    E = 4
+    n = 2 * E
+    G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    A = (G + G.T) / 3
+    Dk = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))) / 2
+    er = np.array([2, 1, 2, 1], dtype=np.int32)
+    steps = int(np.prod(er + 1))
+    length = 2 * 2 + 1 + 1
+    want = _engine.lhaf_batch_gamma_range(A, Dk, er, 0, 1, True, 0, steps, length, dev)
+    with torch.cuda.stream(st):
+        dA, dD = _dev(A, dev), _dev(Dk, dev)
+        out = torch.zeros(4 * length * 3, dtype=torch.float64, device=dev)
+        rc = lib.wb200_lhaf_batch_gamma_dev(dA.data_ptr(), dD.data_ptr(), n, 3, er.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                            0, 1, 1, 0, steps, out.data_ptr(), length, st.cuda_stream)
+        _lib.check(rc, "wb200_lhaf_batch_gamma_dev")
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    # montrealer
+    nm = 6
+    G = rng.standard_normal((2 * nm, 2 * nm)) + 1j * rng.standard_normal((2 * nm, 2 * nm))
+    A = (G + G.T) / 5
+    z = rng.standard_normal(2 * nm) + 1j * rng.standard_normal(2 * nm)
+    want = _engine.mtl_range(A, z, 0, 1 << nm, dev)
+    with torch.cuda.stream(st):
+        dA, dz = _dev(A, dev), _dev(z, dev)
+        out = torch.zeros(8, dtype=torch.float64, device=dev)
+        _lib.check(lib.wb200_mtl_dev(dA.data_ptr(), dz.data_ptr(), nm, 0, 1 << nm, out.data_ptr(), st.cuda_stream), "wb200_mtl_dev")
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    # Bristolian
+    m, nn = 5, 6
+    Ab = (rng.standard_normal((m, nn)) + 1j * rng.standard_normal((m, nn))) / 3
+    Eb = (rng.standard_normal((nn, nn)) + 1j * rng.standard_normal((nn, nn))) / 3
+    want = _engine.brs_range(Ab, Eb, 0, 1 << m, dev)
+    with torch.cuda.stream(st):
+        dA, dE = _dev(Ab, dev), _dev(Eb, dev)
+        out = torch.zeros(4, dtype=torch.float64, device=dev)
+        _lib.check(lib.wb200_brs_dev(dA.data_ptr(), dE.data_ptr(), m, nn, 0, 1 << m, out.data_ptr(), st.cuda_stream), "wb200_brs_dev")
+    st.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)

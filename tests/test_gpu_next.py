@@ -147,7 +147,8 @@ def test_ltor_vs_reference_outputs(golden_next):
         got = wb.ltor(O, gamma)
         assert isinstance(got, np.complex128)
         assert relv(got, dec(c["direct"])) < TOL, len(gamma)
-        assert relv(got, dec(c["rec"])) < 1e-9, len(gamma)   # the reference's two variants differ by ~1e-11
+        # yardstick for the second variant: the gap between the reference's own two variants (rec vs direct)
+        assert relv(got, dec(c["rec"])) < TOL + relv(dec(c["rec"]), dec(c["direct"])), len(gamma)
 
 
 def test_ltor_vs_oracle_and_ranges():
@@ -194,7 +195,7 @@ def test_threshold_probabilities_sum_to_one():
     cov = S @ S.T / (2 * M) + np.identity(2 * M)
     mu = 0.4 * rng.standard_normal(2 * M)
     tot = sum(wb.threshold_detection_prob(mu, cov, np.array(d)) for d in product([0, 1], repeat=M))
-    assert abs(tot - 1.0) < 1e-9
+    assert abs(tot - 1.0) < TOL
 
 
 # ------------------------------------------------------------------------------ batched-matrix front end

@@ -73,8 +73,8 @@ def test_tor_vs_reference_outputs(golden):
         O = dec(c["O"])
         O = O.real if c["kind"] == "real" else O
         tol = TOL
-        if c["direct"] is not None:
-            tol += 10 * rel(dec(c["rec"]), dec(c["direct"]))
+        if c["direct"] is not None:      # yardstick: the gap between the reference's own two variants (rec vs direct)
+            tol += rel(dec(c["rec"]), dec(c["direct"]))
         got = wb.tor(O)
         assert rel(got, dec(c["rec"])) < tol, c["N"]
         assert rel(wb.tor(O, recursive=False), dec(c["rec"])) < tol
@@ -180,7 +180,12 @@ def test_perm_vs_long_double_oracle(n):
     exact = co.perm(U, "bbfg", long_double=True)
     assert rel(wb.perm(U), exact) < TOL
     if n <= 20:
-        assert rel(wb.perm(U, "ryser"), exact) < 1e-9
+        # Ryser in plain FP64 is itself not 1e-10 accurate on Haar blocks: the yardstick is the error of the
+        # reference algorithm's own FP64 evaluation (the C port of perm_ryser) against the 80-bit value
+        port_err = rel(co.perm(U, "ryser"), exact)
+        err = rel(wb.perm(U, "ryser"), exact)
+        print(f"\n[ryser n={n}] gpu rel_err {err:.2e}, reference-algorithm FP64 port {port_err:.2e}")
+        assert err < TOL + port_err
     R = rng.standard_normal((n, n))
     assert rel(wb.perm(R), co.perm(R, "bbfg", long_double=True).real) < TOL
 
@@ -272,11 +277,12 @@ def test_full_size_properties_n40():
     A = random_symmetric(rng, n) / np.sqrt(n)
     h = wb.hafnian(A)
     c = 0.9 - 0.3j
-    assert rel(wb.hafnian(c * A), c ** (n // 2) * h) < 1e-9
+    assert rel(wb.hafnian(c * A), c ** (n // 2) * h) < TOL
     k = 16
     B = (rng.standard_normal((k, k)) + 1j * rng.standard_normal((k, k))) / np.sqrt(k)
     Z = np.zeros((k, k))
-    assert rel(wb.hafnian(np.block([[Z, B], [B.T, Z]])), wb.perm(B)) < 1e-9
+    assert rel(wb.hafnian(np.block([[Z, B], [B.T, Z]])), co.perm(B, "bbfg", long_double=True)) < TOL
+    assert rel(wb.perm(B), co.perm(B, "bbfg", long_double=True)) < TOL
 
 
 def test_perm_properties_n30():
@@ -362,12 +368,12 @@ def test_gbs_probabilities_vs_reference_outputs(golden):
     d = golden["dme"]
     mu, cov, pats = np.array(d["mu"]), np.array(d["cov"]), np.array(d["patterns"])
     p = wb.probabilities_batch(mu, cov, pats)
-    assert np.max(np.abs(p - np.array(d["displaced"])) / np.maximum(np.array(d["displaced"]), 1e-30)) < 1e-9
+    assert np.max(np.abs(p - np.array(d["displaced"])) / np.maximum(np.array(d["displaced"]), 1e-30)) < TOL
     p0 = wb.probabilities_batch(0 * mu, cov, pats)
     want0 = np.array(d["zero_mean"])
-    assert np.max(np.abs(p0 - want0)) < 1e-12 + 1e-9 * np.max(want0)
+    assert np.max(np.abs(p0 - want0)) < TOL * np.max(want0)
     one = wb.density_matrix_element(mu, cov, list(pats[3]), list(pats[3]))
-    assert rel(one.real, d["displaced"][3]) < 1e-9
+    assert rel(one.real, d["displaced"][3]) < TOL
 
 
 def test_gbs_probabilities_16_modes_sample_and_normalisation():
@@ -384,13 +390,13 @@ def test_gbs_probabilities_16_modes_sample_and_normalisation():
     for b in idx:
         r = [int(x) for x in rpt[b]]
         want = wb.hafnian_repeated(A, r, mu=gamma, loop=True)
-        assert abs(got[b] - want) <= 1e-9 * max(abs(want), 1e-300), (b, pats[b])
+        assert abs(got[b] - want) <= TOL * max(abs(want), 1e-300), (b, pats[b])
         if sum(r) <= 8:
-            assert abs(got[b] - wo.loop_hafnian(A, gamma, r)) <= 1e-9 * max(abs(want), 1e-300)
+            assert abs(got[b] - wo.loop_hafnian(A, gamma, r)) <= TOL * max(abs(want), 1e-300)
     # normalisation on a small lossy displaced state: probabilities over a generous cutoff sum to ~1
     mu2, cov2, _ = sys_path_bench.make_gbs_state(2, 1, seed=7, r=0.4)
     P = wb.probabilities(mu2, cov2, 14)
-    assert abs(P.sum() - 1.0) < 1e-6 and P.min() >= 0.0
+    assert abs(P.sum() - 1.0) < 1e-6 and P.min() >= 0.0     # truncation of the Fock space at 14 photons per mode, not rounding
 
 
 def test_gbs_probabilities_config3_state_vs_reference_outputs(golden):
@@ -405,7 +411,7 @@ def test_gbs_probabilities_config3_state_vs_reference_outputs(golden):
     assert sel.tolist() == d["patterns"]
     p = wb.probabilities_batch(mu, cov, pats)[d["index"]]
     want = np.array(d["displaced"])
-    assert np.max(np.abs(p - want) / want) < 1e-9
+    assert np.max(np.abs(p - want) / want) < TOL
     p0 = wb.probabilities_batch(0 * mu, cov, sel)
     want0 = np.array(d["zero_mean"])
-    assert np.max(np.abs(p0 - want0)) < 1e-9 * np.max(want0) + 1e-18
+    assert np.max(np.abs(p0 - want0)) < TOL * np.max(want0)

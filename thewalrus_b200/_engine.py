@@ -55,6 +55,9 @@ def _to_dev(arr_c128, dev):
 def combine4(parts):
     """Fixed-order double-double sum of (re_hi, re_lo, im_hi, im_lo) partials -> complex."""
     parts = np.asarray(parts, dtype=np.float64).reshape(-1, 4)
+    if len(parts) == 1:     # single process: nothing to combine
+        p = parts[0]
+        return complex(p[0] + p[1], p[2] + p[3])
     re, re_lo = dd_sum([(p[0], p[1]) for p in parts])
     im, im_lo = dd_sum([(p[2], p[3]) for p in parts])
     return complex(re + re_lo, im + im_lo)

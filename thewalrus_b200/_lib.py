@@ -34,6 +34,14 @@ SIGNATURES = {
     "wb200_lhaf_general_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p,
                                                ctypes.c_int, _c_int32_p, ctypes.c_int, _u64, _u64, _c_double_p,
                                                _c_double_p]),
+    "wb200_lhaf_general_dev": (ctypes.c_int, [_vp, _vp, _vp, _c_double_p, ctypes.c_int, _c_int32_p, ctypes.c_int, _u64, _u64,
+                                              _vp, _vp]),
+    "wb200_lhaf_matrices_dev": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, _vp,
+                                               ctypes.c_int64, ctypes.c_int, _vp, _vp]),
+    "wb200_lhaf_batch_gamma_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, _u64, _u64, _vp, ctypes.c_int, _vp]),
+    "wb200_mtl_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _u64, _u64, _vp, _vp]),
+    "wb200_brs_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, ctypes.c_int, _u64, _u64, _vp, _vp]),
     "wb200_lhaf_patterns_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _c_int32_p,
                                                 ctypes.c_int64, ctypes.c_int, _c_double_p, _c_double_p]),
     "wb200_lhaf_patterns_multi_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _c_int32_p,

@@ -300,10 +300,12 @@ constexpr int PAT_NCLS = 8;      // 7 DMMA tile classes + the fallback class (==
 __host__ __device__ inline int pat_class_of(int E, int N, int odd);
 
 __global__ void pat_prep_kernel(const int32_t* __restrict__ rpt, long long B, int nv, int loops, int glynn, int force_fallback,
+                                const int32_t* __restrict__ aidx, int n_A, const int32_t* __restrict__ gidx, int n_gamma,
                                 PatDesc* __restrict__ desc, unsigned int* __restrict__ nchunks,
                                 unsigned char* __restrict__ cls_out, PatMeta* meta) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
+    if ((aidx && (aidx[p] < 0 || aidx[p] >= n_A)) || (gidx && loops && (gidx[p] < 0 || gidx[p] >= n_gamma))) atomicExch(&meta->err, 3);
     int cnt[BW_NVMAX];
     int N = 0, npool = 0;
     bool bad = false;
@@ -699,35 +701,39 @@ static int bw_pick_warps(size_t per_warp, int* ctas) {
 // caller's stream.  Scratch comes from the caching pool.  ONE host synchronisation in the middle (the class totals and
 // shared-memory maxima decide the launch shapes) and one at the end (the scratch is released on return).
 // env WB200_PAT_DFMA=1 forces every pattern onto the warp-per-subset DFMA kernel (A/B measurements, tests).
-static int lhaf_matrices_device(const double2* dA, const int32_t* dai, const double2* dD, const int32_t* dgi, int nv,
-                                const int32_t* drpt, int64_t B, int glynn, double2* dout, int sms, cudaStream_t st,
+static int lhaf_matrices_device(const double2* dA, int n_A, const int32_t* dai, const double2* dD, int n_gamma, const int32_t* dgi,
+                                int nv, const int32_t* drpt, int64_t B, int glynn, double2* dout, int sms, cudaStream_t st,
                                 double* kernel_ms) {
     const char* env_dfma = getenv("WB200_PAT_DFMA");      // read per call: the tests toggle it
     const int force_fallback = (env_dfma && atoi(env_dfma)) ? 1 : 0;
-    DevBufB ddesc, dnch, dcls, dcoff, dmeta, dcounter, dpartial;
-    WB_POOL(pool_alloc(&ddesc.p, sizeof(PatDesc) * (size_t)B));
-    WB_POOL(pool_alloc(&dnch.p, sizeof(unsigned int) * (size_t)B));
-    WB_POOL(pool_alloc(&dcls.p, (size_t)B));
-    WB_POOL(pool_alloc(&dcoff.p, sizeof(unsigned long long) * ((size_t)B + 1) * PAT_NCLS));
+    StreamBuf ddesc, dnch, dcls, dcoff, dmeta, dpartial;
+    WB_POOL(ddesc.alloc(sizeof(PatDesc) * (size_t)B, st));
+    WB_POOL(dnch.alloc(sizeof(unsigned int) * (size_t)B, st));
+    WB_POOL(dcls.alloc((size_t)B, st));
+    WB_POOL(dcoff.alloc(sizeof(unsigned long long) * ((size_t)B + 1) * PAT_NCLS, st));
     // meta block: PatMeta | totals[PAT_NCLS] | counters[PAT_NCLS]
     const size_t meta_bytes = 64 + 2 * sizeof(unsigned long long) * PAT_NCLS;
-    WB_POOL(pool_alloc(&dmeta.p, meta_bytes));
+    WB_POOL(dmeta.alloc(meta_bytes, st));
     WB_CUDA(cudaMemsetAsync(dmeta.p, 0, meta_bytes, st));
     PatMeta* d_meta = (PatMeta*)dmeta.p;
     unsigned long long* d_totals = (unsigned long long*)((char*)dmeta.p + 64);
     unsigned long long* d_counters = d_totals + PAT_NCLS;
     EvPair ev;
-    WB_CUDA(cudaEventCreate(&ev.e0));
-    WB_CUDA(cudaEventCreate(&ev.e1));
-    WB_CUDA(cudaEventRecord(ev.e0, st));
-    pat_prep_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(drpt, B, nv, dD != nullptr, glynn, force_fallback, (PatDesc*)ddesc.p,
-                                                                 (unsigned int*)dnch.p, (unsigned char*)dcls.p, d_meta);
+    if (kernel_ms) {
+        WB_CUDA(cudaEventCreate(&ev.e0));
+        WB_CUDA(cudaEventCreate(&ev.e1));
+        WB_CUDA(cudaEventRecord(ev.e0, st));
+    }
+    pat_prep_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(drpt, B, nv, dD != nullptr, glynn, force_fallback, dai, n_A, dgi,
+                                                                 n_gamma, (PatDesc*)ddesc.p, (unsigned int*)dnch.p,
+                                                                 (unsigned char*)dcls.p, d_meta);
     scan_kernel<<<PAT_NCLS, 1024, 0, st>>>((const unsigned int*)dnch.p, (const unsigned char*)dcls.p, B,
                                            (unsigned long long*)dcoff.p, d_totals);
     WB_CUDA(cudaGetLastError());
     struct { PatMeta meta; char pad[64 - sizeof(PatMeta)]; unsigned long long totals[PAT_NCLS]; } h;
     WB_CUDA(cudaMemcpyAsync(&h, dmeta.p, 64 + sizeof(unsigned long long) * PAT_NCLS, cudaMemcpyDeviceToHost, st));
     WB_CUDA(cudaStreamSynchronize(st));
+    if (h.meta.err == 3) { set_error("lhaf_patterns: A_index / gamma_index entry outside the table"); return WB200_EINVAL; }
     if (h.meta.err) {
         set_error(h.meta.err == 1 ? "lhaf_patterns: repetition counts must be in [0, 65535] with total <= 32000"
                                   : "lhaf_patterns: a pattern exceeds the kernel limits (edges <= %d, series order <= %d, steps <= 1e12) or has an odd total without loops", BW_EMAX, BW_MAX_ORDER);
@@ -737,7 +743,7 @@ static int lhaf_matrices_device(const double2* dA, const int32_t* dai, const dou
     unsigned long long nchunks = 0;
     for (int c = 0; c < PAT_NCLS; ++c) { cb.base[c] = nchunks; nchunks += h.totals[c]; }
     if (nchunks > 0) {
-        WB_POOL(pool_alloc(&dpartial.p, sizeof(double) * 4 * (size_t)nchunks));
+        WB_POOL(dpartial.alloc(sizeof(double) * 4 * (size_t)nchunks, st));
         // largest classes first: the small ones fill the tail of the big ones' last wave
         for (int c = PAT_NCLS - 1; c >= 0; --c) {
             if (!h.totals[c]) continue;
@@ -767,13 +773,15 @@ static int lhaf_matrices_device(const double2* dA, const int32_t* dai, const dou
     }
     pat_final_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const PatDesc*)ddesc.p, (const unsigned long long*)dcoff.p, cb,
                                                                   (const double*)dpartial.p, dD, dgi, nv, glynn, B, dout);
-    WB_CUDA(cudaEventRecord(ev.e1, st));
-    WB_CUDA(cudaEventSynchronize(ev.e1));
     WB_CUDA(cudaGetLastError());
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
-    if (kernel_ms) *kernel_ms = ms;
-    return WB200_OK;
+    if (kernel_ms) {
+        WB_CUDA(cudaEventRecord(ev.e1, st));
+        WB_CUDA(cudaEventSynchronize(ev.e1));
+        float ms = 0;
+        WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
+        *kernel_ms = ms;
+    }
+    return WB200_OK;       // the stream-ordered scratch is released when the stream reaches this point
 }
 
 }  // namespace wb
@@ -791,26 +799,46 @@ extern "C" int wb200_lhaf_patterns_multi_host(int device, const double* A, const
     return wb200_lhaf_matrices_host(device, A, 1, nullptr, gamma, n_gamma, gamma_index, nv, rpt, B, glynn, out, kernel_ms);
 }
 
+static int pat_check_args(const void* A, int n_A, const void* A_index, const void* gamma, int n_gamma, const void* gamma_index,
+                          int nv, const void* rpt, int64_t B, const void* out) {
+    if (!A || !rpt || !out) { set_error("lhaf_patterns: null pointer"); return WB200_EINVAL; }
+    if (n_A < 1 || (n_A > 1 && !A_index)) { set_error("lhaf_patterns: n_A must be >= 1 and A_index given for n_A > 1"); return WB200_EINVAL; }
+    if (gamma && n_gamma < 1) { set_error("lhaf_patterns: n_gamma must be >= 1 when gamma is given"); return WB200_EINVAL; }
+    if (gamma && n_gamma > 1 && !gamma_index) { set_error("lhaf_patterns: gamma_index is required for n_gamma > 1"); return WB200_EINVAL; }
+    if (nv < 1 || nv > BW_NVMAX) { set_error("lhaf_patterns: %d vertices outside [1, %d]", nv, BW_NVMAX); return nv > BW_NVMAX ? WB200_ENOSUP : WB200_EINVAL; }
+    if (B < 0) { set_error("lhaf_patterns: negative batch"); return WB200_EINVAL; }
+    return WB200_OK;
+}
+
+extern "C" int wb200_lhaf_matrices_dev(const double* dA, int n_A, const int32_t* dA_index, const double* dgamma, int n_gamma,
+                                       const int32_t* dgamma_index, int nv, const int32_t* drpt, int64_t B, int glynn,
+                                       double* d_out, void* stream) {
+    int rc = pat_check_args(dA, n_A, dA_index, dgamma, n_gamma, dgamma_index, nv, drpt, B, d_out);
+    if (rc || B == 0) return rc;
+    int device = 0, sms = 0;
+    (void)cudaGetLastError();
+    WB_CUDA(cudaGetDevice(&device));
+    if (device_sm_count(device, &sms)) return WB200_ECUDA;
+    return lhaf_matrices_device((const double2*)dA, n_A, dA_index, (const double2*)dgamma, n_gamma, dgamma ? dgamma_index : nullptr, nv,
+                                drpt, B, glynn, (double2*)d_out, sms, (cudaStream_t)stream, nullptr);
+}
+
 extern "C" int wb200_lhaf_matrices_host(int device, const double* A, int n_A, const int32_t* A_index,
                                         const double* gamma, int n_gamma, const int32_t* gamma_index, int nv,
                                         const int32_t* rpt, int64_t B, int glynn, double* out, double* kernel_ms) {
-    if (!A || !rpt || !out) { set_error("lhaf_patterns: null pointer"); return WB200_EINVAL; }
-    if (n_A < 1 || (n_A > 1 && !A_index)) { set_error("lhaf_patterns: n_A must be >= 1 and A_index given for n_A > 1"); return WB200_EINVAL; }
-    if (A_index)
+    int rc = pat_check_args(A, n_A, A_index, gamma, n_gamma, gamma_index, nv, rpt, B, out);
+    if (rc) return rc;
+    if (A_index)      // host tables are checked before any CUDA call (the device twin checks them in its prep kernel)
         for (int64_t i = 0; i < B; ++i)
             if (A_index[i] < 0 || A_index[i] >= n_A) { set_error("lhaf_patterns: A_index[%lld] = %d outside [0, %d)", (long long)i, A_index[i], n_A); return WB200_EINVAL; }
-    if (gamma && n_gamma < 1) { set_error("lhaf_patterns: n_gamma must be >= 1 when gamma is given"); return WB200_EINVAL; }
-    if (gamma && n_gamma > 1 && !gamma_index) { set_error("lhaf_patterns: gamma_index is required for n_gamma > 1"); return WB200_EINVAL; }
     if (gamma && gamma_index)
         for (int64_t i = 0; i < B; ++i)
             if (gamma_index[i] < 0 || gamma_index[i] >= n_gamma) { set_error("lhaf_patterns: gamma_index[%lld] = %d outside [0, %d)", (long long)i, gamma_index[i], n_gamma); return WB200_EINVAL; }
-    if (nv < 1 || nv > BW_NVMAX) { set_error("lhaf_patterns: %d vertices outside [1, %d]", nv, BW_NVMAX); return nv > BW_NVMAX ? WB200_ENOSUP : WB200_EINVAL; }
-    if (B < 0) { set_error("lhaf_patterns: negative batch"); return WB200_EINVAL; }
     if (B == 0) { if (kernel_ms) *kernel_ms = 0.0; return WB200_OK; }
     WB_CUDA(cudaSetDevice(device));
     int sms = 0;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    DevBufB dA, dai, dD, dgi, drpt, ddesc, dnch, dcls, dcoff, dmeta, dtotals, dcounter, dpartial, dout;
+    DevBufB dA, dai, dD, dgi, drpt, dout;
     WB_POOL(pool_alloc(&dA.p, sizeof(double2) * (size_t)n_A * nv * nv));
     WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * (size_t)n_A * nv * nv, cudaMemcpyHostToDevice));
     if (A_index) {
@@ -828,8 +856,8 @@ extern "C" int wb200_lhaf_matrices_host(int device, const double* A, int n_A, co
     WB_POOL(pool_alloc(&drpt.p, sizeof(int32_t) * (size_t)B * nv));
     WB_CUDA(cudaMemcpy(drpt.p, rpt, sizeof(int32_t) * (size_t)B * nv, cudaMemcpyHostToDevice));
     WB_POOL(pool_alloc(&dout.p, sizeof(double2) * (size_t)B));
-    int rc = lhaf_matrices_device((const double2*)dA.p, (const int32_t*)dai.p, (const double2*)dD.p, (const int32_t*)dgi.p, nv,
-                                  (const int32_t*)drpt.p, B, glynn, (double2*)dout.p, sms, (cudaStream_t)0, kernel_ms);
+    rc = lhaf_matrices_device((const double2*)dA.p, n_A, (const int32_t*)dai.p, (const double2*)dD.p, n_gamma, (const int32_t*)dgi.p, nv,
+                              (const int32_t*)drpt.p, B, glynn, (double2*)dout.p, sms, (cudaStream_t)0, kernel_ms);
     if (rc) return rc;
     WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double2) * (size_t)B, cudaMemcpyDeviceToHost));
     return WB200_OK;
@@ -847,10 +875,10 @@ extern "C" int wb200_lhaf_batch_steps(const int32_t* edge_reps, int n_edges, uin
     return WB200_OK;
 }
 
-extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, int n, int n_D,
-                                           const int32_t* edge_reps, int odd_variant, int cutoff_extra, int glynn,
-                                           uint64_t j0, uint64_t j1, double* out, int length, double* kernel_ms) {
-    if (!Ax || !Dx || !edge_reps || !out) { set_error("lhaf_batch: null pointer"); return WB200_EINVAL; }
+extern "C" int wb200_lhaf_batch_gamma_dev(const double* dAx, const double* dDx, int n, int n_D, const int32_t* edge_reps,
+                                          int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* d_out,
+                                          int length, void* stream) {
+    if (!dAx || !dDx || !edge_reps || !d_out) { set_error("lhaf_batch: null pointer"); return WB200_EINVAL; }
     if (n < 2 || (n & 1)) { set_error("lhaf_batch: n must be even and >= 2 (got %d)", n); return WB200_EINVAL; }
     if (n_D < 1 || n_D > 65536) { set_error("lhaf_batch: number of loop vectors %d outside [1, 65536]", n_D); return WB200_EINVAL; }
     const int E = n / 2;
@@ -878,15 +906,12 @@ extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const d
     if (p.N_max > BW_MAX_ORDER) { set_error("lhaf_batch: photon number %d too large", p.N_max); return WB200_ENOSUP; }
     p.n = n; p.n_D = n_D; p.E = E; p.glynn = glynn; p.odd_variant = odd_variant; p.j0 = j0; p.j1 = j1;
     p.smax = n; p.T = p.N_max / 2; p.O = p.N_max;
-    WB_CUDA(cudaSetDevice(device));
-    int sms = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0, sms = 0;
+    (void)cudaGetLastError();
+    WB_CUDA(cudaGetDevice(&device));
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    DevBufB dA, dD, dpart, dout;
-    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * n * n));
-    WB_CUDA(cudaMemcpy(dA.p, Ax, sizeof(double2) * n * n, cudaMemcpyHostToDevice));
-    WB_POOL(pool_alloc(&dD.p, sizeof(double2) * (size_t)n * n_D));
-    WB_CUDA(cudaMemcpy(dD.p, Dx, sizeof(double2) * (size_t)n * n_D, cudaMemcpyHostToDevice));
-    p.A = (const double2*)dA.p; p.D = (const double2*)dD.p;
+    p.A = (const double2*)dAx; p.D = (const double2*)dDx;
     const size_t per_warp = warp_ws_bytes(p.smax, p.T, p.O);
     int ctas = 1;
     const int wpc = bw_pick_warps(per_warp, &ctas);
@@ -899,22 +924,60 @@ extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const d
     const size_t rows = (size_t)p.length * n_D;                 // independent outputs
     while (grid > 1 && rows * (size_t)grid * wpc * 32 > ((size_t)1 << 31)) grid /= 2;   // bound the partial table (2 GiB)
     const int nwarps = grid * wpc;
-    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 4 * rows * nwarps));
-    WB_CUDA(cudaMemset(dpart.p, 0, sizeof(double) * 4 * rows * nwarps));
-    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4 * rows));
+    StreamBuf dpart;
+    WB_POOL(dpart.alloc(sizeof(double) * 4 * rows * nwarps, st));
+    WB_CUDA(cudaMemsetAsync(dpart.p, 0, sizeof(double) * 4 * rows * nwarps, st));
     p.partials = (double*)dpart.p;
-    EvPair ev;
-    WB_CUDA(cudaEventCreate(&ev.e0));
-    WB_CUDA(cudaEventCreate(&ev.e1));
-    WB_CUDA(cudaEventRecord(ev.e0, 0));
-    batch_kernel<<<grid, 32 * wpc, shm>>>(p);
-    batch_final_kernel<<<(unsigned)((rows + 63) / 64), 64>>>((const double*)dpart.p, nwarps, (int)rows, (double*)dout.p);
-    WB_CUDA(cudaEventRecord(ev.e1, 0));
-    WB_CUDA(cudaEventSynchronize(ev.e1));
+    batch_kernel<<<grid, 32 * wpc, shm, st>>>(p);
+    batch_final_kernel<<<(unsigned)((rows + 63) / 64), 64, 0, st>>>((const double*)dpart.p, nwarps, (int)rows, d_out);
     WB_CUDA(cudaGetLastError());
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
-    if (kernel_ms) *kernel_ms = ms;
+    return WB200_OK;
+}
+
+namespace {
+struct HostTimer {       // CUDA events around a *_dev call on the legacy stream, only when the caller asks for the time
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~HostTimer() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    int start(bool want) {
+        if (!want) return WB200_OK;
+        WB_CUDA(cudaEventCreate(&e0)); WB_CUDA(cudaEventCreate(&e1)); WB_CUDA(cudaEventRecord(e0, 0));
+        return WB200_OK;
+    }
+    int stop(double* ms) {
+        if (!e0) return WB200_OK;
+        WB_CUDA(cudaEventRecord(e1, 0));
+        WB_CUDA(cudaEventSynchronize(e1));
+        float f = 0;
+        WB_CUDA(cudaEventElapsedTime(&f, e0, e1));
+        if (ms) *ms = f;
+        return WB200_OK;
+    }
+};
+}  // namespace
+
+extern "C" int wb200_lhaf_batch_gamma_host(int device, const double* Ax, const double* Dx, int n, int n_D,
+                                           const int32_t* edge_reps, int odd_variant, int cutoff_extra, int glynn,
+                                           uint64_t j0, uint64_t j1, double* out, int length, double* kernel_ms) {
+    if (!Ax || !Dx || !edge_reps || !out) { set_error("lhaf_batch: null pointer"); return WB200_EINVAL; }
+    if (n < 2 || (n & 1) || n > 2 * BW_EMAX || n_D < 1 || n_D > 65536 || length < 1) {
+        set_error("lhaf_batch: bad sizes (n = %d, n_D = %d, length = %d)", n, n_D, length);
+        return n > 2 * BW_EMAX ? WB200_ENOSUP : WB200_EINVAL;
+    }
+    WB_CUDA(cudaSetDevice(device));
+    DevBufB dA, dD, dout;
+    const size_t rows = (size_t)length * n_D;
+    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * n * n));
+    WB_CUDA(cudaMemcpy(dA.p, Ax, sizeof(double2) * n * n, cudaMemcpyHostToDevice));
+    WB_POOL(pool_alloc(&dD.p, sizeof(double2) * (size_t)n * n_D));
+    WB_CUDA(cudaMemcpy(dD.p, Dx, sizeof(double2) * (size_t)n * n_D, cudaMemcpyHostToDevice));
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4 * rows));
+    HostTimer tm;
+    int rc = tm.start(kernel_ms != nullptr);
+    if (rc) return rc;
+    rc = wb200_lhaf_batch_gamma_dev((const double*)dA.p, (const double*)dD.p, n, n_D, edge_reps, odd_variant, cutoff_extra, glynn,
+                                    j0, j1, (double*)dout.p, length, nullptr);
+    if (rc) return rc;
+    if ((rc = tm.stop(kernel_ms))) return rc;
     WB_CUDA(cudaMemcpy(out, dout.p, sizeof(double) * 4 * rows, cudaMemcpyDeviceToHost));
     return WB200_OK;
 }
@@ -926,9 +989,14 @@ extern "C" int wb200_lhaf_batch_host(int device, const double* Ax, const double*
                                        length, kernel_ms);
 }
 
-extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, int n_modes, uint64_t p0, uint64_t p1,
-                              double out8[8], double* kernel_ms) {
-    if (!A || !out8) { set_error("mtl: null pointer"); return WB200_EINVAL; }
+__global__ void conj_kernel(const double2* __restrict__ in, int n, double2* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_double2(in[i].x, -in[i].y);
+}
+
+extern "C" int wb200_mtl_dev(const double* dA, const double* dzeta, int n_modes, uint64_t p0, uint64_t p1, double* d_out8,
+                             void* stream) {
+    if (!dA || !d_out8) { set_error("mtl: null pointer"); return WB200_EINVAL; }
     if (n_modes < 1 || 2 * n_modes > BW_NVMAX) {
         set_error("mtl: %d modes outside [1, %d]", n_modes, BW_NVMAX / 2);
         return n_modes > BW_NVMAX / 2 ? WB200_ENOSUP : WB200_EINVAL;
@@ -936,23 +1004,19 @@ extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, i
     const int n = n_modes, n2 = 2 * n;
     const uint64_t total = 1ull << n;
     if (p0 > p1 || p1 > total) { set_error("mtl: bad subset range"); return WB200_EINVAL; }
-    WB_CUDA(cudaSetDevice(device));
-    int sms = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0, sms = 0;
+    (void)cudaGetLastError();
+    WB_CUDA(cudaGetDevice(&device));
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    DevBufB dA, dz, dzc, dpart, dout;
-    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * n2 * n2));
-    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * n2 * n2, cudaMemcpyHostToDevice));
     MtlParams p;
     memset(&p, 0, sizeof(p));
-    p.A = (const double2*)dA.p; p.n = n; p.smax = n2; p.T = n; p.p0 = p0; p.p1 = p1;
-    if (zeta) {
-        double zc[2 * BW_NVMAX];
-        for (int i = 0; i < n2; ++i) { zc[2 * i] = zeta[2 * i]; zc[2 * i + 1] = -zeta[2 * i + 1]; }
-        WB_POOL(pool_alloc(&dz.p, sizeof(double2) * n2));
-        WB_POOL(pool_alloc(&dzc.p, sizeof(double2) * n2));
-        WB_CUDA(cudaMemcpy(dz.p, zeta, sizeof(double2) * n2, cudaMemcpyHostToDevice));
-        WB_CUDA(cudaMemcpy(dzc.p, zc, sizeof(double2) * n2, cudaMemcpyHostToDevice));
-        p.zeta = (const double2*)dz.p; p.zetac = (const double2*)dzc.p;
+    p.A = (const double2*)dA; p.n = n; p.smax = n2; p.T = n; p.p0 = p0; p.p1 = p1;
+    StreamBuf dzc, dpart;
+    if (dzeta) {
+        WB_POOL(dzc.alloc(sizeof(double2) * n2, st));
+        conj_kernel<<<1, 128, 0, st>>>((const double2*)dzeta, n2, (double2*)dzc.p);
+        p.zeta = (const double2*)dzeta; p.zetac = (const double2*)dzc.p;
     }
     const size_t per_warp = warp_ws_bytes(p.smax, p.T, 0);
     int ctas = 1;
@@ -964,21 +1028,37 @@ extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, i
     const uint64_t want = (p1 - p0 + wpc - 1) / wpc;
     if ((uint64_t)grid > want) grid = (int)(want ? want : 1);
     const int nwarps = grid * wpc;
-    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 8 * nwarps));
-    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 8));
+    WB_POOL(dpart.alloc(sizeof(double) * 8 * nwarps, st));
     p.partials = (double*)dpart.p;
-    EvPair ev;
-    WB_CUDA(cudaEventCreate(&ev.e0));
-    WB_CUDA(cudaEventCreate(&ev.e1));
-    WB_CUDA(cudaEventRecord(ev.e0, 0));
-    mtl_kernel<<<grid, 32 * wpc, shm>>>(p);
-    batch_final_kernel<<<1, 64>>>((const double*)dpart.p, nwarps, 2, (double*)dout.p);   // two complex outputs
-    WB_CUDA(cudaEventRecord(ev.e1, 0));
-    WB_CUDA(cudaEventSynchronize(ev.e1));
+    mtl_kernel<<<grid, 32 * wpc, shm, st>>>(p);
+    batch_final_kernel<<<1, 64, 0, st>>>((const double*)dpart.p, nwarps, 2, d_out8);   // two complex outputs
     WB_CUDA(cudaGetLastError());
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
-    if (kernel_ms) *kernel_ms = ms;
+    return WB200_OK;
+}
+
+extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, int n_modes, uint64_t p0, uint64_t p1,
+                              double out8[8], double* kernel_ms) {
+    if (!A || !out8) { set_error("mtl: null pointer"); return WB200_EINVAL; }
+    if (n_modes < 1 || 2 * n_modes > BW_NVMAX) {
+        set_error("mtl: %d modes outside [1, %d]", n_modes, BW_NVMAX / 2);
+        return n_modes > BW_NVMAX / 2 ? WB200_ENOSUP : WB200_EINVAL;
+    }
+    const int n2 = 2 * n_modes;
+    WB_CUDA(cudaSetDevice(device));
+    DevBufB dA, dz, dout;
+    WB_POOL(pool_alloc(&dA.p, sizeof(double2) * n2 * n2));
+    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double2) * n2 * n2, cudaMemcpyHostToDevice));
+    if (zeta) {
+        WB_POOL(pool_alloc(&dz.p, sizeof(double2) * n2));
+        WB_CUDA(cudaMemcpy(dz.p, zeta, sizeof(double2) * n2, cudaMemcpyHostToDevice));
+    }
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 8));
+    HostTimer tm;
+    int rc = tm.start(kernel_ms != nullptr);
+    if (rc) return rc;
+    rc = wb200_mtl_dev((const double*)dA.p, (const double*)dz.p, n_modes, p0, p1, (double*)dout.p, nullptr);
+    if (rc) return rc;
+    if ((rc = tm.stop(kernel_ms))) return rc;
     WB_CUDA(cudaMemcpy(out8, dout.p, sizeof(double) * 8, cudaMemcpyDeviceToHost));
     return WB200_OK;
 }

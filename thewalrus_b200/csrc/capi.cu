@@ -117,6 +117,26 @@ int pool_alloc(void** p, size_t bytes) {
     return WB200_OK;
 }
 
+int stream_alloc(void** p, size_t bytes, cudaStream_t st) {
+    static bool configured[64];
+    static std::mutex mu;
+    int dev = 0;
+    WB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!configured[dev]) {      // keep freed blocks in the pool across synchronisations (default threshold 0 returns them to the OS)
+            cudaMemPool_t pool;
+            WB_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            unsigned long long keep = ~0ull;
+            WB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            configured[dev] = true;
+        }
+    }
+    if (bytes < 256) bytes = 256;
+    WB_CUDA(cudaMallocAsync(p, bytes, st));
+    return WB200_OK;
+}
+
 void pool_free(void* p) {
     Pool& pl = g_pool;
     for (int i = 0; i < pl.n; ++i)

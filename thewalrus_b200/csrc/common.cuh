@@ -31,6 +31,16 @@ void pool_free(void* p);
         if (rc__ != WB200_OK) return rc__;  \
     } while (0)
 
+// Stream-ordered scratch for the *_dev entry points (cudaMallocAsync / cudaFreeAsync on the caller's stream): the call
+// returns without synchronising and the block goes back to the device's memory pool when the stream reaches the free.
+int stream_alloc(void** p, size_t bytes, cudaStream_t st);
+struct StreamBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ~StreamBuf() { if (p) cudaFreeAsync(p, st); }
+    int alloc(size_t bytes, cudaStream_t s) { st = s; return stream_alloc(&p, bytes, s); }
+};
+
 // ---------------------------------------------------------------------------------------------
 // error-free transformations; compiled without fast-math so the compiler keeps them
 // ---------------------------------------------------------------------------------------------

@@ -276,15 +276,15 @@ extern "C" int wb200_lhaf_general_steps(const int32_t* edge_reps, int n_edges, i
     return WB200_OK;
 }
 
-extern "C" int wb200_lhaf_general_host(int device, const double* A, const double* D, const double* oddV,
-                                       const double* oddloop, int n, const int32_t* edge_reps, int glynn,
-                                       uint64_t j0, uint64_t j1, double out4[4], double* kernel_ms) {
-    if (!A || !edge_reps || !out4) { set_error("lhaf_general: null pointer"); return WB200_EINVAL; }
+extern "C" int wb200_lhaf_general_dev(const double* dA, const double* dD, const double* doddV, const double* oddloop,
+                                      int n, const int32_t* edge_reps, int glynn, uint64_t j0, uint64_t j1,
+                                      double* d_out4, void* stream) {
+    if (!dA || !edge_reps || !d_out4) { set_error("lhaf_general: null pointer"); return WB200_EINVAL; }
     if (n < 2 || (n & 1)) { set_error("lhaf_general: n must be even and >= 2 (got %d)", n); return WB200_EINVAL; }
     const int E = n / 2;
     if (E > LG_MAX_EDGES) { set_error("lhaf_general: %d edges exceed the limit of %d", E, LG_MAX_EDGES); return WB200_ENOSUP; }
-    const int has_odd = oddV != nullptr;
-    if (has_odd && (!oddloop || !D)) { set_error("lhaf_general: odd vertex needs oddloop and D"); return WB200_EINVAL; }
+    const int has_odd = doddV != nullptr;
+    if (has_odd && (!oddloop || !dD)) { set_error("lhaf_general: odd vertex needs oddloop and D"); return WB200_EINVAL; }
     uint64_t steps = 0;
     int rc = wb200_lhaf_general_steps(edge_reps, E, glynn, has_odd, &steps);
     if (rc) return rc;
@@ -294,20 +294,12 @@ extern "C" int wb200_lhaf_general_host(int device, const double* A, const double
     int N = has_odd ? 1 : 0;
     for (int i = 0; i < E; ++i) { p.reps[i] = edge_reps[i]; N += 2 * edge_reps[i]; }
     if ((has_odd ? N : N / 2) > LG_MAX_ORDER) { set_error("lhaf_general: photon number %d too large", N); return WB200_ENOSUP; }
-    WB_CUDA(cudaSetDevice(device));
-    DevBufLg dA, dD, dV, dout, dpart;
-    WB_POOL(pool_alloc(&dA.p, sizeof(double) * 2 * n * n));
-    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double) * 2 * n * n, cudaMemcpyHostToDevice));
-    if (D) {
-        WB_POOL(pool_alloc(&dD.p, sizeof(double) * 2 * n));
-        WB_CUDA(cudaMemcpy(dD.p, D, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
-    }
-    if (has_odd) {
-        WB_POOL(pool_alloc(&dV.p, sizeof(double) * 2 * n));
-        WB_CUDA(cudaMemcpy(dV.p, oddV, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
-        p.oddloop = make_double2(oddloop[0], oddloop[1]);
-    }
-    p.A = (const double2*)dA.p; p.D = (const double2*)dD.p; p.oddV = (const double2*)dV.p;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0;
+    (void)cudaGetLastError();
+    WB_CUDA(cudaGetDevice(&device));
+    if (has_odd) p.oddloop = make_double2(oddloop[0], oddloop[1]);
+    p.A = (const double2*)dA; p.D = (const double2*)dD; p.oddV = (const double2*)doddV;
     p.n = n; p.E = E; p.glynn = glynn; p.has_odd = has_odd; p.N = N; p.j0 = j0; p.j1 = j1;
     int sms = 0, occ = 1;
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
@@ -317,22 +309,50 @@ extern "C" int wb200_lhaf_general_host(int device, const double* A, const double
     if (occ < 1) occ = 1;
     uint64_t total = j1 - j0, maxgrid = (uint64_t)sms * occ;
     int grid = (int)(total < maxgrid ? (total ? total : 1) : maxgrid);
-    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 4 * grid));
-    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
-    cudaEvent_t e0, e1;
-    WB_CUDA(cudaEventCreate(&e0));
-    WB_CUDA(cudaEventCreate(&e1));
-    WB_CUDA(cudaEventRecord(e0, 0));
-    lhaf_general_kernel<<<grid, LG_THREADS, shm>>>(p, (double*)dpart.p);
-    final_reduce_kernel<<<1, 32>>>((const double*)dpart.p, grid, (double*)dout.p);
-    WB_CUDA(cudaEventRecord(e1, 0));
-    WB_CUDA(cudaEventSynchronize(e1));
+    StreamBuf dpart;
+    WB_POOL(dpart.alloc(sizeof(double) * 4 * grid, st));
+    lhaf_general_kernel<<<grid, LG_THREADS, shm, st>>>(p, (double*)dpart.p);
+    final_reduce_kernel<<<1, 32, 0, st>>>((const double*)dpart.p, grid, d_out4);
     WB_CUDA(cudaGetLastError());
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (kernel_ms) *kernel_ms = ms;
+    return WB200_OK;
+}
+
+extern "C" int wb200_lhaf_general_host(int device, const double* A, const double* D, const double* oddV,
+                                       const double* oddloop, int n, const int32_t* edge_reps, int glynn,
+                                       uint64_t j0, uint64_t j1, double out4[4], double* kernel_ms) {
+    if (!A || !edge_reps || !out4) { set_error("lhaf_general: null pointer"); return WB200_EINVAL; }
+    if (n < 2 || n > 2 * LG_MAX_EDGES) { set_error("lhaf_general: n = %d outside [2, %d]", n, 2 * LG_MAX_EDGES); return n > 2 * LG_MAX_EDGES ? WB200_ENOSUP : WB200_EINVAL; }
+    WB_CUDA(cudaSetDevice(device));
+    DevBufLg dA, dD, dV, dout;
+    WB_POOL(pool_alloc(&dA.p, sizeof(double) * 2 * n * n));
+    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(double) * 2 * n * n, cudaMemcpyHostToDevice));
+    if (D) {
+        WB_POOL(pool_alloc(&dD.p, sizeof(double) * 2 * n));
+        WB_CUDA(cudaMemcpy(dD.p, D, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    }
+    if (oddV) {
+        WB_POOL(pool_alloc(&dV.p, sizeof(double) * 2 * n));
+        WB_CUDA(cudaMemcpy(dV.p, oddV, sizeof(double) * 2 * n, cudaMemcpyHostToDevice));
+    }
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) {
+        WB_CUDA(cudaEventCreate(&e0));
+        WB_CUDA(cudaEventCreate(&e1));
+        WB_CUDA(cudaEventRecord(e0, 0));
+    }
+    int rc = wb200_lhaf_general_dev((const double*)dA.p, (const double*)dD.p, (const double*)dV.p, oddloop, n, edge_reps, glynn,
+                                    j0, j1, (double*)dout.p, nullptr);
+    if (rc) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return rc; }
+    if (kernel_ms) {
+        WB_CUDA(cudaEventRecord(e1, 0));
+        WB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *kernel_ms = ms;
+    }
     WB_CUDA(cudaMemcpy(out4, dout.p, 4 * sizeof(double), cudaMemcpyDeviceToHost));
     return WB200_OK;
 }

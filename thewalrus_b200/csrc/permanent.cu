@@ -85,24 +85,19 @@ template <> struct Traits<unsigned long long> {
     __device__ static unsigned long long one() { return 1ull; }
 };
 
-// Kahan accumulators (fed with block sums)
+// Per-thread accumulators, fed with the plain-FP64 sums of 16 groups of steps: double-double (error-free two-sum), so
+// that the grouping of block sums into threads, warps and ranks does not show in the rounded result — together with
+// the shard-independent segment length (pick_logL) this makes a sharded run return the bits of the single-GPU run
+// (r01: Kahan here, and Ryser at n = 25 differed by 2.9e-11 between world sizes).
 struct KahanC {
-    double sr = 0, cr = 0, si = 0, ci = 0;
-    __device__ __forceinline__ void add(C128 x) {
-        double y = x.re - cr, t = sr + y;
-        cr = (t - sr) - y; sr = t;
-        y = x.im - ci; t = si + y;
-        ci = (t - si) - y; si = t;
-    }
-    __device__ __forceinline__ cdd get() const { cdd o; o.re = {sr, -cr}; o.im = {si, -ci}; return o; }
+    dd re = {0.0, 0.0}, im = {0.0, 0.0};
+    __device__ __forceinline__ void add(C128 x) { dd_add(re, x.re); dd_add(im, x.im); }
+    __device__ __forceinline__ cdd get() const { cdd o; o.re = re; o.im = im; return o; }
 };
 struct KahanR {
-    double s = 0, c = 0;
-    __device__ __forceinline__ void add(double x) {
-        double y = x - c, t = s + y;
-        c = (t - s) - y; s = t;
-    }
-    __device__ __forceinline__ cdd get() const { cdd o; o.re = {s, -c}; o.im = {0.0, 0.0}; return o; }
+    dd s = {0.0, 0.0};
+    __device__ __forceinline__ void add(double x) { dd_add(s, x); }
+    __device__ __forceinline__ cdd get() const { cdd o; o.re = s; o.im = {0.0, 0.0}; return o; }
 };
 struct AccI {
     unsigned long long s = 0;
@@ -312,10 +307,22 @@ perm_kernel(const S* __restrict__ Mg, int n, int ryser, uint64_t k0, uint64_t k1
 constexpr int PERM_MAX_GRID = 4096;
 constexpr int PERM_MAX_N = 64;
 
-// segment length 2^logL: long enough to amortise seeding (n / 6 steps' worth), short enough to fill the grid
-static int pick_logL(uint64_t total, uint64_t nstreams) {
+// Segment length 2^logL: long enough to amortise seeding (n / 6 steps' worth), short enough to fill the grid.  It is
+// chosen from the FULL step count of the problem and the full grid, as if the range were split over 8 ranks — never
+// from the shard [k0, k1) — because the rounding of the incrementally updated column sums depends on where a segment
+// was seeded: with one segment length for every world size <= 8 each step's term is bit-identical wherever it runs.
+static int pick_logL_for(uint64_t total, uint64_t nstreams, uint64_t segs_per_slot) {
     int logL = 6;
-    while (logL < 20 && (total >> (logL + 1)) >= nstreams * 32) ++logL;   // >= 32 segments per stream slot: <= 3 % tail
+    while (logL < 20 && (total >> (logL + 1)) >= nstreams * segs_per_slot) ++logL;
+    return logL;
+}
+static int pick_logL(uint64_t full_steps, uint64_t nstreams) {
+    const uint64_t shard = full_steps >> 3;
+    int logL = pick_logL_for(shard, nstreams, 32);            // >= 32 segments per stream slot at 8 ranks: <= 3 % tail
+    if (logL < 9) {                                            // mid sizes: accept >= 8 segments per slot at 8 ranks rather
+        const int alt = pick_logL_for(shard, nstreams, 8);     // than pay the seeding of 64-step segments on one GPU
+        logL = alt < 9 ? alt : 9;
+    }
     return logL;
 }
 
@@ -336,8 +343,8 @@ static int launch_perm(const S* dM, int n, int method, uint64_t k0, uint64_t k1,
     if (maxgrid > PERM_MAX_GRID) maxgrid = PERM_MAX_GRID;
     uint64_t want = (total + spb * 64 - 1) / (spb * 64);
     int grid = (int)(want < maxgrid ? (want ? want : 1) : maxgrid);
-    int logL = pick_logL(total, (uint64_t)grid * spb);
     const int bits = method ? n : n - 1;          // the step index has `bits` bits: rows ctz(t) stay below n
+    int logL = pick_logL(1ull << bits, maxgrid * spb);
     if (logL > bits) logL = bits;
     if (logL < 1) logL = 1;
     perm_kernel<CPL, SL, NS, MINB, S><<<grid, PERM_THREADS, shm, st>>>(dM, n, method, k0, k1, logL, partials, iout);
@@ -545,25 +552,20 @@ extern "C" int wb200_perm_dev(const double* dM, int n, int method, uint64_t k0, 
     return WB200_OK;
 }
 
-extern "C" int wb200_brs_host(int device, const double* A, const double* E, int m, int n, uint64_t j0, uint64_t j1,
-                              double out4[4], double* kernel_ms) {
-    if (!A || !out4) { set_error("brs: null pointer"); return WB200_EINVAL; }
+extern "C" int wb200_brs_dev(const double* dA, const double* dE, int m, int n, uint64_t j0, uint64_t j1, double* d_out4,
+                             void* stream) {
+    if (!dA || !d_out4) { set_error("brs: null pointer"); return WB200_EINVAL; }
     if (m < 1 || n < 1) { set_error("brs: A must be m x n with m, n >= 1 (got %d x %d)", m, n); return WB200_EINVAL; }
     if (n > BRS_MAX_N || m > BRS_MAX_M) { set_error("brs: %d x %d exceeds the kernel limits (%d rows, %d columns)", m, n, BRS_MAX_M, BRS_MAX_N); return WB200_ENOSUP; }
     const uint64_t outer = 1ull << m;
     if (j0 > j1 || j1 > outer) { set_error("brs: bad subset range"); return WB200_EINVAL; }
-    WB_CUDA(cudaSetDevice(device));
-    int sms = 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device = 0, sms = 0;
+    (void)cudaGetLastError();
+    WB_CUDA(cudaGetDevice(&device));
     if (device_sm_count(device, &sms)) return WB200_ECUDA;
-    struct Buf { void* p = nullptr; ~Buf() { if (p) pool_free(p); } } dA, dE, dpart, dout;
-    WB_POOL(pool_alloc(&dA.p, sizeof(C128) * m * n));
-    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(C128) * m * n, cudaMemcpyHostToDevice));
-    if (E) {
-        WB_POOL(pool_alloc(&dE.p, sizeof(C128) * n * n));
-        WB_CUDA(cudaMemcpy(dE.p, E, sizeof(C128) * n * n, cudaMemcpyHostToDevice));
-    }
     BrsParams p;
-    p.A = (const C128*)dA.p; p.E = (const C128*)dE.p; p.m = m; p.n = n; p.j0 = j0; p.j1 = j1;
+    p.A = (const C128*)dA; p.E = (const C128*)dE; p.m = m; p.n = n; p.j0 = j0; p.j1 = j1;
     // inner Gray code of 2^(n-1) steps = chunks x 32 lanes x 2^log_seg; more chunks when there are few outer subsets
     const int inner_bits = n - 1;
     int log_seg = inner_bits > 5 ? inner_bits - 5 : 0, log_chunks = 0;
@@ -574,33 +576,56 @@ extern "C" int wb200_brs_host(int device, const double* A, const double* E, int 
     int grid = (int)((units + BRS_WARPS - 1) / BRS_WARPS);
     if (grid > sms * 2) grid = sms * 2;
     if (grid < 1) grid = 1;
-    WB_POOL(pool_alloc(&dpart.p, sizeof(double) * 4 * grid * BRS_WARPS));
-    WB_CUDA(cudaMemset(dpart.p, 0, sizeof(double) * 4 * grid * BRS_WARPS));
-    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
+    StreamBuf dpart;
+    WB_POOL(dpart.alloc(sizeof(double) * 4 * grid * BRS_WARPS, st));
+    WB_CUDA(cudaMemsetAsync(dpart.p, 0, sizeof(double) * 4 * grid * BRS_WARPS, st));
     p.partials = (double*)dpart.p;
-    cudaEvent_t e0, e1;
-    WB_CUDA(cudaEventCreate(&e0));
-    WB_CUDA(cudaEventCreate(&e1));
-    WB_CUDA(cudaEventRecord(e0, 0));
     int rc;
-    if (n <= 4) rc = launch_brs<4>(p, grid, 0);
-    else if (n <= 8) rc = launch_brs<8>(p, grid, 0);
-    else if (n <= 12) rc = launch_brs<12>(p, grid, 0);
-    else if (n <= 16) rc = launch_brs<16>(p, grid, 0);
-    else if (n <= 20) rc = launch_brs<20>(p, grid, 0);
-    else if (n <= 24) rc = launch_brs<24>(p, grid, 0);
-    else if (n <= 28) rc = launch_brs<28>(p, grid, 0);
-    else rc = launch_brs<32>(p, grid, 0);
-    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
-    final_reduce_kernel<<<1, 32>>>((const double*)dpart.p, grid * BRS_WARPS, (double*)dout.p);
-    WB_CUDA(cudaEventRecord(e1, 0));
-    WB_CUDA(cudaEventSynchronize(e1));
+    if (n <= 4) rc = launch_brs<4>(p, grid, st);
+    else if (n <= 8) rc = launch_brs<8>(p, grid, st);
+    else if (n <= 12) rc = launch_brs<12>(p, grid, st);
+    else if (n <= 16) rc = launch_brs<16>(p, grid, st);
+    else if (n <= 20) rc = launch_brs<20>(p, grid, st);
+    else if (n <= 24) rc = launch_brs<24>(p, grid, st);
+    else if (n <= 28) rc = launch_brs<28>(p, grid, st);
+    else rc = launch_brs<32>(p, grid, st);
+    if (rc) return rc;
+    final_reduce_kernel<<<1, 32, 0, st>>>((const double*)dpart.p, grid * BRS_WARPS, d_out4);
     WB_CUDA(cudaGetLastError());
-    float ms = 0;
-    WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    if (kernel_ms) *kernel_ms = ms;
+    return WB200_OK;
+}
+
+extern "C" int wb200_brs_host(int device, const double* A, const double* E, int m, int n, uint64_t j0, uint64_t j1,
+                              double out4[4], double* kernel_ms) {
+    if (!A || !out4) { set_error("brs: null pointer"); return WB200_EINVAL; }
+    if (m < 1 || n < 1) { set_error("brs: A must be m x n with m, n >= 1 (got %d x %d)", m, n); return WB200_EINVAL; }
+    if (n > BRS_MAX_N || m > BRS_MAX_M) { set_error("brs: %d x %d exceeds the kernel limits (%d rows, %d columns)", m, n, BRS_MAX_M, BRS_MAX_N); return WB200_ENOSUP; }
+    WB_CUDA(cudaSetDevice(device));
+    struct Buf { void* p = nullptr; ~Buf() { if (p) pool_free(p); } } dA, dE, dout;
+    WB_POOL(pool_alloc(&dA.p, sizeof(C128) * m * n));
+    WB_CUDA(cudaMemcpy(dA.p, A, sizeof(C128) * m * n, cudaMemcpyHostToDevice));
+    if (E) {
+        WB_POOL(pool_alloc(&dE.p, sizeof(C128) * n * n));
+        WB_CUDA(cudaMemcpy(dE.p, E, sizeof(C128) * n * n, cudaMemcpyHostToDevice));
+    }
+    WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (kernel_ms) {
+        WB_CUDA(cudaEventCreate(&e0));
+        WB_CUDA(cudaEventCreate(&e1));
+        WB_CUDA(cudaEventRecord(e0, 0));
+    }
+    int rc = wb200_brs_dev((const double*)dA.p, (const double*)dE.p, m, n, j0, j1, (double*)dout.p, nullptr);
+    if (rc) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return rc; }
+    if (kernel_ms) {
+        WB_CUDA(cudaEventRecord(e1, 0));
+        WB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        WB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *kernel_ms = ms;
+    }
     WB_CUDA(cudaMemcpy(out4, dout.p, 4 * sizeof(double), cudaMemcpyDeviceToHost));
     return WB200_OK;
 }
