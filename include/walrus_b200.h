@@ -125,6 +125,17 @@ int wb200_lhaf_batch_gamma_dev(const double* dAx, const double* dDx, int n, int 
                                int odd_variant, int cutoff_extra, int glynn, uint64_t j0, uint64_t j1, double* d_out,
                                int length, void* stream);
 
+/* ---- chain-rule photon-number sampler: all mode steps on the device ----------------------------------------
+ * Replaces the per-mode loop of generate_hafnian_sample (thewalrus/samples.py:204-261) for S chains at once.  Inputs (host,
+ * prepared as the reference does, :228-247): B = Amat(T)[:M, :M] (M x M complex), gamma0 = conj(pure_alpha) +
+ * (het_alpha - pure_alpha) B^T (S x M complex), het = het_alpha (S x M complex), uniforms (M x S doubles in [0, 1): row i
+ * holds the draws of mode step i).  Mode step i: gamma <- gamma - het[:, i] B[:, i]; p(k) ~ |lhaf(B[:i+1, :i+1],
+ * gamma[:i+1], reps = (n_0 .. n_(i-1), k))|^2 / k!, k = 0 .. cutoff; n_i = the outcome numpy.random.choice returns for
+ * that uniform.  det_out: S x M int32 photon numbers (rejection of chains — last mode at the cutoff, too many photons —
+ * is the caller's, :253-261).  M <= 64, cutoff <= 63.  WB200_EINVAL if a probability row is NaN / negative / all zero. */
+int wb200_hafnian_chains_host(int device, const double* B, const double* gamma0, const double* het, const double* uniforms,
+                              int M, int64_t S, int cutoff, int32_t* det_out, double* kernel_ms);
+
 /* ---- montrealer ---------------------------------------------------------------------------------------
  * Replaces montrealer / lmontrealer (thewalrus/_montrealer.py:37-102) as called by mtl / lmtl (:105-135):
  * A: 2n x 2n complex (the matrix passed to mtl, NOT pre-multiplied by Xmat), zeta: 2n complex or NULL.

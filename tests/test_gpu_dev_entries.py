@@ -137,3 +137,26 @@ def test_batch_gamma_mtl_brs_dev_match_host(ctx):
         _lib.check(lib.wb200_brs_dev(dA.data_ptr(), dE.data_ptr(), m, nn, 0, 1 << m, out.data_ptr(), st.cuda_stream), "wb200_brs_dev")
     st.synchronize()
     assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_device_chain_sampler_reproduces_the_host_walk():
+    """wb200_hafnian_chains_host (all mode steps on the device) draws the same patterns as the per-mode host walk from the
+    same numpy.random seed: same loop hafnians, same uniforms in the same order, same inverse-CDF rule."""
+    import bench
+    from thewalrus_b200 import samples as ws
+
+    _, M, (mu, cov) = bench.make_input("hsample6")
+    ch = ws._Chain(cov, mu, 2)
+    S, cutoff = 256, 5
+    np.random.seed(1234)
+    dev_det = ws._hafnian_chains(ch, S, cutoff, None)
+    saved = ws.DEVICE_CHAIN_MIN
+    try:
+        ws.DEVICE_CHAIN_MIN = 10 ** 9
+        np.random.seed(1234)
+        host_det = ws._hafnian_chains(ch, S, cutoff, None)
+    finally:
+        ws.DEVICE_CHAIN_MIN = saved
+    assert dev_det.shape == host_det.shape == (S, M)
+    assert np.array_equal(dev_det, host_det)
+    assert dev_det.sum() > 0 and dev_det.max() <= cutoff

@@ -323,6 +323,30 @@ def lhaf_patterns_local(A, gamma, rpt, glynn=True, device=None, want_ms=False, g
     return (out, ms.value) if want_ms else out
 
 
+def hafnian_chains(B, gamma0, het, uniforms, cutoff, device=None):
+    """All mode steps of S chain-rule photon-number chains on the device (``wb200_hafnian_chains_host``):
+    ``B`` [M, M], ``gamma0`` / ``het`` [S, M] complex, ``uniforms`` [M, S] -> int32 patterns [S, M]."""
+    lib = _lib.load()
+    idx = _dev_index(device)
+    B, pB = _lib.as_c128(B)
+    gamma0, pG = _lib.as_c128(gamma0)
+    het, pH = _lib.as_c128(het)
+    S, M = gamma0.shape
+    u = np.ascontiguousarray(uniforms, dtype=np.float64)
+    if u.shape != (M, S) or het.shape != (S, M) or B.shape != (M, M):
+        raise ValueError("hafnian_chains: inconsistent shapes")
+    det = np.zeros((S, M), dtype=np.int32)
+    ms = ctypes.c_double(0.0)
+    rc = lib.wb200_hafnian_chains_host(idx, pB, pG, pH, _lib.dptr(u), M, S, int(cutoff),
+                                       det.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                       ctypes.byref(ms) if kernel_ms_log is not None else None)
+    if rc == -1 and b"probabilities" in lib.wb200_last_error():
+        raise ValueError(lib.wb200_last_error().decode())
+    _lib.check(rc, "wb200_hafnian_chains_host")
+    _log_ms(ms)
+    return det
+
+
 def run_sharded_patterns(A, gamma, rpt, glynn, group, device, local=None, gamma_index=None, A_index=None):
     """Shard the PATTERNS in contiguous blocks over the ranks of ``group`` and all-gather the results
     (the batched front end shards the batch, not the subset index).  ``local`` overrides the

@@ -57,6 +57,8 @@ SIGNATURES = {
     "wb200_lhaf_batch_gamma_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, ctypes.c_int,
                                                    _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _u64, _u64,
                                                    _c_double_p, ctypes.c_int, _c_double_p]),
+    "wb200_hafnian_chains_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, _c_double_p, _c_double_p, ctypes.c_int,
+                                                 ctypes.c_int64, ctypes.c_int, _c_int32_p, _c_double_p]),
     "wb200_mtl_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _u64, _u64, _c_double_p,
                                       _c_double_p]),
     "wb200_perm_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int]),

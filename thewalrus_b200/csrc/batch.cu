@@ -410,6 +410,7 @@ struct PatParams {
     const int32_t* gidx;  // per-pattern row of D, or null (all patterns use row 0)
     const int32_t* aidx;  // per-pattern matrix of the table A[n_A][nv][nv], or null (all patterns use matrix 0)
     int nv, glynn, smax, T, O;
+    int lda, ldg;   // row strides of A and of the loop-vector table (>= nv: the samplers pass leading blocks of one matrix)
     long long B;
     const PatDesc* desc;
     const unsigned long long* coff;  // B + 1 chunk offsets
@@ -452,8 +453,8 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
         const PatDesc* d = p.desc + pat;
         const int E = d->E, N = d->N, odd = d->odd;
         const unsigned long long steps = d->steps;
-        const double2* Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.nv : p.D;
-        const double2* Ap = p.aidx ? p.A + (size_t)__ldg(p.aidx + pat) * p.nv * p.nv : p.A;
+        const double2* Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.ldg : p.D;
+        const double2* Ap = p.aidx ? p.A + (size_t)__ldg(p.aidx + pat) * p.lda * p.lda : p.A;
         __syncwarp();
         if (lane < BW_EMAX) { w.eu[lane] = d->u[lane]; w.ev[lane] = d->v[lane]; w.er[lane] = d->r[lane]; }
         __syncwarp();
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(32 * BW_WARPS) pat_main_kernel(PatParams p) {
             }
             __syncwarp();
             const int k = s_k[warp];
-            subset_traces(w, Ap, p.nv, Dp, odd, -1, k, T, lane);
+            subset_traces(w, Ap, p.lda, Dp, odd, -1, k, T, lane);
             if (odd >= 0) fac_odd(w, order, __ldg(Dp + odd), w.ov, lane);
             else fac_even(w, order, lane);
             exp_series(w, w.cs0, order, lane);
@@ -498,14 +499,14 @@ struct PatBases {
 
 __global__ void pat_final_kernel(const PatDesc* __restrict__ desc, const unsigned long long* __restrict__ coff_all, PatBases cb,
                                  const double* __restrict__ partial_all, const double2* __restrict__ D,
-                                 const int32_t* __restrict__ gidx, int nv, int glynn, long long B,
+                                 const int32_t* __restrict__ gidx, int ldg, int glynn, long long B,
                                  double2* __restrict__ out) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= B) return;
     const PatDesc* d = desc + p;
     if (d->kind == 1) { out[p] = make_double2(1.0, 0.0); return; }
     if (d->kind == 2) { out[p] = make_double2(0.0, 0.0); return; }
-    if (d->kind == 3) { out[p] = D[(gidx ? (size_t)gidx[p] * nv : 0) + d->odd]; return; }
+    if (d->kind == 3) { out[p] = D[(gidx ? (size_t)gidx[p] * ldg : 0) + d->odd]; return; }
     dd re = {0.0, 0.0}, im = {0.0, 0.0};
     const unsigned long long* coff = coff_all + (size_t)d->cls * (B + 1);
     const double* partial = partial_all + 4 * cb.base[d->cls];
@@ -703,7 +704,9 @@ static int bw_pick_warps(size_t per_warp, int* ctas) {
 // env WB200_PAT_DFMA=1 forces every pattern onto the warp-per-subset DFMA kernel (A/B measurements, tests).
 static int lhaf_matrices_device(const double2* dA, int n_A, const int32_t* dai, const double2* dD, int n_gamma, const int32_t* dgi,
                                 int nv, const int32_t* drpt, int64_t B, int glynn, double2* dout, int sms, cudaStream_t st,
-                                double* kernel_ms) {
+                                double* kernel_ms, int lda = 0, int ldg = 0) {
+    if (lda < nv) lda = nv;
+    if (ldg < nv) ldg = nv;
     const char* env_dfma = getenv("WB200_PAT_DFMA");      // read per call: the tests toggle it
     const int force_fallback = (env_dfma && atoi(env_dfma)) ? 1 : 0;
     StreamBuf ddesc, dnch, dcls, dcoff, dmeta, dpartial;
@@ -748,7 +751,7 @@ static int lhaf_matrices_device(const double2* dA, int n_A, const int32_t* dai, 
         for (int c = PAT_NCLS - 1; c >= 0; --c) {
             if (!h.totals[c]) continue;
             PatParams p;
-            p.A = dA; p.D = dD; p.gidx = dgi; p.aidx = dai; p.nv = nv; p.glynn = glynn;
+            p.A = dA; p.D = dD; p.gidx = dgi; p.aidx = dai; p.nv = nv; p.glynn = glynn; p.lda = lda; p.ldg = ldg;
             p.smax = 2 * h.meta.maxE; p.T = h.meta.maxN / 2; p.O = h.meta.anyOdd ? h.meta.maxN : h.meta.maxN / 2;
             p.B = B; p.desc = (const PatDesc*)ddesc.p; p.coff = (const unsigned long long*)dcoff.p + (size_t)c * (B + 1);
             p.nchunks = h.totals[c]; p.counter = d_counters + c;
@@ -772,7 +775,7 @@ static int lhaf_matrices_device(const double2* dA, int n_A, const int32_t* dai, 
         }
     }
     pat_final_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>((const PatDesc*)ddesc.p, (const unsigned long long*)dcoff.p, cb,
-                                                                  (const double*)dpartial.p, dD, dgi, nv, glynn, B, dout);
+                                                                  (const double*)dpartial.p, dD, dgi, ldg, glynn, B, dout);
     WB_CUDA(cudaGetLastError());
     if (kernel_ms) {
         WB_CUDA(cudaEventRecord(ev.e1, st));
@@ -1060,5 +1063,127 @@ extern "C" int wb200_mtl_host(int device, const double* A, const double* zeta, i
     if (rc) return rc;
     if ((rc = tm.stop(kernel_ms))) return rc;
     WB_CUDA(cudaMemcpy(out8, dout.p, sizeof(double) * 8, cudaMemcpyDeviceToHost));
+    return WB200_OK;
+}
+
+// =================================================================================================
+// chain-rule photon-number sampler, every mode step on the device
+// =================================================================================================
+// Replaces the per-mode loop of generate_hafnian_sample (thewalrus/samples.py:204-261) for S chains at once: at mode i a
+// chain with outcomes n_1 .. n_(i-1) draws n_i from  p(k) ~ |lhaf(B[:i,:i], gamma[:i], reps = (n_1 .. n_(i-1), k))|^2 / k!,
+// k = 0 .. cutoff, after the heterodyne shift  gamma <- gamma - het_i B[:, i]  (:243-249).  The S (cutoff + 1) loop
+// hafnians of a mode step are one call of the batched front end on leading blocks of B and gamma (row strides M), the
+// outcome is drawn on the device from a host-supplied uniform (one per chain and mode, numpy.random's stream), and
+// only the final patterns travel back.
+namespace wb {
+
+__global__ void chain_update_kernel(double2* __restrict__ gamma, const double2* __restrict__ het, const double2* __restrict__ Bm,
+                                    int mode, long long S, int M) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= S * M) return;
+    const long long s = idx / M;
+    const int j = (int)(idx - s * M);
+    const double2 h = het[s * M + mode], b = Bm[(size_t)j * M + mode];
+    double2 g = gamma[idx];
+    g.x -= h.x * b.x - h.y * b.y;
+    g.y -= h.x * b.y + h.y * b.x;
+    gamma[idx] = g;
+}
+
+// rpt[(s K + k), :] = (det[s, 0 .. mode-1], k);  gidx[s K + k] = s
+__global__ void chain_rpt_kernel(const int32_t* __restrict__ det, int32_t* __restrict__ rpt, int32_t* __restrict__ gidx,
+                                 int mode, int K, long long S, int M) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= S * K) return;
+    const long long s = row / K;
+    const int k = (int)(row - s * K), m = mode + 1;
+    for (int j = 0; j < mode; ++j) rpt[row * m + j] = det[s * M + j];
+    rpt[row * m + mode] = k;
+    gidx[row] = (int32_t)s;
+}
+
+struct ChainFact { double inv[64]; };   // 1 / k!
+
+// det[s, mode] = inverse-CDF draw from p(k) = |lh[s, k]|^2 / k! with the uniform u[s]: the outcome
+// numpy.random.choice(K, p = p / sum p) returns for that uniform (count of cdf entries <= u, samples.py:245-249).
+__global__ void chain_draw_kernel(const double2* __restrict__ lh, const double* __restrict__ u, ChainFact f, int32_t* __restrict__ det,
+                                  int mode, int K, long long S, int M, int* __restrict__ err) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    double tot = 0.0;
+    bool bad = false;
+    for (int k = 0; k < K; ++k) {
+        const double2 v = lh[s * K + k];
+        const double p = (v.x * v.x + v.y * v.y) * f.inv[k];
+        if (!(p >= 0.0) || isinf(p)) bad = true;
+        tot += p;
+    }
+    if (bad || !(tot > 0.0)) { atomicExch(err, 1); det[s * M + mode] = 0; return; }
+    double run = 0.0, cdf_last = 0.0;
+    for (int k = 0; k < K; ++k) { const double2 v = lh[s * K + k]; cdf_last += ((v.x * v.x + v.y * v.y) * f.inv[k]) / tot; }
+    int cnt = 0;
+    const double us = u[s];
+    for (int k = 0; k < K; ++k) {
+        const double2 v = lh[s * K + k];
+        run += ((v.x * v.x + v.y * v.y) * f.inv[k]) / tot;
+        if (run / cdf_last <= us) ++cnt;
+    }
+    det[s * M + mode] = cnt < K - 1 ? cnt : K - 1;
+}
+
+}  // namespace wb
+
+extern "C" int wb200_hafnian_chains_host(int device, const double* Bmat, const double* gamma0, const double* het,
+                                         const double* uniforms, int M, int64_t S, int cutoff, int32_t* det_out,
+                                         double* kernel_ms) {
+    if (!Bmat || !gamma0 || !het || !uniforms || !det_out) { set_error("hafnian_chains: null pointer"); return WB200_EINVAL; }
+    if (M < 1 || M > BW_NVMAX) { set_error("hafnian_chains: %d modes outside [1, %d]", M, BW_NVMAX); return M > BW_NVMAX ? WB200_ENOSUP : WB200_EINVAL; }
+    if (S < 1 || cutoff < 0 || cutoff > 63) { set_error("hafnian_chains: need S >= 1 and 0 <= cutoff <= 63"); return WB200_EINVAL; }
+    const int K = cutoff + 1;
+    WB_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    if (device_sm_count(device, &sms)) return WB200_ECUDA;
+    cudaStream_t st = 0;
+    DevBufB dB, dg, dh, du, ddet, drpt, dgi, dlh, derr;
+    WB_POOL(pool_alloc(&dB.p, sizeof(double2) * (size_t)M * M));
+    WB_POOL(pool_alloc(&dg.p, sizeof(double2) * (size_t)S * M));
+    WB_POOL(pool_alloc(&dh.p, sizeof(double2) * (size_t)S * M));
+    WB_POOL(pool_alloc(&du.p, sizeof(double) * (size_t)S * M));
+    WB_POOL(pool_alloc(&ddet.p, sizeof(int32_t) * (size_t)S * M));
+    WB_POOL(pool_alloc(&drpt.p, sizeof(int32_t) * (size_t)S * K * M));
+    WB_POOL(pool_alloc(&dgi.p, sizeof(int32_t) * (size_t)S * K));
+    WB_POOL(pool_alloc(&dlh.p, sizeof(double2) * (size_t)S * K));
+    WB_POOL(pool_alloc(&derr.p, sizeof(int)));
+    WB_CUDA(cudaMemcpy(dB.p, Bmat, sizeof(double2) * (size_t)M * M, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(dg.p, gamma0, sizeof(double2) * (size_t)S * M, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(dh.p, het, sizeof(double2) * (size_t)S * M, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(du.p, uniforms, sizeof(double) * (size_t)S * M, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemsetAsync(ddet.p, 0, sizeof(int32_t) * (size_t)S * M, st));
+    WB_CUDA(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+    ChainFact f;
+    f.inv[0] = 1.0;
+    for (int k = 1; k < 64; ++k) f.inv[k] = f.inv[k - 1] / k;
+    HostTimer tm;
+    int rc = tm.start(kernel_ms != nullptr);
+    if (rc) return rc;
+    const long long SK = (long long)S * K;
+    for (int mode = 0; mode < M; ++mode) {
+        chain_update_kernel<<<(unsigned)((S * M + 255) / 256), 256, 0, st>>>((double2*)dg.p, (const double2*)dh.p, (const double2*)dB.p,
+                                                                            mode, S, M);
+        chain_rpt_kernel<<<(unsigned)((SK + 127) / 128), 128, 0, st>>>((const int32_t*)ddet.p, (int32_t*)drpt.p, (int32_t*)dgi.p, mode, K,
+                                                                     S, M);
+        WB_CUDA(cudaGetLastError());
+        rc = lhaf_matrices_device((const double2*)dB.p, 1, nullptr, (const double2*)dg.p, (int)(S < 0x7fffffff ? S : 0x7fffffff),
+                                  (const int32_t*)dgi.p, mode + 1, (const int32_t*)drpt.p, SK, 1, (double2*)dlh.p, sms, st, nullptr, M, M);
+        if (rc) return rc;
+        chain_draw_kernel<<<(unsigned)((S + 127) / 128), 128, 0, st>>>((const double2*)dlh.p, (const double*)du.p + (size_t)mode * S, f,
+                                                                    (int32_t*)ddet.p, mode, K, S, M, (int*)derr.p);
+        WB_CUDA(cudaGetLastError());
+    }
+    if ((rc = tm.stop(kernel_ms))) return rc;
+    int herr = 0;
+    WB_CUDA(cudaMemcpy(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost));
+    WB_CUDA(cudaMemcpy(det_out, ddet.p, sizeof(int32_t) * (size_t)S * M, cudaMemcpyDeviceToHost));
+    if (herr) { set_error("hafnian_chains: probabilities contain NaN, are negative or do not sum to a positive number"); return WB200_EINVAL; }
     return WB200_OK;
 }

@@ -143,8 +143,8 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
             const PatDesc* d = p.desc + pat;
             E = d->E; T = d->N / 2; steps = d->steps;
             tp = TAIL ? E - 4 * TF : 0;
-            Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.nv : p.D;
-            Ap = p.aidx ? p.A + (size_t)__ldg(p.aidx + pat) * p.nv * p.nv : p.A;
+            Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.ldg : p.D;
+            Ap = p.aidx ? p.A + (size_t)__ldg(p.aidx + pat) * p.lda * p.lda : p.A;
             __syncwarp();
             if (lane < PD_EMAX) {
                 verts[lane] = lane < E ? d->u[lane] : 0;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                         const int in = 4 * tile + (ncol >> 1);
                         if (in < E) {
                             const int vn = (ncol & 1) ? verts[PD_EMAX + in] : verts[in];
-                            const double2 a = __ldg(Ap + (size_t)vk * p.nv + vn);
+                            const double2 a = __ldg(Ap + (size_t)vk * p.lda + vn);
                             v = imag_slot ? make_double2(-a.y, a.x) : a;
                         }
                     } else {
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                         if ((tq >> 1) < tp) {
                             const int in = 4 * TF + (tq >> 1);
                             const int vn = (tq & 1) ? verts[PD_EMAX + in] : verts[in];
-                            const double2 a = __ldg(Ap + (size_t)vk * p.nv + vn);
+                            const double2 a = __ldg(Ap + (size_t)vk * p.lda + vn);
                             v = (ncol & 1) ? make_double2(a.y, a.x) : make_double2(a.x, -a.y);
                             if (packk) v = make_double2(imag_slot ? v.y : v.x, 0.0);
                         }
@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                             double2 a = make_double2(0.0, 0.0);
                             if (ok) {
                                 const int vc = r ? verts[PD_EMAX + iv] : verts[iv];
-                                a = isD ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.nv + vc);
+                                a = isD ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.lda + vc);
                             }
                             w.wr[tau][r] = a.x;
                             w.wi[tau][r] = a.y;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                         if (ok) {
                             const int iv = 4 * TF + (t >> 1);
                             const int vc = (t & 1) ? verts[PD_EMAX + iv] : verts[iv];
-                            const double2 a = isD ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.nv + vc);
+                            const double2 a = isD ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.lda + vc);
                             w.wtr = a.x; w.wti = a.y;
                         }
                     }
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                     else pat_advance<TF, TAIL, false, false>(w, y, dl, dlt, orr, oi, er, ei);
                     if (t == 0) {
                         const int sv = half ? verts[i] : verts[PD_EMAX + i];                 // sigma(v)
-                        const double2 a = __ldg(Ap + (size_t)vv * p.nv + sv);
+                        const double2 a = __ldg(Ap + (size_t)vv * p.lda + sv);
                         double2 pp = part[1 * 8 + g];
                         pp.x += rs * a.x; pp.y += rs * a.y;
                         part[1 * 8 + g] = pp;

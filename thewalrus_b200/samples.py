@@ -18,6 +18,7 @@ requested samples (same distribution, different stream).
 import numpy as np
 from scipy.special import gammaln
 
+from . import _engine
 from . import quantum as _q
 
 __all__ = ["decompose_cov", "mu_to_alpha", "invert_permutation", "photon_means_order", "get_heterodyne_fanout",
@@ -109,6 +110,12 @@ class _Chain:
         return mu_to_alpha(pure_mu, self.hbar), mu_to_alpha(het_mu, self.hbar)
 
 
+def _engine_available():
+    """The device walk bypasses ``quantum.lhaf_patterns``; tests that substitute the oracle for that call (CPU twins)
+    keep the host walk."""
+    return getattr(_q.lhaf_patterns, "__module__", "") == _q.__name__
+
+
 def _lhaf_table(B, gammas, gidx, fixed, cutoff, device):
     """|lhaf|^2 / k! for k = 0..cutoff and every row of ``gidx``/``fixed``:
     ``loop_hafnian(B, gammas[gidx[r]], reps = fixed[r] + [k])`` -> ``[R, cutoff + 1]`` in one GPU call."""
@@ -136,11 +143,22 @@ def _draw_outcomes(probs):
     return np.minimum((cdf <= u[:, None]).sum(axis=1), probs.shape[1] - 1)
 
 
+DEVICE_CHAIN_MIN = 16      # from this many chains on, all mode steps run on the device (one C call per batch)
+
+
 def _hafnian_chains(ch, S, cutoff, device):
-    """Photon-number patterns (in the sorted mode order) of S chains advanced together."""
+    """Photon-number patterns (in the sorted mode order) of S chains advanced together.
+
+    Small batches (and ``batch=1``, which reproduces the reference's seeded stream) walk the modes on the host with one
+    GPU call per mode; from ``DEVICE_CHAIN_MIN`` chains on the whole walk — heterodyne shift, the S (cutoff + 1) loop
+    hafnians of every mode step, the inverse-CDF draws — is one call of ``wb200_hafnian_chains_host`` and consumes
+    ``numpy.random`` in the same order (normals, then one uniform per chain and mode, mode-major)."""
     M, B = ch.M, ch.B
     pure, het = ch.draw(S)
     gamma = pure.conj() + (het - pure) @ B.T
+    if S >= DEVICE_CHAIN_MIN and cutoff <= 63 and _engine_available():
+        u = np.random.random_sample((M, S))
+        return _engine.hafnian_chains(B, gamma, het, u, cutoff, device)
     det = np.zeros((S, M), dtype=np.int32)
     sidx = np.arange(S, dtype=np.int32)
     for mode in range(M):
