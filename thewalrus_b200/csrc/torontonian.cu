@@ -14,6 +14,7 @@
 // elimination per prefix), and expands the last DC modes of every prefix breadth-first in shared memory down to
 // 2-mode (4x4, loop variant 5x5) nodes, which single threads finish in registers.  Nodes are (offset, stride)
 // views of stored lower triangles, so excluding a mode copies nothing; see the comment above tor_kernel.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace wb {
@@ -349,6 +350,292 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
     block_reduce_store(a2, red, partials);
 }
 
+// =================================================================================================
+// v4 EXPERIMENT (torontonian only, opt-in with WB200_TOR_V4=1): warp-autonomous expansion of the last 9 modes on the
+// FP64 tensor cores.  Measured SLOWER than tor_kernel (2.5 ms vs 1.22 ms at 2N = 48, see tor_launch) — kept because it is
+// correct, documents the rank-2 DMMA form of the Schur complement, and is the starting point for a version with more
+// eliminations in flight per warp.
+// =================================================================================================
+// Phases A and B (shared leading modes, depth-first walk of the g group modes, all threads of the CTA) are those of
+// tor_kernel.  What changes is the expansion of a prefix's 18 x 18 root: instead of a breadth-first sweep by the whole
+// CTA (seven barriers per prefix, one or two matrix entries per thread and level — 21 % FP64 pipe, barrier and
+// short-scoreboard stalls: profiles/r01_ncu_tor48_v3b.txt), every WARP expands a root on its own:
+//   * modes 0 .. 5 of the root are walked depth-first with one buffer per depth (packed lower triangles); stepping to
+//     the next of the 64 paths costs ONE elimination, and that elimination is a rank-2 complex Hermitian update
+//         C <- C - i1 a a^H - i2 u u^H        (a = column 0, u = column 1 after the first pivot)
+//     which in real arithmetic is a K = 4 product:  Re C -= [a_r a_i u_r u_i] diag(i1 i1 i2 i2) [a_r a_i u_r u_i]^T
+//     — exactly one DMMA.8x8x4 per 8 x 8 tile for the real part and one for the imaginary part (40 flops per
+//     entry in 2 tensor instructions per 64 entries instead of ~20 FP64 instructions per entry);
+//   * the 64 three-mode (6 x 6) nodes of a root are collected 32 at a time and finished one per LANE in registers
+//     (one 4 x 4 Schur complement and two 2-mode tails = 8 subsets per lane), so the deepest levels, where almost
+//     all nodes live, run with every lane busy and no shared-memory traffic.
+// No CTA barrier inside an expansion; the CTA synchronises only for the shared eliminations of phases A / B.
+constexpr int T4_DC = 9;                 // modes expanded per root (the C-ABI prefix unit, as tor_kernel)
+constexpr int T4_WLV = 6;                // of which walked by the warp (root dim 18 -> children 16 .. 6)
+constexpr int T4_MAXW = 8;               // warps per CTA (fewer if shared memory does not allow)
+constexpr int T4_LEAF = 21;              // double2 per packed 6 x 6 leaf (odd: conflict-free per quarter warp)
+__host__ __device__ constexpr int t4_tri(int r, int c) { return r * (r + 1) / 2 + c; }
+// per-warp area (double2 units): root | depth buffers (child dims 16, 14, 12, 10, 8) | 32 leaves | leaf (det, sgn) | fragment vectors
+constexpr int T4_OFF_ROOT = 0;
+constexpr int T4_OFF_DEPTH = T4_OFF_ROOT + t4_tri(18, 0);                                          // 171
+constexpr int T4_OFF_LEAF = T4_OFF_DEPTH + t4_tri(16, 0) + t4_tri(14, 0) + t4_tri(12, 0) + t4_tri(10, 0) + t4_tri(8, 0);
+constexpr int T4_OFF_LDS = T4_OFF_LEAF + 32 * T4_LEAF;
+constexpr int T4_OFF_VEC = T4_OFF_LDS + 32;                                                         // 32 x (det, sgn)
+constexpr int T4_WARP_D2 = T4_OFF_VEC + 3 * 4 * 16 / 2;                                             // 3 tables x 4 components x 16 rows of doubles
+
+__device__ __forceinline__ void t4_dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// Eliminate the leading mode of the packed lower-triangular view (P, row offset k, dimension d) into the packed
+// buffer Q (dimension d - 2) with one warp.  vec: 192 doubles of scratch.  Returns d1 * d2.
+__device__ __forceinline__ double t4_schur(const double2* __restrict__ P, int k, int d, double2* __restrict__ Q,
+                                           double* __restrict__ vec, int lane) {
+    const int cd = d - 2;
+    const double2 e = P[t4_tri(k + 1, k)];
+    double i1, i2, d1d2;
+    pivot_inverses(P[t4_tri(k, k)].x, P[t4_tri(k + 1, k + 1)].x, e, i1, i2, d1d2);
+    if (lane < 16) {
+        double2 a = make_double2(0.0, 0.0), u = a;
+        if (lane < cd) {
+            a = P[t4_tri(k + 2 + lane, k)];
+            u = P[t4_tri(k + 2 + lane, k + 1)];
+            const double2 q = cmulc(a, e);
+            u.x -= q.x * i1; u.y -= q.y * i1;
+        }
+        // B operand: unscaled components; A operand (real part): -i scaled; A' operand (imaginary part)
+        vec[0 * 16 + lane] = a.x;            vec[1 * 16 + lane] = a.y;           vec[2 * 16 + lane] = u.x;            vec[3 * 16 + lane] = u.y;
+        vec[64 + 0 * 16 + lane] = -i1 * a.x; vec[64 + 1 * 16 + lane] = -i1 * a.y; vec[64 + 2 * 16 + lane] = -i2 * u.x; vec[64 + 3 * 16 + lane] = -i2 * u.y;
+        vec[128 + 0 * 16 + lane] = -i1 * a.y; vec[128 + 1 * 16 + lane] = i1 * a.x; vec[128 + 2 * 16 + lane] = -i2 * u.y; vec[128 + 3 * 16 + lane] = i2 * u.x;
+    }
+    __syncwarp();
+    const int g = lane >> 2, t = lane & 3;
+    const int ntile = cd > 8 ? 2 : 1;
+    for (int ti = 0; ti < ntile; ++ti) {
+        const int row = 8 * ti + g;
+        const double ar = vec[64 + t * 16 + row], ai = vec[128 + t * 16 + row];
+        for (int tj = 0; tj <= ti; ++tj) {
+            const int c0 = 8 * tj + 2 * t;
+            const double b = vec[t * 16 + 8 * tj + g];
+            const bool ok0 = row < cd && c0 <= row, ok1 = row < cd && c0 + 1 <= row;
+            double2 v0 = make_double2(0.0, 0.0), v1 = v0;
+            if (ok0) v0 = P[t4_tri(k + 2 + row, k + 2 + c0)];
+            if (ok1) v1 = P[t4_tri(k + 2 + row, k + 2 + c0 + 1)];
+            t4_dmma(v0.x, v1.x, ar, b);
+            t4_dmma(v0.y, v1.y, ai, b);
+            if (ok0) Q[t4_tri(row, c0)] = v0;
+            if (ok1) Q[t4_tri(row, c0 + 1)] = v1;
+        }
+    }
+    __syncwarp();
+    return d1d2;
+}
+
+// One lane finishes a packed 6 x 6 (three-mode) node: 8 subsets.
+__device__ __forceinline__ double t4_leaf(const double2* __restrict__ L, double det, double sgn) {
+    double2 q[16];
+    // exclude the leading mode: the trailing 4 x 4 block, sign flipped
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) q[r * 4 + c] = L[t4_tri(r + 2, c + 2)];
+    double sum = tail2(q, 4, det, -sgn);
+    // include it: both pivots fused (schur_entry on the packed triangle)
+    const double2 e = L[t4_tri(1, 0)];
+    double i1, i2, d1d2;
+    pivot_inverses(L[0].x, L[t4_tri(1, 1)].x, e, i1, i2, d1d2);
+    double2 a[4], u[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        a[r] = L[t4_tri(r + 2, 0)];
+        u[r] = L[t4_tri(r + 2, 1)];
+        const double2 w = cmulc(a[r], e);
+        u[r].x -= w.x * i1; u[r].y -= w.y * i1;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) {
+            double2 v = q[r * 4 + c];
+            { const double2 w = cmulc(a[r], a[c]); v.x -= w.x * i1; v.y -= w.y * i1; }
+            { const double2 w = cmulc(u[r], u[c]); v.x -= w.x * i2; v.y -= w.y * i2; }
+            q[r * 4 + c] = v;
+        }
+    sum += tail2(q, 4, det * d1d2, sgn);
+    return sum;
+}
+
+// Expand one 18 x 18 root (packed lower triangle in W + T4_OFF_ROOT) with one warp: 512 subsets.
+__device__ __forceinline__ void t4_expand(double2* __restrict__ W, double rdet, double rsgn, dd& acc, int lane) {
+    double* vec = reinterpret_cast<double*>(W + T4_OFF_VEC);
+    double2* lds = W + T4_OFF_LDS;
+    int nbase[T4_WLV + 1], nk[T4_WLV + 1];
+    double ndet[T4_WLV + 1], nsgn[T4_WLV + 1];
+#pragma unroll
+    for (int l = 0; l <= T4_WLV; ++l) { nbase[l] = T4_OFF_ROOT; nk[l] = 0; ndet[l] = rdet; nsgn[l] = rsgn; }
+    int prev = -1, nleaf = 0;
+    for (int sub = 0; sub < (1 << T4_WLV); ++sub) {
+        const int first = prev < 0 ? 0 : T4_WLV - (32 - __clz(sub ^ prev));
+        prev = sub;
+        double2* slot = W + T4_OFF_LEAF + nleaf * T4_LEAF;
+        int dbuf = T4_OFF_DEPTH;
+#pragma unroll
+        for (int lvl = 0; lvl < T4_WLV; ++lvl) {
+            const int dim = 2 * T4_DC - 2 * lvl, cd = dim - 2;
+            if (lvl >= first) {
+                const bool inc = (sub >> (T4_WLV - 1 - lvl)) & 1;
+                if (inc) {
+                    const int dst = (lvl == T4_WLV - 1) ? (int)(slot - W) : dbuf;      // the last level writes the leaf slot itself
+                    ndet[lvl + 1] = ndet[lvl] * t4_schur(W + nbase[lvl], nk[lvl], dim, W + dst, vec, lane);
+                    nsgn[lvl + 1] = nsgn[lvl];
+                    nbase[lvl + 1] = dst; nk[lvl + 1] = 0;
+                } else {
+                    ndet[lvl + 1] = ndet[lvl]; nsgn[lvl + 1] = -nsgn[lvl];
+                    nbase[lvl + 1] = nbase[lvl]; nk[lvl + 1] = nk[lvl] + 2;
+                }
+            }
+            dbuf += t4_tri(cd, 0);
+        }
+        // the three-mode node of this path: gather it into the leaf slot unless the last elimination wrote it there
+        if (nbase[T4_WLV] != (int)(slot - W)) {
+            if (lane < T4_LEAF) {
+                int r = 0;                       // lane -> (r, c) of the 6 x 6 lower triangle
+                while (t4_tri(r + 1, 0) <= lane) ++r;
+                const int c = lane - t4_tri(r, 0), k = nk[T4_WLV];
+                slot[lane] = W[nbase[T4_WLV] + t4_tri(k + r, k + c)];
+            }
+        }
+        if (lane == 0) lds[nleaf] = make_double2(ndet[T4_WLV], nsgn[T4_WLV]);
+        ++nleaf;
+        if (nleaf == 32 || sub == (1 << T4_WLV) - 1) {
+            __syncwarp();
+            if (lane < nleaf) {
+                const double2 ds = lds[lane];
+                dd_add(acc, t4_leaf(W + T4_OFF_LEAF + lane * T4_LEAF, ds.x, ds.y));
+            }
+            __syncwarp();
+            nleaf = 0;
+        }
+    }
+}
+
+// shared-memory plan of tor4_kernel (double2 units): T | depth buffers of the group walk | per-warp areas | root (det, sgn)
+__host__ __device__ inline size_t tor4_smem_plan(int N, int g, int warps, int* off_depth, int* off_warp) {
+    const int n2 = 2 * N, dg = 2 * (T4_DC + g);
+    int off = n2 * tor_ld(n2);
+    *off_depth = off;
+    for (int k = 1; k <= g; ++k) off += (dg - 2 * k) * tor_ld(dg - 2 * k);
+    *off_warp = off;
+    off += warps * T4_WARP_D2;
+    return (size_t)off * sizeof(double2) + 2 * T4_MAXW * sizeof(double);
+}
+
+__global__ void __launch_bounds__(32 * T4_MAXW) tor4_kernel(TorParams p, int off_warp, double* __restrict__ partials) {
+    extern __shared__ __align__(16) double smem_tor[];
+    const int N = p.N, n2 = 2 * N, g = p.g, P = p.P;
+    const int dg = 2 * (T4_DC + g), ldT = tor_ld(n2);
+    const int threads = blockDim.x, nwarps = threads >> 5;
+    double2* S = reinterpret_cast<double2*>(smem_tor);
+    double* rootds = reinterpret_cast<double*>(S + off_warp + nwarps * T4_WARP_D2);     // (det, sgn) of the collected roots
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double2* W = S + off_warp + warp * T4_WARP_D2;
+
+    // eliminate the leading mode of view (V, ld, dim) into (Q, ldq) with all threads (eliminate_into for a runtime CTA size)
+    auto eliminate = [&](const double2* V, int ld, int dim, double2* Q, int ldq) -> double {
+        __syncthreads();
+        const double2 e = V[ld];
+        double i1, i2, d1d2;
+        pivot_inverses(V[0].x, V[ld + 1].x, e, i1, i2, d1d2);
+        const int cd = dim - 2, tri = cd * (cd + 1) / 2;
+        for (int el = tid; el < tri; el += threads) {
+            int r, c;
+            tri_decode(el, r, c);
+            Q[r * ldq + c] = schur_entry(V, ld, r + 2, c + 2, e, i1, i2);
+        }
+        __syncthreads();
+        return d1d2;
+    };
+
+    dd acc = {0.0, 0.0};
+    const uint64_t ngroups_first = p.p0 >> g, ngroups_last = (p.p1 + (1ull << g) - 1) >> g;
+    for (uint64_t grp = ngroups_first + blockIdx.x; grp < ngroups_last; grp += gridDim.x) {
+        // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0), in place on T
+        __syncthreads();
+        for (int idx = tid; idx < n2 * n2; idx += threads) S[(idx / n2) * ldT + idx % n2] = p.B[idx];
+        __syncthreads();
+        double det0 = 1.0, sgn0 = 1.0;
+        const int lead = P - g;
+        for (int i = 0; i < lead; ++i) {
+            const bool inc = (grp >> (lead - 1 - i)) & 1ull;
+            double2* V = S + 2 * i * (ldT + 1);
+            if (inc) det0 *= eliminate(V, ldT, n2 - 2 * i, V + 2 * (ldT + 1), ldT);
+            else sgn0 = -sgn0;
+        }
+        // ---- phase B: the 2^g prefixes of this group, depth-first; roots are handed to the warps nwarps at a time
+        int nptr[TOR_MAXG + 1], nld[TOR_MAXG + 1];
+        double ndet[TOR_MAXG + 1], nsgn[TOR_MAXG + 1];
+        nptr[0] = 2 * lead * (ldT + 1); nld[0] = ldT; ndet[0] = det0; nsgn[0] = sgn0;
+#pragma unroll
+        for (int k = 1; k <= TOR_MAXG; ++k) { nptr[k] = 0; nld[k] = 1; ndet[k] = 1.0; nsgn[k] = 1.0; }
+        int cur = -1, nroots = 0;
+        for (int sub = 0; sub < (1 << g); ++sub) {
+            const uint64_t pfx = (grp << g) + sub;
+            const bool live = pfx >= p.p0 && pfx < p.p1;
+            if (live) {
+                const int first = cur < 0 ? 0 : g - (32 - __clz(sub ^ cur));
+                cur = sub;
+                int dbuf = p.off_depth;
+#pragma unroll
+                for (int lvl = 0; lvl < TOR_MAXG; ++lvl) {
+                    if (lvl < g) {
+                        const int dim = dg - 2 * lvl, cdim = dim - 2, cld = tor_ld(cdim);
+                        if (lvl >= first) {
+                            const bool inc = (sub >> (g - 1 - lvl)) & 1;
+                            if (inc) {
+                                ndet[lvl + 1] = ndet[lvl] * eliminate(S + nptr[lvl], nld[lvl], dim, S + dbuf, cld);
+                                nsgn[lvl + 1] = nsgn[lvl];
+                                nptr[lvl + 1] = dbuf; nld[lvl + 1] = cld;
+                            } else {
+                                ndet[lvl + 1] = ndet[lvl]; nsgn[lvl + 1] = -nsgn[lvl];
+                                nptr[lvl + 1] = nptr[lvl] + 2 * (nld[lvl] + 1); nld[lvl + 1] = nld[lvl];
+                            }
+                        }
+                        dbuf += cdim * cld;
+                    }
+                }
+                int rptr = nptr[0], rld = nld[0];
+                double rdet = ndet[0], rsgn = nsgn[0];
+#pragma unroll
+                for (int k = 1; k <= TOR_MAXG; ++k)
+                    if (k == g) { rptr = nptr[k]; rld = nld[k]; rdet = ndet[k]; rsgn = nsgn[k]; }
+                // warp `nroots` copies the root (a view of CTA-level storage, stable until the next elimination's barrier)
+                if (warp == nroots) {
+                    const double2* R = S + rptr;
+                    double2* dst = W + T4_OFF_ROOT;
+                    for (int el = lane; el < t4_tri(2 * T4_DC, 0); el += 32) {
+                        int r, c;
+                        tri_decode(el, r, c);
+                        dst[el] = R[r * rld + c];
+                    }
+                    if (lane == 0) { rootds[2 * warp] = rdet; rootds[2 * warp + 1] = rsgn; }
+                    __syncwarp();
+                }
+                ++nroots;
+            }
+            if (nroots == nwarps || (sub == (1 << g) - 1 && nroots > 0)) {
+                if (warp < nroots) t4_expand(W, rootds[2 * warp], rootds[2 * warp + 1], acc, lane);
+                nroots = 0;
+                __syncthreads();     // the next root copies and eliminations may overwrite what the expansions read
+            }
+        }
+    }
+    __shared__ double red[T4_MAXW * 4];
+    cdd a2;
+    a2.re = acc;
+    a2.im = {0.0, 0.0};
+    block_reduce_store(a2, red, partials);
+}
+
 // DC modes expanded breadth-first, 2^g prefixes per CTA group; g shrinks if shared memory does not allow 5.
 static void tor_shape(int N, int aug, int* P, int* g, int* DC) {
     *DC = N < TOR_DC ? N : TOR_DC;
@@ -406,12 +693,46 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     int dev = 0, sms = 0;
     WB_CUDA(cudaGetDevice(&dev));
     if (device_sm_count(dev, &sms)) return WB200_ECUDA;
-    // small problems (or thin multi-GPU shards): fewer prefixes per CTA so that every SM gets a group
-    while (p.g > 0 && ((p1 - p0) >> p.g) < 2ull * (uint64_t)sms) --p.g;
-    const size_t shm = tor_smem_plan(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc);
     double2* dB = reinterpret_cast<double2*>(d_workspace);
     double* dpart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_workspace) + tor_ws_partials_offset(N));
     p.B = dB;
+    const char* ev4 = getenv("WB200_TOR_V4");
+    if (!aug && p.DC == T4_DC && ev4 && atoi(ev4)) {
+        // v4 EXPERIMENT (opt-in, WB200_TOR_V4=1): warp-autonomous tensor-core expansion (tor4_kernel).  Correct (same
+        // parity tests pass), but 2.5 ms at 2N = 48 against 1.22 ms for the breadth-first kernel below: the depth-first
+        // chain of a warp is one long latency chain (pivot loads -> FP64 division -> fragment vectors -> DMMA -> store,
+        // ~2000 cycles per elimination at 0.13 IPC) and shared memory only admits 7 such warps per SM
+        // (profiles/r02_ncu_tor48_v4.txt, profiles/r02_tor4_shapes.txt).  g group modes and as many warps as shared
+        // memory allows next to the CTA-level buffers; env WB200_TOR4_G / WB200_TOR4_W override.
+        const char* eg = getenv("WB200_TOR4_G");
+        const char* ew = getenv("WB200_TOR4_W");
+        int g = p.P < 4 ? p.P : 4;
+        if (eg) { g = atoi(eg); if (g > p.P) g = p.P; if (g > TOR_MAXG) g = TOR_MAXG; if (g < 0) g = 0; }
+        while (g > 0 && ((p1 - p0) >> g) < 2ull * (uint64_t)sms) --g;     // thin shards: every SM gets a group
+        int warps = ew ? atoi(ew) : T4_MAXW;
+        if (warps > T4_MAXW) warps = T4_MAXW;
+        if (warps < 1) warps = 1;
+        int off_warp = 0;
+        size_t shm = 0;
+        for (;;) {
+            shm = tor4_smem_plan(N, g, warps, &p.off_depth, &off_warp);
+            if (shm <= (size_t)226 * 1024) break;
+            if (warps > 4) --warps; else if (g > 0) --g; else break;
+        }
+        if (shm > (size_t)226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
+        p.g = g;
+        WB_CUDA(cudaFuncSetAttribute(tor4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        const uint64_t groups = ((p1 + (1ull << g) - 1) >> g) - (p0 >> g);
+        int grid = (int)(groups < (uint64_t)sms ? (groups ? groups : 1) : (uint64_t)sms);
+        tor_prep_kernel<<<8, 256, 0, st>>>(reinterpret_cast<const double2*>(dO), nullptr, N, dB);
+        tor4_kernel<<<grid, 32 * warps, shm, st>>>(p, off_warp, dpart);
+        final_reduce_kernel<<<1, 32, 0, st>>>(dpart, grid, d_out4);
+        WB_CUDA(cudaGetLastError());
+        return WB200_OK;
+    }
+    // small problems (or thin multi-GPU shards): fewer prefixes per CTA so that every SM gets a group
+    while (p.g > 0 && ((p1 - p0) >> p.g) < 2ull * (uint64_t)sms) --p.g;
+    const size_t shm = tor_smem_plan(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc);
     if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
     if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1, TOR_THREADS_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0, TOR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
