@@ -867,7 +867,11 @@ def gpu_arm(workload, args, env, steps, warmup, min_seconds=0.0):
 
     r_e2e = e2e_step()
     sync_all()
-    e2e_steps = steps if min_seconds <= 0 else int(min(4000, max(3, math.ceil(0.5 * min_seconds / max(1e-5, total_ms * 1e-3 / steps)))))
+    step_s = total_ms * 1e-3 / steps
+    if min_seconds > 0:
+        e2e_steps = int(min(4000, max(3, math.ceil(0.5 * min_seconds / max(1e-5, step_s)))))
+    else:            # multi-second steps: a handful of end-to-end calls is enough (the device-timed K steps stay exact)
+        e2e_steps = steps if step_s < 0.5 else min(steps, 5)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         r_e2e = e2e_step()

@@ -63,6 +63,46 @@ def test_repeated_vertices_vs_oracle(glynn, loops):
     assert _close(got, _dfma(A, D if loops else None, rpt, glynn)) < 1e-10
 
 
+@pytest.mark.parametrize("glynn", [True, False])
+def test_odd_totals_unpaired_vertex_vs_oracle(glynn):
+    """Odd photon totals (f_loop_odd, thewalrus/_hafnian.py:246-285): the loop row of the tensor-core kernel carries the
+    chain of the unpaired vertex's row next to the chain of D; every tile class with an odd vertex on top."""
+    rng = np.random.default_rng(17)
+    nv = 9
+    A, D = _mat(rng, nv)
+    rpt = rng.integers(0, 3, (600, nv)).astype(np.int32)
+    rpt = rpt[(rpt.sum(axis=1) % 2 == 1) & (rpt.sum(axis=1) <= 15)]
+    got = wb.quantum.lhaf_patterns(A, D, rpt, glynn)
+    want = co.lhaf_patterns(A, D, rpt, glynn)
+    assert _close(got, want) < 1e-10
+    assert _close(got, _dfma(A, D, rpt, glynn)) < 1e-10
+    for E in (3, 6, 8, 10, 12):      # 2E + 1 distinct vertices: E edges of one repetition and an unpaired vertex
+        nv2 = 2 * E + 4
+        A2, D2 = _mat(rng, nv2)
+        r2 = np.zeros((4, nv2), dtype=np.int32)
+        for b in range(4):
+            r2[b, rng.permutation(nv2)[: 2 * E + 1]] = 1
+        g2 = wb.quantum.lhaf_patterns(A2, D2, r2, glynn)
+        assert _close(g2, _dfma(A2, D2, r2, glynn)) < 1e-10, E
+        if E <= 8:
+            assert _close(g2, co.lhaf_patterns(A2, D2, r2, glynn)) < 1e-10, E
+
+
+def test_tor_v4_experiment_matches_default_kernel():
+    """The opt-in warp-autonomous torontonian (WB200_TOR_V4=1, rank-2 DMMA Schur complements) against the default kernel."""
+    import bench
+
+    for w in ("tor24", "tor32"):
+        _, _, O = bench.make_input(w)
+        want = wb.tor(O)
+        os.environ["WB200_TOR_V4"] = "1"
+        try:
+            got = wb.tor(O)
+        finally:
+            del os.environ["WB200_TOR_V4"]
+        assert abs(got - want) <= 1e-11 * abs(want), w
+
+
 def test_mixed_batch_even_odd_and_trivial_patterns():
     """Even patterns (DMMA classes), odd ones (DFMA fallback), N = 0 and N = 1 early exits in one call; ragged chunk tails."""
     rng = np.random.default_rng(11)

@@ -425,7 +425,8 @@ namespace wb {
 
 static_assert(PAT_NCLS == PD_NCLS + 1, "class table out of sync");
 __host__ __device__ inline int pat_class_of(int E, int N, int odd) {
-    if (odd >= 0 || N / 2 > PD_TMAX) return PD_NCLS;
+    // even and odd totals both run on the tensor-core kernel; the series order (N / 2, or N with an unpaired vertex) is bounded
+    if ((odd >= 0 ? N : N / 2) > PD_TMAX) return PD_NCLS;
     return pd_class(E);
 }
 

@@ -46,10 +46,11 @@ struct PatCfg {
     static constexpr int NT = TF + (TAIL ? 1 : 0);
     static constexpr int FRAG_D = NK * NT * 64;             // doubles in the fragment table
     static constexpr int PART_D = (PD_TMAX + 2) * 8 * 2;    // part[j][g] complex
-    static constexpr int P_D = (PD_TMAX + 2) * 4 * 2;       // P[k][q] complex
+    static constexpr int P_D = (PD_TMAX + 2) * 4 * 2;       // P[k][q] complex (power traces; loop terms; odd-row terms)
+    static constexpr int C_D = P_D;                         // series factors / coefficients: order <= PD_TMAX (odd totals: N <= PD_TMAX)
     static constexpr int DELTA_D = 4 * PD_EMAX;             // delta[q][e]
     static constexpr int INFO_D = 4 + 2 * PD_EMAX + PD_EMAX + PD_EMAX / 2;   // pre[4], stride[16] (u64), verts[32] int, reps[16] int
-    static constexpr int WARP_D = FRAG_D + PART_D + 3 * P_D + DELTA_D + INFO_D;
+    static constexpr int WARP_D = FRAG_D + PART_D + 3 * P_D + C_D + DELTA_D + INFO_D;   // the factors F reuse part[]
     // every warp carries its own pattern's fragment table: as many warps as fit in 227 KB, at most PD_WARPS
     static constexpr int FIT = (227 * 1024 - 1024) / (int)(sizeof(double) * WARP_D);
     static constexpr int WARPS = FIT < PD_WARPS ? FIT : PD_WARPS;
@@ -101,6 +102,29 @@ __device__ __forceinline__ void pat_advance(const HafRow<TF, TAIL>& w, HafY<TF, 
     }
 }
 
+// <X, Y> over this thread's slots, reduced over the four lanes of the row; X = W itself (SELF) or W of the partner
+// row (lane ^ 16).  Used by the loop row of patterns with an unpaired vertex, where half 0 carries the chain of D and
+// half 1 the chain of the odd vertex's row of A.
+template <int TF, bool TAIL, bool SELF>
+__device__ __forceinline__ void pat_inner(const HafRow<TF, TAIL>& w, const HafY<TF, TAIL>& y, double& sr, double& si) {
+    double s2r = 0.0, s2i = 0.0;
+    sr = si = 0.0;
+#pragma unroll
+    for (int tau = 0; tau < TF; ++tau) {
+        const double x0r = SELF ? w.wr[tau][0] : shfl_xor_d(w.wr[tau][0], 16), x0i = SELF ? w.wi[tau][0] : shfl_xor_d(w.wi[tau][0], 16);
+        const double x1r = SELF ? w.wr[tau][1] : shfl_xor_d(w.wr[tau][1], 16), x1i = SELF ? w.wi[tau][1] : shfl_xor_d(w.wi[tau][1], 16);
+        WB_CFMA(sr, si, x0r, x0i, y.yr[2 * tau], y.yi[2 * tau]);
+        WB_CFMA(s2r, s2i, x1r, x1i, y.yr[2 * tau + 1], y.yi[2 * tau + 1]);
+    }
+    if (TAIL) {
+        const double xr = SELF ? w.wtr : shfl_xor_d(w.wtr, 16), xi = SELF ? w.wti : shfl_xor_d(w.wti, 16);
+        WB_CFMA(sr, si, xr, xi, y.ytr, y.yti);
+    }
+    sr += s2r; si += s2i;
+    sr += shfl_xor_d(sr, 1); si += shfl_xor_d(si, 1);
+    sr += shfl_xor_d(sr, 2); si += shfl_xor_d(si, 2);
+}
+
 template <int TF, bool TAIL>
 __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kernel(PatParams p) {
     using C = PatCfg<TF, TAIL>;
@@ -111,9 +135,11 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
     double2* sfrag = reinterpret_cast<double2*>(wsm);
     double2* part = reinterpret_cast<double2*>(wsm + C::FRAG_D);     // part[j * 8 + g]: row-g share of tr(M^j)
     double* Pk = wsm + C::FRAG_D + C::PART_D;                         // P[k][q] complex
-    double* Lk = Pk + C::P_D;                                         // loop terms
-    double* Ck = Lk + C::P_D;                                         // series coefficients
-    double* delta = Ck + C::P_D;                                      // delta[q * PD_EMAX + e]
+    double* Lk = Pk + C::P_D;                                         // loop terms l_t
+    double* Ok = Lk + C::P_D;                                         // odd-row terms o_t (patterns with an unpaired vertex)
+    double* Fk = wsm + C::FRAG_D;                                     // series factors i a_i: reuse part[] (dead after the combine)
+    double* Ck = Ok + C::P_D;                                         // series coefficients
+    double* delta = Ck + C::C_D;                                      // delta[q * PD_EMAX + e]
     double* pre = delta + C::DELTA_D;                                 // prefactor of subset q
     unsigned long long* stride = reinterpret_cast<unsigned long long*>(pre + 4);   // mixed-radix stride of edge e
     int* verts = reinterpret_cast<int*>(stride + PD_EMAX);            // verts[e] = u_e, verts[E + e] = v_e
@@ -122,7 +148,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
     constexpr int NK = C::NK, NT = C::NT;
 
     long long cur_pat = -1;
-    int E = 0, T = 0, tp = 0;
+    int E = 0, T = 0, tp = 0, odd = -1, order = 0;
     unsigned long long steps = 0;
     const double2* Ap = p.A;
     const double2* Dp = p.D;
@@ -141,7 +167,8 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
         if (pat != cur_pat) {
             cur_pat = pat;
             const PatDesc* d = p.desc + pat;
-            E = d->E; T = d->N / 2; steps = d->steps;
+            E = d->E; T = d->N / 2; steps = d->steps; odd = d->odd;
+            order = odd >= 0 ? d->N : T;                     // series order: vertices for an odd total (f_loop_odd), pairs otherwise
             tp = TAIL ? E - 4 * TF : 0;
             Dp = (p.D && p.gidx) ? p.D + (size_t)__ldg(p.gidx + pat) * p.ldg : p.D;
             Ap = p.aidx ? p.A + (size_t)__ldg(p.aidx + pat) * p.lda * p.lda : p.A;
@@ -231,7 +258,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                 const bool dz = __shfl_sync(0xffffffffu, d0zero ? 1 : 0, lane & ~7) != 0;
                 if (e8 == 0) {
                     double pf = (((T - es) & 1) ? -1.0 : 1.0) * wt;      // (-1)^(N/2 - sum kept) prod C(r, kept)  (_hafnian.py:553-556)
-                    if (p.glynn && dz) pf *= 0.5;
+                    if (p.glynn && dz && odd < 0) pf *= 0.5;                 // Glynn halving of edge 0: only without an unpaired vertex (:557-559)
                     pre[q8] = (jj < je) ? pf : 0.0;
                 }
             }
@@ -254,9 +281,11 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                 HafRow<TF, TAIL> w;
                 HafY<TF, TAIL> y = {};
                 const int v = i + half * E;                                   // row index in A'' (vertex pair i)
-                const int vv = isD ? 0 : (half ? verts[PD_EMAX + i] : verts[i]);
+                // loop row: half 0 = D; half 1 = row `odd` of A (the unpaired vertex, f_loop_odd) or empty
+                const bool oddrow = isD && half == 1 && odd >= 0;
+                const int vv = isD ? (oddrow ? odd : 0) : (half ? verts[PD_EMAX + i] : verts[i]);
                 {
-                    const bool rowok = isD ? (half == 0) : true;
+                    const bool rowok = isD ? (half == 0 || oddrow) : true;
 #pragma unroll
                     for (int tau = 0; tau < TF; ++tau) {
 #pragma unroll
@@ -266,7 +295,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                             double2 a = make_double2(0.0, 0.0);
                             if (ok) {
                                 const int vc = r ? verts[PD_EMAX + iv] : verts[iv];
-                                a = isD ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.lda + vc);
+                                a = (isD && !oddrow) ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.lda + vc);
                             }
                             w.wr[tau][r] = a.x;
                             w.wi[tau][r] = a.y;
@@ -278,7 +307,7 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                         if (ok) {
                             const int iv = 4 * TF + (t >> 1);
                             const int vc = (t & 1) ? verts[PD_EMAX + iv] : verts[iv];
-                            const double2 a = isD ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.lda + vc);
+                            const double2 a = (isD && !oddrow) ? __ldg(Dp + vc) : __ldg(Ap + (size_t)vv * p.lda + vc);
                             w.wtr = a.x; w.wti = a.y;
                         }
                     }
@@ -304,11 +333,15 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                         }
                     }
                 } else {
-                    HafY<TF, TAIL> y0;  // l_1 = <Z_0, S Z_0>
+                    HafY<TF, TAIL> y0;  // l_1 = <Z_0, S Z_0>;  o_1 = <Z_0, S V_0> (V = chain of the odd vertex's row, half 1)
                     pat_advance<TF, TAIL, false, true>(w, y0, dl, dlt, orr, oi, er, ei);
                     y = y0;
-                    pat_advance<TF, TAIL, true, true>(w, y, dl, dlt, orr, oi, er, ei);
+                    pat_inner<TF, TAIL, true>(w, y, orr, oi);
                     if (t == 0 && half == 0) { Lk[(1 * 4 + q) * 2] = orr; Lk[(1 * 4 + q) * 2 + 1] = oi; }
+                    if (odd >= 0) {
+                        pat_inner<TF, TAIL, false>(w, y, er, ei);
+                        if (t == 0 && half == 1) { Ok[(1 * 4 + q) * 2] = er; Ok[(1 * 4 + q) * 2 + 1] = ei; }
+                    }
                 }
                 const int nsteps = isD ? nstepD : nprod;
                 for (int k = 1; k <= nsteps; ++k) {
@@ -338,11 +371,26 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                         } else {
                             pat_advance<TF, TAIL, false, false>(w, y, dl, dlt, orr, oi, er, ei);
                         }
-                    } else {  // l_(2k) = <Z_k, S Z_(k-1)>, l_(2k+1) = <Z_k, S Z_k>
+                    } else if (odd < 0) {  // l_(2k) = <Z_k, S Z_(k-1)>, l_(2k+1) = <Z_k, S Z_k>
                         pat_advance<TF, TAIL, true, true>(w, y, dl, dlt, orr, oi, er, ei);
                         if (t == 0 && half == 0) {
                             Lk[((2 * k) * 4 + q) * 2] = orr; Lk[((2 * k) * 4 + q) * 2 + 1] = oi;
                             Lk[((2 * k + 1) * 4 + q) * 2] = er; Lk[((2 * k + 1) * 4 + q) * 2 + 1] = ei;
+                        }
+                    } else {               // also o_(2k) = <Z_k, S V_(k-1)>, o_(2k+1) = <Z_k, S V_k>: the partner row's W against this row's Y
+                        double cr, ci, c2r, c2i;
+                        pat_inner<TF, TAIL, true>(w, y, orr, oi);
+                        pat_inner<TF, TAIL, false>(w, y, cr, ci);
+                        pat_advance<TF, TAIL, false, true>(w, y, dl, dlt, er, ei, c2r, c2i);      // y <- S w
+                        pat_inner<TF, TAIL, true>(w, y, er, ei);
+                        pat_inner<TF, TAIL, false>(w, y, c2r, c2i);
+                        if (t == 0 && half == 0) {
+                            Lk[((2 * k) * 4 + q) * 2] = orr; Lk[((2 * k) * 4 + q) * 2 + 1] = oi;
+                            Lk[((2 * k + 1) * 4 + q) * 2] = er; Lk[((2 * k + 1) * 4 + q) * 2 + 1] = ei;
+                        }
+                        if (t == 0 && half == 1) {
+                            Ok[((2 * k) * 4 + q) * 2] = cr; Ok[((2 * k) * 4 + q) * 2 + 1] = ci;
+                            Ok[((2 * k + 1) * 4 + q) * 2] = c2r; Ok[((2 * k + 1) * 4 + q) * 2 + 1] = c2i;
                         }
                     }
                 }
@@ -355,24 +403,54 @@ __global__ void __launch_bounds__(32 * PatCfg<TF, TAIL>::WARPS, 1) pat_dmma_kern
                 Pk[(j * 4 + qq) * 2] = a.x + b.x; Pk[(j * 4 + qq) * 2 + 1] = a.y + b.y;
             }
             __syncwarp();
-            // ---- coefficient [eta^T] of exp(sum_i a_i eta^i), a_i = p_i/(2i) (+ l_i/2): c_t = (1/t) sum_i i a_i c_(t-i)
-            if (t == 0 && half == 0) {
-                Ck[(0 * 4 + q) * 2] = 1.0; Ck[(0 * 4 + q) * 2 + 1] = 0.0;
-                for (int tt = 1; tt <= T; ++tt) {
+            // ---- series factors F_i = i a_i of exp(sum_i a_i eta^i).  Even total (f_loop, _hafnian.py:212-242): a_i = p_i/(2i) + l_i/2,
+            // order T.  Odd total (f_loop_odd, :246-285): a_1 = oddloop, a_(2t) = p_t/(2t) + l_t/2, a_(2t+1) = o_t, order N = 2T + 1.
+            {
+                const double2 oddloop = odd >= 0 ? __ldg(Dp + odd) : make_double2(0.0, 0.0);
+                for (int s = lane; s < order * 4; s += 32) {
+                    const int i = (s >> 2) + 1, qq = s & 3;
+                    double fr, fi;
+                    if (odd < 0) {
+                        fr = 0.5 * Pk[(i * 4 + qq) * 2]; fi = 0.5 * Pk[(i * 4 + qq) * 2 + 1];
+                        if (loop) { fr += 0.5 * i * Lk[(i * 4 + qq) * 2]; fi += 0.5 * i * Lk[(i * 4 + qq) * 2 + 1]; }
+                    } else if (i == 1) {
+                        fr = oddloop.x; fi = oddloop.y;
+                    } else if ((i & 1) == 0) {
+                        const int tt = i >> 1;
+                        fr = Pk[(tt * 4 + qq) * 2] + tt * Lk[(tt * 4 + qq) * 2]; fi = Pk[(tt * 4 + qq) * 2 + 1] + tt * Lk[(tt * 4 + qq) * 2 + 1];
+                    } else {
+                        const int tt = i >> 1;
+                        fr = i * Ok[(tt * 4 + qq) * 2]; fi = i * Ok[(tt * 4 + qq) * 2 + 1];
+                    }
+                    Fk[(i * 4 + qq) * 2] = fr; Fk[(i * 4 + qq) * 2 + 1] = fi;
+                }
+                if (lane < 4) { Ck[lane * 2] = 1.0; Ck[lane * 2 + 1] = 0.0; }
+                __syncwarp();
+            }
+            // ---- c_s = (1/s) sum_(i=1..s) F_i c_(s-i): the eight lanes of a subset (same q) split the sum over i and reduce by
+            // shuffles (a serial version costs ~30 cycles per term on one lane: 1200 terms at order 49)
+            {
+                const int l8 = half * 4 + t;
+                for (int sidx = 1; sidx <= order; ++sidx) {
                     double sr = 0.0, si = 0.0;
-                    for (int i = 1; i <= tt; ++i) {
-                        double fr = 0.5 * Pk[(i * 4 + q) * 2], fi = 0.5 * Pk[(i * 4 + q) * 2 + 1];
-                        if (loop) { fr += 0.5 * i * Lk[(i * 4 + q) * 2]; fi += 0.5 * i * Lk[(i * 4 + q) * 2 + 1]; }
-                        const double c_r = Ck[((tt - i) * 4 + q) * 2], c_i = Ck[((tt - i) * 4 + q) * 2 + 1];
+                    for (int i = 1 + l8; i <= sidx; i += 8) {
+                        const double fr = Fk[(i * 4 + q) * 2], fi = Fk[(i * 4 + q) * 2 + 1];
+                        const double c_r = Ck[((sidx - i) * 4 + q) * 2], c_i = Ck[((sidx - i) * 4 + q) * 2 + 1];
                         sr = fma(fr, c_r, sr); sr = fma(-fi, c_i, sr);
                         si = fma(fr, c_i, si); si = fma(fi, c_r, si);
                     }
-                    Ck[(tt * 4 + q) * 2] = sr / tt; Ck[(tt * 4 + q) * 2 + 1] = si / tt;
+                    sr += shfl_xor_d(sr, 1); si += shfl_xor_d(si, 1);
+                    sr += shfl_xor_d(sr, 2); si += shfl_xor_d(si, 2);
+                    sr += shfl_xor_d(sr, 16); si += shfl_xor_d(si, 16);
+                    if (l8 == 0) { Ck[(sidx * 4 + q) * 2] = sr / sidx; Ck[(sidx * 4 + q) * 2 + 1] = si / sidx; }
+                    __syncwarp();
                 }
-                const double pf = pre[q];
-                if (pf != 0.0) {
-                    dd_add(acc.re, pf * Ck[(T * 4 + q) * 2]);
-                    dd_add(acc.im, pf * Ck[(T * 4 + q) * 2 + 1]);
+                if (l8 == 0) {
+                    const double pf = pre[q];
+                    if (pf != 0.0) {
+                        dd_add(acc.re, pf * Ck[(order * 4 + q) * 2]);
+                        dd_add(acc.im, pf * Ck[(order * 4 + q) * 2 + 1]);
+                    }
                 }
             }
             __syncwarp();
