@@ -725,7 +725,7 @@ def gpu_arm(workload, args, env, steps, warmup, min_seconds=0.0):
         dA = torch.from_numpy(Ax.view(np.float64).reshape(-1)).to(dev)
         dD = torch.from_numpy(np.ascontiguousarray(np.diag(X)[x]).view(np.float64).reshape(-1)).to(dev) if kind == "lhaf" else None
         wsb = lib.wb200_hafnian_workspace_bytes(n)
-        launches_per_step = 3      # haf_prep, haf_dmma, final_reduce
+        launches_per_step = 2      # haf_dmma (builds its fragment table itself), final_reduce
     elif kind == "perm":
         dA = torch.from_numpy(np.ascontiguousarray(X).view(np.float64).reshape(-1)).to(dev)
         wsb = lib.wb200_perm_workspace_bytes(n)
@@ -744,9 +744,9 @@ def gpu_arm(workload, args, env, steps, warmup, min_seconds=0.0):
     elif kind == "brs":
         launches_per_step = 2      # brs_kernel, final reduction
     elif kind == "hsample":
-        launches_per_step = 4 * n  # one patterns call (prep, scan, main, final) per mode
+        launches_per_step = 9 * n  # per mode: shift, pattern build, prep, scan, ~3 class kernels, final, draw
     else:
-        launches_per_step = 4      # pat_prep, scan, pat_main (one per size class), pat_final
+        launches_per_step = 7      # pat_prep, scan, pat_dmma x4 (tile classes of E <= 10), pat_final
     host_entry = kind in ("gbs", "mtl", "brs", "hsample")   # *_host entry points: they time their own launches
     drawn = []
     ws = torch.empty((wsb + 7) // 8, dtype=torch.float64, device=dev)
