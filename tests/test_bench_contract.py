@@ -63,3 +63,12 @@ def test_headline_metric_and_inputs():
     assert O.shape == (48, 48) and np.allclose(O, O.conj().T) and np.all(np.linalg.eigvalsh(np.identity(48) - O) > 0)
     mu, cov, pats = bench.make_gbs_state(16, 1000, seed=3016)
     assert pats.shape == (1000, 16) and pats.sum(axis=1).max() <= 10 and cov.shape == (32, 32)
+
+
+def test_gbs_flop_models_are_consistent():
+    """Executed (useful) flops of the batched kernels are below the reference-algorithm equivalent (trace pairing and
+    un-expanded mixed-radix subsets) and scale with the number of patterns."""
+    M, mu, cov, pats, A, gamma, rpt = bench.gbs_inputs("gbs16", 2000)
+    ex, ref = bench.gbs_executed_flops(rpt), bench.gbs_reference_flops(pats)
+    assert 0 < ex < ref
+    assert np.isclose(bench.gbs_executed_flops(np.concatenate([rpt, rpt])), 2 * ex)
