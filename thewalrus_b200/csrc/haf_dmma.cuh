@@ -33,6 +33,50 @@ static inline void haf_shape(int m, int* TF, int* tail) {
 }
 
 
+// Fragment table, (kappa * NT + tile) * 32 + lane:
+//   standard tile taup: (Ar, Ai)[e_k, e_n], e_n = 4 taup + (ncol >> 1) + (ncol & 1) m
+//   tail tile        : (F1, F2) with column ncol <-> vertex u(ncol >> 1), output part ncol & 1:
+//                      re: (Ar, -Ai), im: (Ai, Ar)   so that  D += yr * F1 + yi * F2
+// Every CTA builds the table straight into its shared memory (it costs what copying a prebuilt table would, and
+// saves the separate prep launch of round 1: 3 us + a launch gap on a 40 us n = 24 call).
+__device__ __forceinline__ void haf_build_frag(const double* __restrict__ A, int n, int m, int TF, int tail,
+                                               double2* __restrict__ frag, int tid, int nthreads) {
+    const int tp = tail ? m - 4 * TF : 0;
+    const int NK = 2 * TF + (tail ? 1 : 0), NT = TF + (tail ? 1 : 0);
+    const int total = NK * NT * 32;
+    for (int idx = tid; idx < total; idx += nthreads) {
+        const int lane = idx & 31, pair = idx >> 5;
+        const int tile = pair % NT, kappa = pair / NT;
+        const int k = lane & 3, ncol = lane >> 2;
+        // K-packed tail chunk (one vertex pair in the tail, tp == 1): only positions 0, 1 of the chunk carry
+        // elements, so positions 2, 3 take the IMAGINARY parts of the same two elements and the step needs two
+        // DMMAs per tile for this chunk instead of four:  D_re += [yr | yi] . [Ar ; -Ai],  D_im += [yr | yi] . [Ai ; Ar]
+        const bool packk = tail && tp == 1 && kappa == 2 * TF;
+        const bool imag_slot = packk && k >= 2;
+        const int ek = haf_chunk_elem(kappa, packk ? (k & 1) : k, m, TF, tp);
+        double2 v = make_double2(0.0, 0.0);
+        if (ek >= 0) {
+            if (tile < TF) {
+                const int in = 4 * tile + (ncol >> 1);
+                if (in < m) {
+                    const int en = in + (ncol & 1) * m;
+                    const double ar = __ldg(A + 2 * ((size_t)ek * n + en)), ai = __ldg(A + 2 * ((size_t)ek * n + en) + 1);
+                    v = imag_slot ? make_double2(-ai, ar) : make_double2(ar, ai);
+                }
+            } else {
+                const int tq = ncol >> 1;
+                if ((tq >> 1) < tp) {
+                    const int en = 4 * TF + (tq >> 1) + (tq & 1) * m;
+                    const double ar = __ldg(A + 2 * ((size_t)ek * n + en)), ai = __ldg(A + 2 * ((size_t)ek * n + en) + 1);
+                    v = (ncol & 1) ? make_double2(ai, ar) : make_double2(ar, -ai);
+                    if (packk) v = make_double2(imag_slot ? v.y : v.x, 0.0);   // D += [yr | yi] . [F1 ; F2]
+                }
+            }
+        }
+        frag[idx] = v;
+    }
+}
+
 template <int TF, bool TAIL>
 struct HafRow {  // one 8-row panel slice held by a thread
     double wr[TF > 0 ? TF : 1][2], wi[TF > 0 ? TF : 1][2];

@@ -33,50 +33,6 @@
 
 namespace wb {
 
-// Fragment table, (kappa * NT + tile) * 32 + lane:
-//   standard tile taup: (Ar, Ai)[e_k, e_n], e_n = 4 taup + (ncol >> 1) + (ncol & 1) m
-//   tail tile        : (F1, F2) with column ncol <-> vertex u(ncol >> 1), output part ncol & 1:
-//                      re: (Ar, -Ai), im: (Ai, Ar)   so that  D += yr * F1 + yi * F2
-// Every CTA builds the table straight into its shared memory (it costs what copying a prebuilt table would, and
-// saves the separate prep launch of round 1: 3 us + a launch gap on a 40 us n = 24 call).
-__device__ __forceinline__ void haf_build_frag(const double* __restrict__ A, int n, int m, int TF, int tail,
-                                               double2* __restrict__ frag, int tid, int nthreads) {
-    const int tp = tail ? m - 4 * TF : 0;
-    const int NK = 2 * TF + (tail ? 1 : 0), NT = TF + (tail ? 1 : 0);
-    const int total = NK * NT * 32;
-    for (int idx = tid; idx < total; idx += nthreads) {
-        const int lane = idx & 31, pair = idx >> 5;
-        const int tile = pair % NT, kappa = pair / NT;
-        const int k = lane & 3, ncol = lane >> 2;
-        // K-packed tail chunk (one vertex pair in the tail, tp == 1): only positions 0, 1 of the chunk carry
-        // elements, so positions 2, 3 take the IMAGINARY parts of the same two elements and the step needs two
-        // DMMAs per tile for this chunk instead of four:  D_re += [yr | yi] . [Ar ; -Ai],  D_im += [yr | yi] . [Ai ; Ar]
-        const bool packk = tail && tp == 1 && kappa == 2 * TF;
-        const bool imag_slot = packk && k >= 2;
-        const int ek = haf_chunk_elem(kappa, packk ? (k & 1) : k, m, TF, tp);
-        double2 v = make_double2(0.0, 0.0);
-        if (ek >= 0) {
-            if (tile < TF) {
-                const int in = 4 * tile + (ncol >> 1);
-                if (in < m) {
-                    const int en = in + (ncol & 1) * m;
-                    const double ar = __ldg(A + 2 * ((size_t)ek * n + en)), ai = __ldg(A + 2 * ((size_t)ek * n + en) + 1);
-                    v = imag_slot ? make_double2(-ai, ar) : make_double2(ar, ai);
-                }
-            } else {
-                const int tq = ncol >> 1;
-                if ((tq >> 1) < tp) {
-                    const int en = 4 * TF + (tq >> 1) + (tq & 1) * m;
-                    const double ar = __ldg(A + 2 * ((size_t)ek * n + en)), ai = __ldg(A + 2 * ((size_t)ek * n + en) + 1);
-                    v = (ncol & 1) ? make_double2(ai, ar) : make_double2(ar, -ai);
-                    if (packk) v = make_double2(imag_slot ? v.y : v.x, 0.0);   // D += [yr | yi] . [F1 ; F2]
-                }
-            }
-        }
-        frag[idx] = v;
-    }
-}
-
 template <int TF, bool TAIL, int WARPS>
 struct HafCfg {
     static constexpr int NK = 2 * TF + (TAIL ? 1 : 0);
@@ -336,6 +292,9 @@ static int launch_haf(const double* dA, const double* dD, int n, int m, uint64_t
 
 constexpr int HAF_MAX_GRID = 4096;
 
+// hafnian_sym.cu: symmetric-half kernel for n = 48 / 50 (WB200_ENOSUP for other shapes)
+int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st);
+
 }  // namespace wb
 
 using namespace wb;
@@ -365,6 +324,17 @@ extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
     int grid = 1;
     int rc = WB200_ENOSUP;
+    {   // full-size hafnians of n = 48 / 50 without loops: only the tiles on and above the diagonal of every product
+        const char* es = getenv("WB200_HAF_SYM");
+        const bool want = !(es && atoi(es) == 0);
+        if (want && !dD && (n == 48 || n == 50) && ngroups >= 8ull * (uint64_t)sms) {
+            rc = haf_sym_launch(dA, n, j0, j1, partials, sms, &grid, st);
+            if (rc) return rc;
+            final_reduce_kernel<<<1, 32, 0, st>>>(partials, grid, d_out4);
+            WB_CUDA(cudaGetLastError());
+            return WB200_OK;
+        }
+    }
 #define WB_HAF_CASE(tf, tl) case (tf) * 2 + (tl): rc = launch_haf<tf, (tl) != 0>(dA, dD, n, m, j0, j1, partials, ngroups, sms, &grid, st); break;
     switch (TF * 2 + tail) {
         WB_HAF_CASE(1, 0) WB_HAF_CASE(2, 0) WB_HAF_CASE(3, 0) WB_HAF_CASE(4, 0)

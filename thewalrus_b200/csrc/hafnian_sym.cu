@@ -1,0 +1,387 @@
+// Hafnian, all edge repetitions 1, Glynn sieve — SYMMETRIC-HALF tensor-core kernel for n = 48 and n = 50.
+//
+// Same sum as haf_dmma_kernel (thewalrus/_hafnian.py:416-467 + charpoly.powertrace + f), same row-panel products
+// row c of B_(k+1) = (row c of B_k) S_j A'  on DMMA.8x8x4 with trace pairing.  What is new: B_k = M_j^(k-1) A' is
+// SYMMETRIC, so of every product only the tiles on and above the diagonal are computed:
+// the row panel of vertex pair i (tile tau_i = i / 4) computes the N-tiles tau' >= tau_i (+ the packed tail tile) and
+// the tiles below the diagonal are the transposes of what the other panels computed.  At n = 50 that is 96.5 tile
+// units per product and group instead of 162.5 (0.59 of the DMMAs).
+//
+// That couples the panels of a group: all of them must finish product k before any starts product k + 1, and every
+// panel needs entries other panels computed.  So the iterates of ONE group of four subsets live in shared memory
+// (4 x n x n complex = 160 KB at n = 50, next to the 46 KB fragment table of A') and the 12 warps of the CTA advance
+// that group together, two barriers per product: [all panels read their rows of B_k and compute] | barrier |
+// [write the computed tiles, directly and transposed] | barrier.  Each warp owns two row panels whose tile counts add
+// up to the same number (tau and 5 - tau: 6.5 - tau + tau + 1.5 = 8 tile units with the tail tile), so the warps are
+// balanced; the tail panel (vertex pair 24 at n = 50: one packed tile, everything else arrives by transposition) rides
+// along on warp 0.
+//
+// The power traces stay warp-local although no warp ever sees a whole row of B_(k+1): with U = B_a S, V = B_b,
+//     tr(M^(a+b)) = sum_(x,y) V[x][y] delta_x U[sigma(x)][y]
+// and the term of (y, x) equals the term of (x, y) (both B_a and B_b are symmetric), so every COMPUTED entry (x, y) of
+// a strictly-upper tile counts twice and the entries of the diagonal tiles once — the same partner-row inner products
+// as haf_advance, restricted to the computed tiles, with a weight.  (NumPy emulation of exactly this bookkeeping
+// against the oracle: 3e-15)
+//
+// Shape: TF = 6 full tiles (24 vertex pairs = 12 warps x 2 panels) with no tail (n = 48) or a one-pair packed tail
+// (n = 50).  Everything else, and the loop hafnian, stays on haf_dmma_kernel.
+#include <stdlib.h>
+#include "common.cuh"
+#include "haf_dmma.cuh"
+
+namespace wb {
+
+constexpr int HS_TF = 6;
+constexpr int HS_WARPS = 12;
+
+template <bool TAIL>
+struct HsCfg {
+    static constexpr int NK = 2 * HS_TF + (TAIL ? 1 : 0);
+    static constexpr int NT = HS_TF + (TAIL ? 1 : 0);
+    static constexpr int M = 4 * HS_TF + (TAIL ? 1 : 0);          // vertex pairs
+    static constexpr int N = 2 * M;
+    static constexpr int FRAG_D = NK * NT * 64;                    // doubles
+    static constexpr int STATE_D2 = 4 * N * N;                     // double2: state[q][row][col]
+    static constexpr int P_D = (M + 2) * 4 * 2;                    // P[j][q] complex (doubles)
+    static constexpr int TMP_D = 2 * 3 * HS_WARPS * 8 * 2;         // ptmp[parity][kind][warp][row] complex (doubles)
+    static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + 2 * P_D + TMP_D);
+};
+
+// sign mask of vertex pair p in subset jq: delta = +1 (bit set) -> 0, delta = -1 -> sign bit
+template <bool TAIL>
+__device__ __forceinline__ unsigned hs_sign(uint64_t jq, int p) {
+    return ((unsigned)(jq >> (HsCfg<TAIL>::M - 1 - p)) & 1u) ? 0u : 0x80000000u;
+}
+
+// One row of Y_k = B_k S, read just in time: chunk kap, position t of the lane.  Y_k[v][c] = delta_c B_k[v][sigma(c)], with
+// B_1 = A' (global memory, k = 1) or B_k in the shared-memory state.  Holding the row in registers (as haf_dmma_kernel
+// does) on top of the accumulators of two panels does not fit 168 registers.
+template <bool TAIL>
+struct HsY {
+    const double2* row;      // state row of this lane's (subset, vertex), or the row of A' as double2
+    uint64_t jq;
+    int t;
+    __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {
+        constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
+        if (kap < 2 * TF) {
+            const int tau = kap >> 1;
+            const double2 a = row[4 * tau + t + (1 - (kap & 1)) * m];
+            const unsigned s = hs_sign<TAIL>(jq, 4 * tau + t);
+            yr = flipsign(a.x, s); yi = flipsign(a.y, s);
+        } else {
+            yr = yi = 0.0;
+            if (TAIL && t < 2) {
+                const double2 a = row[4 * TF + (1 - (t & 1)) * m];
+                const unsigned s = hs_sign<TAIL>(jq, 4 * TF);
+                yr = flipsign(a.x, s); yi = flipsign(a.y, s);
+            }
+        }
+    }
+};
+
+// W <- Y * A' for the N-tiles tau' >= TAU (and the tail tile); TAU == HS_TF: the tail tile only.
+// The loop over the K tiles is deliberately NOT unrolled: fully unrolled, ptxas hoists some thirty 16-byte fragment
+// loads to the top of the block (130 registers) and spills the accumulators of the other panel.
+template <bool TAIL, int TAU>
+__device__ __forceinline__ void hs_step(const double2* __restrict__ sfrag, int lane, const HsY<TAIL>& y,
+                                        HafRow<HS_TF, TAIL>& w) {
+    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M;
+#pragma unroll
+    for (int tp = TAU; tp < TF; ++tp) {
+        w.wr[tp][0] = w.wr[tp][1] = 0.0;
+        w.wi[tp][0] = w.wi[tp][1] = 0.0;
+    }
+    w.wtr = w.wti = 0.0;
+    const double2* fr = sfrag + lane;
+    const double2* yp = y.row + y.t;
+    int sh = m - 1 - y.t;
+#pragma unroll 1
+    for (int tau = 0; tau < TF; ++tau) {
+        const unsigned s = ((unsigned)(y.jq >> sh) & 1u) ? 0u : 0x80000000u;
+        const double2 a0 = yp[m], a1 = yp[0];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
+#pragma unroll
+            for (int tp = TAU; tp < TF; ++tp) {
+                const double2 b = fr[tp * 32];
+                const double nbi = -b.y;
+                dmma884(w.wr[tp][0], w.wr[tp][1], ar, b.x);
+                dmma884(w.wi[tp][0], w.wi[tp][1], ar, b.y);
+                dmma884(w.wr[tp][0], w.wr[tp][1], ai, nbi);
+                dmma884(w.wi[tp][0], w.wi[tp][1], ai, b.x);
+            }
+            if (TAIL) {
+                const double2 b = fr[TF * 32];
+                dmma884(w.wtr, w.wti, ar, b.x);
+                dmma884(w.wtr, w.wti, ai, b.y);
+            }
+            fr += NT * 32;
+        }
+        yp += 4;
+        sh -= 4;
+    }
+    if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
+        double ar, ai;
+        y.get(2 * TF, ar, ai);
+        const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
+        const double ap = (lane & 2) ? yi2 : ar;
+#pragma unroll
+        for (int tp = TAU; tp < TF; ++tp) {
+            const double2 b = fr[tp * 32];
+            dmma884(w.wr[tp][0], w.wr[tp][1], ap, b.x);
+            dmma884(w.wi[tp][0], w.wi[tp][1], ap, b.y);
+        }
+        const double2 b = fr[TF * 32];
+        dmma884(w.wtr, w.wti, ap, b.x);
+    }
+}
+
+// Local pairing sums of one panel over its computed tiles: odd = <W(partner row), Y_old(own row)>, even = the same with
+// Y_new = S W(own row); strictly-upper tiles weigh 2, the diagonal tile 1 (see the header).  Not reduced over lanes.
+template <bool TAIL, int TAU>
+__device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL>& y,
+                                           double& orr, double& oi, double& er, double& ei) {
+    constexpr int TF = HS_TF;
+    orr = oi = er = ei = 0.0;
+#pragma unroll
+    for (int tau = TAU; tau < TF; ++tau) {
+        const double wgt = tau == TAU ? 1.0 : 2.0;        // strictly-upper tiles count twice (their transposes are never computed)
+        const double x0r = wgt * shfl_xor_d(w.wr[tau][0], 16), x0i = wgt * shfl_xor_d(w.wi[tau][0], 16);
+        const double x1r = wgt * shfl_xor_d(w.wr[tau][1], 16), x1i = wgt * shfl_xor_d(w.wi[tau][1], 16);
+        const unsigned s = hs_sign<TAIL>(y.jq, 4 * tau + y.t);
+        double yr, yi;
+        y.get(2 * tau, yr, yi);
+        WB_CFMA(orr, oi, x0r, x0i, yr, yi);
+        y.get(2 * tau + 1, yr, yi);
+        WB_CFMA(orr, oi, x1r, x1i, yr, yi);
+        WB_CFMA(er, ei, x0r, x0i, flipsign(w.wr[tau][1], s), flipsign(w.wi[tau][1], s));   // Y_new, chunk 2 tau
+        WB_CFMA(er, ei, x1r, x1i, flipsign(w.wr[tau][0], s), flipsign(w.wi[tau][0], s));   // Y_new, chunk 2 tau + 1
+    }
+    if (TAIL) {
+        const double wgt = TAU == TF ? 1.0 : 2.0;
+        const double xr = wgt * shfl_xor_d(w.wtr, 16), xi = wgt * shfl_xor_d(w.wti, 16);
+        const unsigned smt = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
+        const double nr = flipsign(shfl_xor_d(w.wtr, 1), smt), ni = flipsign(shfl_xor_d(w.wti, 1), smt);
+        double ytr, yti;
+        y.get(2 * TF, ytr, yti);
+        WB_CFMA(orr, oi, xr, xi, ytr, yti);
+        WB_CFMA(er, ei, xr, xi, nr, ni);
+    }
+}
+
+// One product step of one row panel (vertex pair i, tile TAU): load the rows of Y_k = B_k S (from A' at k = 1, else
+// from the shared-memory state), compute the tiles >= TAU, add the panel's trace shares to the per-lane sums.
+template <bool TAIL, int TAU>
+__device__ __forceinline__ void hs_panel(const double2* __restrict__ sfrag, const double2* __restrict__ state, const double* __restrict__ A,
+                                         int i, int k, bool needO, bool needE, uint64_t jq, int lane,
+                                         HafRow<HS_TF, TAIL>& w, double (&tr)[6]) {
+    using C = HsCfg<TAIL>;
+    constexpr int TF = HS_TF, m = C::M, n = C::N;
+    const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
+    const int v = i + half * m;
+    // k = 1: B_1 = A' (read through the read-only path); k > 1: the shared-memory state
+    HsY<TAIL> y;
+    y.row = (k == 1) ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + ((size_t)q * n + v) * n;
+    y.jq = jq; y.t = t;
+    hs_step<TAIL, TAU>(sfrag, lane, y, w);
+    // trace shares of this panel: delta of the panel's vertex pair
+    const double rs = ((jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;
+    {   // tr(M^(k+1)) share: element sigma(v) of this row, in the diagonal tile
+        const bool in_tail = TAIL && (i >= 4 * TF);
+        const int own_t = in_tail ? (1 - half) : (i & 3);
+        if (t == own_t) {
+            double dr, di;
+            if (in_tail) { dr = w.wtr; di = w.wti; }
+            else { dr = half ? w.wr[TAU < TF ? TAU : 0][0] : w.wr[TAU < TF ? TAU : 0][1]; di = half ? w.wi[TAU < TF ? TAU : 0][0] : w.wi[TAU < TF ? TAU : 0][1]; }
+            tr[0] += rs * dr; tr[1] += rs * di;
+        }
+    }
+    if (needO || needE) {
+        double orr, oi, er, ei;
+        hs_pairing<TAIL, TAU>(w, y, orr, oi, er, ei);
+        tr[2] += rs * orr; tr[3] += rs * oi;
+        tr[4] += rs * er; tr[5] += rs * ei;
+    }
+}
+
+// write the computed tiles of a panel: directly, and transposed for the strictly-upper tiles
+template <bool TAIL, int TAU>
+__device__ __forceinline__ void hs_store(double2* __restrict__ state, int i, int lane, const HafRow<HS_TF, TAIL>& w) {
+    using C = HsCfg<TAIL>;
+    constexpr int TF = HS_TF, m = C::M, n = C::N;
+    const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
+    const int v = i + half * m;
+    double2* base = state + (size_t)q * n * n;
+#pragma unroll
+    for (int tau = TAU; tau < TF; ++tau) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int c = 4 * tau + t + r * m;
+            const double2 val = make_double2(w.wr[tau][r], w.wi[tau][r]);
+            base[(size_t)v * n + c] = val;
+            if (tau > TAU) base[(size_t)c * n + v] = val;
+        }
+    }
+    if (TAIL && (t >> 1) < 1) {
+        const int c = 4 * TF + (t & 1) * m;
+        const double2 val = make_double2(w.wtr, w.wti);
+        base[(size_t)v * n + c] = val;
+        if (TAU < TF) base[(size_t)c * n + v] = val;
+    }
+}
+
+// one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ the tail panel on warp 0)
+template <bool TAIL, int RHO>
+__device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
+                                             int sub, int k, bool needO, bool needE, bool store, uint64_t jq,
+                                             int lane, int warp, double (&tr)[6]) {
+    constexpr int TF = HS_TF;
+    const int iA = 4 * RHO + sub, iB = 4 * (TF - 1 - RHO) + sub;
+    HafRow<TF, TAIL> wA, wB, wC;
+    const bool tailpanel = TAIL && warp == 0;     // the short panels first: fewer accumulators live during the long one
+    if (tailpanel) hs_panel<TAIL, TF>(sfrag, state, A, 4 * TF, k, needO, needE, jq, lane, wC, tr);
+    hs_panel<TAIL, TF - 1 - RHO>(sfrag, state, A, iB, k, needO, needE, jq, lane, wB, tr);
+    hs_panel<TAIL, RHO>(sfrag, state, A, iA, k, needO, needE, jq, lane, wA, tr);
+    __syncthreads();                       // every panel has read its rows of B_k
+    if (store) {
+        hs_store<TAIL, RHO>(state, iA, lane, wA);
+        hs_store<TAIL, TF - 1 - RHO>(state, iB, lane, wB);
+        if (tailpanel) hs_store<TAIL, TF>(state, 4 * TF, lane, wC);
+    }
+}
+
+template <bool TAIL>
+__global__ void __launch_bounds__(32 * HS_WARPS, 1)
+haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials) {
+    using C = HsCfg<TAIL>;
+    constexpr int TF = HS_TF, m = C::M, n = C::N;
+    extern __shared__ __align__(16) double smem[];
+    double2* sfrag = reinterpret_cast<double2*>(smem);
+    double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D);
+    double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[j][q] complex; touched by warp 0 only
+    double* Ck = Pk + C::P_D;
+    double* ptmp = Ck + C::P_D;                                        // [parity][kind][warp][row] complex
+    haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
+    const int rho = warp >> 2, sub = warp & 3;
+    const int nprod = (m - 1) >> 1, K = nprod + 1;
+    const uint64_t ngroups = (j1 - j0 + 3) >> 2;
+
+    cdd acc;
+    acc.re = {0.0, 0.0};
+    acc.im = {0.0, 0.0};
+
+    for (uint64_t G = blockIdx.x; G < ngroups; G += gridDim.x) {
+        const uint64_t jq = j0 + 4 * G + q;
+        if (warp == 0) {
+            // tr(M^1) = sum_r delta_r A'[r][sigma(r)] = 2 sum_i delta_i A'[i][i + m]; P is private to warp 0
+            for (int s = lane; s < (m + 2) * 4; s += 32) { Pk[2 * s] = 0.0; Pk[2 * s + 1] = 0.0; }
+            __syncwarp();
+            if (lane < 4) {
+                const uint64_t jj = j0 + 4 * G + lane;
+                double sr = 0.0, si = 0.0;
+                for (int i = 0; i < m; ++i) {
+                    const double d = ((jj >> (m - 1 - i)) & 1ull) ? 2.0 : -2.0;
+                    sr += d * __ldg(A + 2 * ((size_t)i * n + i + m));
+                    si += d * __ldg(A + 2 * ((size_t)i * n + i + m) + 1);
+                }
+                Pk[(1 * 4 + lane) * 2] = sr; Pk[(1 * 4 + lane) * 2 + 1] = si;
+            }
+            __syncwarp();
+        }
+        for (int k = 1; k <= nprod; ++k) {
+            const bool needO = (2 * k + 1 > K) && (2 * k + 1 <= m);
+            const bool needE = (2 * k + 2 > K) && (2 * k + 2 <= m);
+            double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            const bool store = k < nprod;
+            if (rho == 0) hs_warp_step<TAIL, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tr);
+            else if (rho == 1) hs_warp_step<TAIL, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tr);
+            else hs_warp_step<TAIL, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tr);
+            // per-row trace shares of this warp: reduce over the four lanes of a row, park them for warp 0
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                tr[c] += shfl_xor_d(tr[c], 1);
+                tr[c] += shfl_xor_d(tr[c], 2);
+            }
+            if (t == 0) {
+                double* pt = ptmp + (size_t)(k & 1) * (3 * HS_WARPS * 8 * 2);
+#pragma unroll
+                for (int kind = 0; kind < 3; ++kind) {
+                    pt[((kind * HS_WARPS + warp) * 8 + g) * 2] = tr[2 * kind];
+                    pt[((kind * HS_WARPS + warp) * 8 + g) * 2 + 1] = tr[2 * kind + 1];
+                }
+            }
+            __syncthreads();                   // B_(k+1) is complete in shared memory; so are this step's trace shares
+            if (warp == 0 && lane < 12) {      // fixed-order sum over warps and the two rows of each subset
+                const int kind = lane >> 2, qq = lane & 3;
+                const double* pt = ptmp + (size_t)(k & 1) * (3 * HS_WARPS * 8 * 2);
+                double sr = 0.0, si = 0.0;
+                for (int wv = 0; wv < HS_WARPS; ++wv) {
+                    const double* e0 = pt + ((kind * HS_WARPS + wv) * 8 + qq) * 2;
+                    const double* e1 = pt + ((kind * HS_WARPS + wv) * 8 + qq + 4) * 2;
+                    sr += e0[0] + e1[0]; si += e0[1] + e1[1];
+                }
+                const int j = kind == 0 ? k + 1 : (kind == 1 ? 2 * k + 1 : 2 * k + 2);
+                const bool want = kind == 0 || (kind == 1 ? needO : needE);
+                if (want && j <= m) { Pk[(j * 4 + qq) * 2] = sr; Pk[(j * 4 + qq) * 2 + 1] = si; }
+            }
+        }
+        // ---- series c_t = (1/t) sum_i (p_i / 2) c_(t-i), the eight lanes of a subset split the sum (warp 0 only)
+        if (warp == 0) {
+            __syncwarp();
+            if (lane < 4) { Ck[lane * 2] = 1.0; Ck[lane * 2 + 1] = 0.0; }
+            __syncwarp();
+            const int l8 = half * 4 + t;
+            for (int sidx = 1; sidx <= m; ++sidx) {
+                double sr = 0.0, si = 0.0;
+                for (int i = 1 + l8; i <= sidx; i += 8) {
+                    const double fr = 0.5 * Pk[(i * 4 + q) * 2], fi = 0.5 * Pk[(i * 4 + q) * 2 + 1];
+                    const double c_r = Ck[((sidx - i) * 4 + q) * 2], c_i = Ck[((sidx - i) * 4 + q) * 2 + 1];
+                    sr = fma(fr, c_r, sr); sr = fma(-fi, c_i, sr);
+                    si = fma(fr, c_i, si); si = fma(fi, c_r, si);
+                }
+                sr += shfl_xor_d(sr, 1); si += shfl_xor_d(si, 1);
+                sr += shfl_xor_d(sr, 2); si += shfl_xor_d(si, 2);
+                sr += shfl_xor_d(sr, 16); si += shfl_xor_d(si, 16);
+                if (l8 == 0) { Ck[(sidx * 4 + q) * 2] = sr / sidx; Ck[(sidx * 4 + q) * 2 + 1] = si / sidx; }
+                __syncwarp();
+            }
+            if (l8 == 0 && jq < j1) {
+                const int nk = __popcll(jq);
+                const double sg = ((m - nk) & 1) ? -1.0 : 1.0;
+                dd_add(acc.re, sg * Ck[(m * 4 + q) * 2]);
+                dd_add(acc.im, sg * Ck[(m * 4 + q) * 2 + 1]);
+            }
+            __syncwarp();
+        }
+    }
+    __shared__ double red[HS_WARPS * 4];
+    block_reduce_store(acc, red, partials);
+}
+
+template <bool TAIL>
+static int launch_haf_sym(const double* dA, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
+    using C = HsCfg<TAIL>;
+    auto kern = haf_sym_kernel<TAIL>;
+    const uint64_t ngroups = (j1 - j0 + 3) >> 2;
+    const int grid = (int)(ngroups < (uint64_t)sms ? (ngroups ? ngroups : 1) : (uint64_t)sms);
+    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
+    kern<<<grid, 32 * HS_WARPS, C::BYTES, st>>>(dA, j0, j1, partials);
+    WB_CUDA(cudaGetLastError());
+    *grid_out = grid;
+    return WB200_OK;
+}
+
+// Used by wb200_hafnian_dev for n = 48 / 50 without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel).
+// Returns WB200_ENOSUP when the shape is not one of the two this kernel is built for.
+int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
+    if (n == 48) return launch_haf_sym<false>(dA, j0, j1, partials, sms, grid_out, st);
+    if (n == 50) return launch_haf_sym<true>(dA, j0, j1, partials, sms, grid_out, st);
+    return WB200_ENOSUP;
+}
+
+}  // namespace wb
