@@ -43,7 +43,7 @@ struct HsCfg {
     static constexpr int FRAG_D = NK * NT * 64;                    // doubles
     static constexpr int STATE_D2 = 4 * N * N;                     // double2: state[q][row][col]
     static constexpr int P_D = (M + 2) * 4 * 2;                    // P[j][q] complex (doubles)
-    static constexpr int TMP_D = 2 * 3 * HS_WARPS * 8 * 2;         // ptmp[parity][kind][warp][row] complex (doubles)
+    static constexpr int TMP_D = 3 * HS_WARPS * 8 * 2;             // ptmp[kind][warp][row] complex (doubles)
     static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + 2 * P_D + TMP_D);
 };
 
@@ -92,13 +92,18 @@ __device__ __forceinline__ void hs_step(const double2* __restrict__ sfrag, int l
         w.wi[tp][0] = w.wi[tp][1] = 0.0;
     }
     w.wtr = w.wti = 0.0;
+    double u2r = 0.0, u2i = 0.0;                 // second tail accumulator: the tail-only panel would be one dependent chain
     const double2* fr = sfrag + lane;
     const double2* yp = y.row + y.t;
     int sh = m - 1 - y.t;
+    double2 a0 = yp[m], a1 = yp[0];              // the row's entries of the next K tile are fetched one iteration ahead
 #pragma unroll 1
     for (int tau = 0; tau < TF; ++tau) {
         const unsigned s = ((unsigned)(y.jq >> sh) & 1u) ? 0u : 0x80000000u;
-        const double2 a0 = yp[m], a1 = yp[0];
+        // next K tile; after the last one: the tail element of lanes t = 0, 1 (an address every lane may read)
+        const bool last = tau == TF - 1;
+        const double2 n0 = (!last || TAIL) ? yp[last ? 4 + (1 - (y.t & 1)) * m - y.t : 4 + m] : make_double2(0.0, 0.0);
+        const double2 n1 = !last ? yp[4] : n0;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
@@ -114,16 +119,18 @@ __device__ __forceinline__ void hs_step(const double2* __restrict__ sfrag, int l
             if (TAIL) {
                 const double2 b = fr[TF * 32];
                 dmma884(w.wtr, w.wti, ar, b.x);
-                dmma884(w.wtr, w.wti, ai, b.y);
+                if (TAU == TF) dmma884(u2r, u2i, ai, b.y);
+                else dmma884(w.wtr, w.wti, ai, b.y);
             }
             fr += NT * 32;
         }
+        a0 = n0; a1 = n1;
         yp += 4;
         sh -= 4;
     }
     if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
-        double ar, ai;
-        y.get(2 * TF, ar, ai);
+        const unsigned s = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
+        const double ar = (y.t < 2) ? flipsign(a0.x, s) : 0.0, ai = (y.t < 2) ? flipsign(a0.y, s) : 0.0;
         const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
         const double ap = (lane & 2) ? yi2 : ar;
 #pragma unroll
@@ -134,6 +141,97 @@ __device__ __forceinline__ void hs_step(const double2* __restrict__ sfrag, int l
         }
         const double2 b = fr[TF * 32];
         dmma884(w.wtr, w.wti, ap, b.x);
+        if (TAU == TF) { w.wtr += u2r; w.wti += u2i; }
+    }
+}
+
+// The two panels of a warp (tiles RHO and 5 - RHO) in ONE pass over K: the panel of the later tile needs a subset of the
+// fragments of the other, so every 16-byte fragment load feeds both, and the DMMAs of two independent panels interleave
+// (a one-tile panel alone is a chain of dependent DMMAs).
+template <bool TAIL, int RHO>
+__device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<TAIL>& yA, const HsY<TAIL>& yB,
+                                         HafRow<HS_TF, TAIL>& wA, HafRow<HS_TF, TAIL>& wB) {
+    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, TB = TF - 1 - RHO;
+#pragma unroll
+    for (int tp = RHO; tp < TF; ++tp) {
+        wA.wr[tp][0] = wA.wr[tp][1] = 0.0;
+        wA.wi[tp][0] = wA.wi[tp][1] = 0.0;
+    }
+#pragma unroll
+    for (int tp = TB; tp < TF; ++tp) {
+        wB.wr[tp][0] = wB.wr[tp][1] = 0.0;
+        wB.wi[tp][0] = wB.wi[tp][1] = 0.0;
+    }
+    wA.wtr = wA.wti = 0.0;
+    wB.wtr = wB.wti = 0.0;
+    const double2* fr = sfrag + lane;
+    const double2* ypA = yA.row + yA.t;
+    const double2* ypB = yB.row + yA.t;
+    int sh = m - 1 - yA.t;
+    double2 a0 = ypA[m], a1 = ypA[0], c0 = ypB[m], c1 = ypB[0];     // fetched one iteration ahead
+#pragma unroll 1
+    for (int tau = 0; tau < TF; ++tau) {
+        const unsigned s = ((unsigned)(yA.jq >> sh) & 1u) ? 0u : 0x80000000u;
+        // next K tile; after the last one: the tail element of lanes t = 0, 1 (an address every lane may read)
+        const bool last = tau == TF - 1;
+        const int o0 = last ? 4 + (1 - (yA.t & 1)) * m - yA.t : 4 + m;
+        double2 n0 = make_double2(0.0, 0.0), n1 = n0, d0 = n0, d1 = n0;
+        if (!last || TAIL) { n0 = ypA[o0]; d0 = ypB[o0]; }
+        if (!last) { n1 = ypA[4]; d1 = ypB[4]; }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
+            const double cr = flipsign(h ? c1.x : c0.x, s), ci = flipsign(h ? c1.y : c0.y, s);
+#pragma unroll
+            for (int tp = RHO; tp < TF; ++tp) {
+                const double2 b = fr[tp * 32];
+                const double nbi = -b.y;
+                dmma884(wA.wr[tp][0], wA.wr[tp][1], ar, b.x);
+                dmma884(wA.wi[tp][0], wA.wi[tp][1], ar, b.y);
+                if (tp >= TB) {
+                    dmma884(wB.wr[tp][0], wB.wr[tp][1], cr, b.x);
+                    dmma884(wB.wi[tp][0], wB.wi[tp][1], cr, b.y);
+                }
+                dmma884(wA.wr[tp][0], wA.wr[tp][1], ai, nbi);
+                dmma884(wA.wi[tp][0], wA.wi[tp][1], ai, b.x);
+                if (tp >= TB) {
+                    dmma884(wB.wr[tp][0], wB.wr[tp][1], ci, nbi);
+                    dmma884(wB.wi[tp][0], wB.wi[tp][1], ci, b.x);
+                }
+            }
+            if (TAIL) {
+                const double2 b = fr[TF * 32];
+                dmma884(wA.wtr, wA.wti, ar, b.x);
+                dmma884(wB.wtr, wB.wti, cr, b.x);
+                dmma884(wA.wtr, wA.wti, ai, b.y);
+                dmma884(wB.wtr, wB.wti, ci, b.y);
+            }
+            fr += NT * 32;
+        }
+        a0 = n0; a1 = n1; c0 = d0; c1 = d1;
+        ypA += 4; ypB += 4;
+        sh -= 4;
+    }
+    if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
+        const bool own = yA.t < 2;
+        const unsigned s = own ? hs_sign<TAIL>(yA.jq, 4 * TF) : 0u;
+        const double ar = own ? flipsign(a0.x, s) : 0.0, ai = own ? flipsign(a0.y, s) : 0.0;
+        const double cr = own ? flipsign(c0.x, s) : 0.0, ci = own ? flipsign(c0.y, s) : 0.0;
+        const double ai2 = __shfl_sync(0xffffffffu, ai, lane & ~2), ci2 = __shfl_sync(0xffffffffu, ci, lane & ~2);
+        const double ap = (lane & 2) ? ai2 : ar, cp = (lane & 2) ? ci2 : cr;
+#pragma unroll
+        for (int tp = RHO; tp < TF; ++tp) {
+            const double2 b = fr[tp * 32];
+            dmma884(wA.wr[tp][0], wA.wr[tp][1], ap, b.x);
+            dmma884(wA.wi[tp][0], wA.wi[tp][1], ap, b.y);
+            if (tp >= TB) {
+                dmma884(wB.wr[tp][0], wB.wr[tp][1], cp, b.x);
+                dmma884(wB.wi[tp][0], wB.wi[tp][1], cp, b.y);
+            }
+        }
+        const double2 b = fr[TF * 32];
+        dmma884(wA.wtr, wA.wti, ap, b.x);
+        dmma884(wB.wtr, wB.wti, cp, b.x);
     }
 }
 
@@ -170,23 +268,27 @@ __device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const H
     }
 }
 
-// One product step of one row panel (vertex pair i, tile TAU): load the rows of Y_k = B_k S (from A' at k = 1, else
-// from the shared-memory state), compute the tiles >= TAU, add the panel's trace shares to the per-lane sums.
-template <bool TAIL, int TAU>
-__device__ __forceinline__ void hs_panel(const double2* __restrict__ sfrag, const double2* __restrict__ state, const double* __restrict__ A,
-                                         int i, int k, bool needO, bool needE, uint64_t jq, int lane,
-                                         HafRow<HS_TF, TAIL>& w, double (&tr)[6]) {
+// the rows of Y_k = B_k S of a panel (vertex pair i) as seen by this lane: from A' at k = 1 (B_1 = A', read through the
+// generic path), else from the shared-memory state
+template <bool TAIL>
+__device__ __forceinline__ HsY<TAIL> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int i, int k, uint64_t jq, int lane) {
     using C = HsCfg<TAIL>;
-    constexpr int TF = HS_TF, m = C::M, n = C::N;
-    const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
+    constexpr int m = C::M, n = C::N;
+    const int g = lane >> 2, q = g & 3, half = g >> 2;
     const int v = i + half * m;
-    // k = 1: B_1 = A' (read through the read-only path); k > 1: the shared-memory state
     HsY<TAIL> y;
     y.row = (k == 1) ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + ((size_t)q * n + v) * n;
-    y.jq = jq; y.t = t;
-    hs_step<TAIL, TAU>(sfrag, lane, y, w);
-    // trace shares of this panel: delta of the panel's vertex pair
-    const double rs = ((jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;
+    y.jq = jq; y.t = lane & 3;
+    return y;
+}
+
+// trace shares of one computed panel (vertex pair i, tile TAU), added to the per-lane sums
+template <bool TAIL, int TAU>
+__device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL>& y, int i, bool needO, bool needE, int lane,
+                                          double (&tr)[6]) {
+    constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
+    const int t = lane & 3, half = lane >> 4;
+    const double rs = ((y.jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;      // delta of the panel's vertex pair
     {   // tr(M^(k+1)) share: element sigma(v) of this row, in the diagonal tile
         const bool in_tail = TAIL && (i >= 4 * TF);
         const int own_t = in_tail ? (1 - half) : (i & 3);
@@ -239,10 +341,17 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     constexpr int TF = HS_TF;
     const int iA = 4 * RHO + sub, iB = 4 * (TF - 1 - RHO) + sub;
     HafRow<TF, TAIL> wA, wB, wC;
-    const bool tailpanel = TAIL && warp == 0;     // the short panels first: fewer accumulators live during the long one
-    if (tailpanel) hs_panel<TAIL, TF>(sfrag, state, A, 4 * TF, k, needO, needE, jq, lane, wC, tr);
-    hs_panel<TAIL, TF - 1 - RHO>(sfrag, state, A, iB, k, needO, needE, jq, lane, wB, tr);
-    hs_panel<TAIL, RHO>(sfrag, state, A, iA, k, needO, needE, jq, lane, wA, tr);
+    const bool tailpanel = TAIL && warp == 0;
+    HsY<TAIL> yC;
+    if (tailpanel) {
+        yC = hs_rows<TAIL>(state, A, 4 * TF, k, jq, lane);
+        hs_step<TAIL, TF>(sfrag, lane, yC, wC);
+        hs_traces<TAIL, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+    }
+    const HsY<TAIL> yA = hs_rows<TAIL>(state, A, iA, k, jq, lane), yB = hs_rows<TAIL>(state, A, iB, k, jq, lane);
+    hs_step2<TAIL, RHO>(sfrag, lane, yA, yB, wA, wB);
+    hs_traces<TAIL, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
+    hs_traces<TAIL, RHO>(wA, yA, iA, needO, needE, lane, tr);
     __syncthreads();                       // every panel has read its rows of B_k
     if (store) {
         hs_store<TAIL, RHO>(state, iA, lane, wA);
@@ -259,9 +368,9 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     extern __shared__ __align__(16) double smem[];
     double2* sfrag = reinterpret_cast<double2*>(smem);
     double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D);
-    double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[j][q] complex; touched by warp 0 only
+    double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[j][q] complex
     double* Ck = Pk + C::P_D;
-    double* ptmp = Ck + C::P_D;                                        // [parity][kind][warp][row] complex
+    double* ptmp = Ck + C::P_D;                                        // [kind][warp][row] complex
     haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
     __syncthreads();
 
@@ -278,9 +387,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     for (uint64_t G = blockIdx.x; G < ngroups; G += gridDim.x) {
         const uint64_t jq = j0 + 4 * G + q;
         if (warp == 0) {
-            // tr(M^1) = sum_r delta_r A'[r][sigma(r)] = 2 sum_i delta_i A'[i][i + m]; P is private to warp 0
-            for (int s = lane; s < (m + 2) * 4; s += 32) { Pk[2 * s] = 0.0; Pk[2 * s + 1] = 0.0; }
-            __syncwarp();
+            // tr(M^1) = sum_r delta_r A'[r][sigma(r)] = 2 sum_i delta_i A'[i][i + m]; every P[1..m] is rewritten for every group
             if (lane < 4) {
                 const uint64_t jj = j0 + 4 * G + lane;
                 double sr = 0.0, si = 0.0;
@@ -308,28 +415,23 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
                 tr[c] += shfl_xor_d(tr[c], 2);
             }
             if (t == 0) {
-                double* pt = ptmp + (size_t)(k & 1) * (3 * HS_WARPS * 8 * 2);
 #pragma unroll
-                for (int kind = 0; kind < 3; ++kind) {
-                    pt[((kind * HS_WARPS + warp) * 8 + g) * 2] = tr[2 * kind];
-                    pt[((kind * HS_WARPS + warp) * 8 + g) * 2 + 1] = tr[2 * kind + 1];
-                }
+                for (int kind = 0; kind < 3; ++kind)
+                    reinterpret_cast<double2*>(ptmp)[(kind * HS_WARPS + warp) * 8 + g] = make_double2(tr[2 * kind], tr[2 * kind + 1]);
             }
             __syncthreads();                   // B_(k+1) is complete in shared memory; so are this step's trace shares
-            if (warp == 0 && lane < 12) {      // fixed-order sum over warps and the two rows of each subset
-                const int kind = lane >> 2, qq = lane & 3;
-                const double* pt = ptmp + (size_t)(k & 1) * (3 * HS_WARPS * 8 * 2);
-                double sr = 0.0, si = 0.0;
-                for (int wv = 0; wv < HS_WARPS; ++wv) {
-                    const double* e0 = pt + ((kind * HS_WARPS + wv) * 8 + qq) * 2;
-                    const double* e1 = pt + ((kind * HS_WARPS + wv) * 8 + qq + 4) * 2;
-                    sr += e0[0] + e1[0]; si += e0[1] + e1[1];
-                }
+            {   // warp w sums the 24 shares (12 warps x the two rows of a subset) of ONE (kind, subset) in a fixed shuffle tree
+                const int kind = warp >> 2, qq = warp & 3;
+                double2 e = make_double2(0.0, 0.0);
+                if (lane < 2 * HS_WARPS) e = reinterpret_cast<const double2*>(ptmp)[(kind * HS_WARPS + (lane >> 1)) * 8 + qq + 4 * (lane & 1)];
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { e.x += shfl_xor_d(e.x, off); e.y += shfl_xor_d(e.y, off); }
                 const int j = kind == 0 ? k + 1 : (kind == 1 ? 2 * k + 1 : 2 * k + 2);
                 const bool want = kind == 0 || (kind == 1 ? needO : needE);
-                if (want && j <= m) { Pk[(j * 4 + qq) * 2] = sr; Pk[(j * 4 + qq) * 2 + 1] = si; }
+                if (lane == 0 && want && j <= m) reinterpret_cast<double2*>(Pk)[j * 4 + qq] = e;
             }
         }
+        __syncthreads();                       // the last step's traces are in P
         // ---- series c_t = (1/t) sum_i (p_i / 2) c_(t-i), the eight lanes of a subset split the sum (warp 0 only)
         if (warp == 0) {
             __syncwarp();
