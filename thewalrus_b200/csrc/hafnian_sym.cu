@@ -41,10 +41,13 @@ struct HsCfg {
     static constexpr int M = 4 * HS_TF + (TAIL ? 1 : 0);          // vertex pairs
     static constexpr int N = 2 * M;
     static constexpr int FRAG_D = NK * NT * 64;                    // doubles
-    static constexpr int STATE_D2 = 4 * N * N;                     // double2: state[q][row][col]
-    static constexpr int P_D = (M + 2) * 4 * 2;                    // P[j][q] complex (doubles)
+    static constexpr int LD = N + 1;                               // row stride of the state (entries): 4 LD = 12 (mod 32) words
+    static constexpr int QS = ((N * LD + 7) / 8) * 8 + 4;          // subset stride: 4 QS = 16 (mod 32) words -> the two subsets of a
+                                                                   // quarter warp never share a bank, row-wise or column-wise
+    static constexpr int STATE_D2 = 4 * QS;                        // double2: state[q][row][col], only tiles >= the row's tile valid
+    static constexpr int P_D = (M + 2) * 4 * 2;                    // P[q][j] complex (doubles)
     static constexpr int TMP_D = 3 * HS_WARPS * 8 * 2;             // ptmp[kind][warp][row] complex (doubles)
-    static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + 2 * P_D + TMP_D);
+    static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + P_D + TMP_D);
 };
 
 // sign mask of vertex pair p in subset jq: delta = +1 (bit set) -> 0, delta = -1 -> sign bit
@@ -58,10 +61,12 @@ __device__ __forceinline__ unsigned hs_sign(uint64_t jq, int p) {
 // does) on top of the accumulators of two panels does not fit 168 registers.
 template <bool TAIL>
 struct HsY {
-    const double2* row;      // state row of this lane's (subset, vertex), or the row of A' as double2
+    const double2* row;      // row of this lane's (subset, vertex): state (stride LD) or A' (stride n, k = 1)
+    const double2* col;      // the same vertex as a COLUMN of the state: entry [c][v] = col[c * LD]
     uint64_t jq;
     int t;
-    __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {
+    bool first;              // k = 1: B_1 = A', every entry is there, read row-wise
+    __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {   // computed tiles only (row-wise)
         constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
         if (kap < 2 * TF) {
             const int tau = kap >> 1;
@@ -79,70 +84,68 @@ struct HsY {
     }
 };
 
-// W <- Y * A' for the N-tiles tau' >= TAU (and the tail tile); TAU == HS_TF: the tail tile only.
-// The loop over the K tiles is deliberately NOT unrolled: fully unrolled, ptxas hoists some thirty 16-byte fragment
-// loads to the top of the block (130 registers) and spills the accumulators of the other panel.
-template <bool TAIL, int TAU>
-__device__ __forceinline__ void hs_step(const double2* __restrict__ sfrag, int lane, const HsY<TAIL>& y,
-                                        HafRow<HS_TF, TAIL>& w) {
-    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M;
-#pragma unroll
-    for (int tp = TAU; tp < TF; ++tp) {
-        w.wr[tp][0] = w.wr[tp][1] = 0.0;
-        w.wi[tp][0] = w.wi[tp][1] = 0.0;
+// Walks the row of B_k of one lane K tile by K tile (a0 = entry of column 4 tau + t + m, a1 = of column 4 tau + t).
+// A panel of tile T computed and stored only the columns of tiles >= T of its rows; the entries of earlier tiles were
+// computed by other panels as THEIR rows, and B_k is symmetric: read them column-wise (conflict-free with the padded
+// strides).  Nothing is stored twice (the first version stored every strictly-upper tile also transposed: 6 % of the kernel).
+template <bool TAIL, int T>
+struct HsCur {
+    const double2* p;
+    int d, inc;
+    __device__ __forceinline__ void init(const HsY<TAIL>& y) {
+        constexpr int m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
+        if (y.first || T == 0) { p = y.row + y.t; d = m; inc = 4; }
+        else { p = y.col + y.t * LD; d = m * LD; inc = 4 * LD; }
     }
+    __device__ __forceinline__ void next(const HsY<TAIL>& y, int tau_next) {
+        constexpr int m = HsCfg<TAIL>::M;
+        if (T > 0 && T < HS_TF && !y.first && tau_next == T) { p = y.row + 4 * T + y.t; d = m; inc = 4; }
+        else p += inc;
+    }
+    __device__ __forceinline__ double2 tail(const HsY<TAIL>& y) const {    // tail columns: every panel computes them itself
+        return y.row[4 * HS_TF + (1 - (y.t & 1)) * HsCfg<TAIL>::M];
+    }
+};
+
+// The tail panel (the one vertex pair beyond the full tiles, n = 50): W <- Y * A' for the tail tile only; every other
+// entry of its rows arrives by symmetry.  Two accumulators (the panel alone would be one chain of dependent DMMAs).
+template <bool TAIL>
+__device__ __forceinline__ void hs_step_tail(const double2* __restrict__ sfrag, int lane, const HsY<TAIL>& y,
+                                             HafRow<HS_TF, TAIL>& w) {
+    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M;
     w.wtr = w.wti = 0.0;
-    double u2r = 0.0, u2i = 0.0;                 // second tail accumulator: the tail-only panel would be one dependent chain
-    const double2* fr = sfrag + lane;
-    const double2* yp = y.row + y.t;
+    double u2r = 0.0, u2i = 0.0;
+    const double2* fr = sfrag + lane + TF * 32;
+    HsCur<TAIL, TF> cur;
+    cur.init(y);
     int sh = m - 1 - y.t;
-    double2 a0 = yp[m], a1 = yp[0];              // the row's entries of the next K tile are fetched one iteration ahead
+    double2 a0 = cur.p[cur.d], a1 = cur.p[0];
 #pragma unroll 1
     for (int tau = 0; tau < TF; ++tau) {
         const unsigned s = ((unsigned)(y.jq >> sh) & 1u) ? 0u : 0x80000000u;
-        // next K tile; after the last one: the tail element of lanes t = 0, 1 (an address every lane may read)
         const bool last = tau == TF - 1;
-        const double2 n0 = (!last || TAIL) ? yp[last ? 4 + (1 - (y.t & 1)) * m - y.t : 4 + m] : make_double2(0.0, 0.0);
-        const double2 n1 = !last ? yp[4] : n0;
+        cur.next(y, tau + 1);
+        double2 n0 = make_double2(0.0, 0.0), n1 = n0;
+        if (!last) { n0 = cur.p[cur.d]; n1 = cur.p[0]; }
+        else n0 = cur.tail(y);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
-#pragma unroll
-            for (int tp = TAU; tp < TF; ++tp) {
-                const double2 b = fr[tp * 32];
-                const double nbi = -b.y;
-                dmma884(w.wr[tp][0], w.wr[tp][1], ar, b.x);
-                dmma884(w.wi[tp][0], w.wi[tp][1], ar, b.y);
-                dmma884(w.wr[tp][0], w.wr[tp][1], ai, nbi);
-                dmma884(w.wi[tp][0], w.wi[tp][1], ai, b.x);
-            }
-            if (TAIL) {
-                const double2 b = fr[TF * 32];
-                dmma884(w.wtr, w.wti, ar, b.x);
-                if (TAU == TF) dmma884(u2r, u2i, ai, b.y);
-                else dmma884(w.wtr, w.wti, ai, b.y);
-            }
+            const double2 b = fr[0];
+            dmma884(w.wtr, w.wti, ar, b.x);
+            dmma884(u2r, u2i, ai, b.y);
             fr += NT * 32;
         }
         a0 = n0; a1 = n1;
-        yp += 4;
         sh -= 4;
     }
-    if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
-        const unsigned s = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
-        const double ar = (y.t < 2) ? flipsign(a0.x, s) : 0.0, ai = (y.t < 2) ? flipsign(a0.y, s) : 0.0;
-        const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
-        const double ap = (lane & 2) ? yi2 : ar;
-#pragma unroll
-        for (int tp = TAU; tp < TF; ++tp) {
-            const double2 b = fr[tp * 32];
-            dmma884(w.wr[tp][0], w.wr[tp][1], ap, b.x);
-            dmma884(w.wi[tp][0], w.wi[tp][1], ap, b.y);
-        }
-        const double2 b = fr[TF * 32];
-        dmma884(w.wtr, w.wti, ap, b.x);
-        if (TAU == TF) { w.wtr += u2r; w.wti += u2i; }
-    }
+    const unsigned s = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
+    const double ar = (y.t < 2) ? flipsign(a0.x, s) : 0.0, ai = (y.t < 2) ? flipsign(a0.y, s) : 0.0;
+    const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
+    const double ap = (lane & 2) ? yi2 : ar;
+    const double2 b = fr[0];
+    dmma884(w.wtr, w.wti, ap, b.x);
+    w.wtr += u2r; w.wti += u2i;
 }
 
 // The two panels of a warp (tiles RHO and 5 - RHO) in ONE pass over K: the panel of the later tile needs a subset of the
@@ -165,19 +168,20 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
     wA.wtr = wA.wti = 0.0;
     wB.wtr = wB.wti = 0.0;
     const double2* fr = sfrag + lane;
-    const double2* ypA = yA.row + yA.t;
-    const double2* ypB = yB.row + yA.t;
+    HsCur<TAIL, RHO> curA;
+    HsCur<TAIL, TB> curB;
+    curA.init(yA); curB.init(yB);
     int sh = m - 1 - yA.t;
-    double2 a0 = ypA[m], a1 = ypA[0], c0 = ypB[m], c1 = ypB[0];     // fetched one iteration ahead
+    double2 a0 = curA.p[curA.d], a1 = curA.p[0], c0 = curB.p[curB.d], c1 = curB.p[0];     // fetched one iteration ahead
 #pragma unroll 1
     for (int tau = 0; tau < TF; ++tau) {
         const unsigned s = ((unsigned)(yA.jq >> sh) & 1u) ? 0u : 0x80000000u;
         // next K tile; after the last one: the tail element of lanes t = 0, 1 (an address every lane may read)
         const bool last = tau == TF - 1;
-        const int o0 = last ? 4 + (1 - (yA.t & 1)) * m - yA.t : 4 + m;
+        curA.next(yA, tau + 1); curB.next(yB, tau + 1);
         double2 n0 = make_double2(0.0, 0.0), n1 = n0, d0 = n0, d1 = n0;
-        if (!last || TAIL) { n0 = ypA[o0]; d0 = ypB[o0]; }
-        if (!last) { n1 = ypA[4]; d1 = ypB[4]; }
+        if (!last) { n0 = curA.p[curA.d]; n1 = curA.p[0]; d0 = curB.p[curB.d]; d1 = curB.p[0]; }
+        else if (TAIL) { n0 = curA.tail(yA); d0 = curB.tail(yB); }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
@@ -209,7 +213,6 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
             fr += NT * 32;
         }
         a0 = n0; a1 = n1; c0 = d0; c1 = d1;
-        ypA += 4; ypB += 4;
         sh -= 4;
     }
     if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
@@ -277,7 +280,9 @@ __device__ __forceinline__ HsY<TAIL> hs_rows(const double2* __restrict__ state, 
     const int g = lane >> 2, q = g & 3, half = g >> 2;
     const int v = i + half * m;
     HsY<TAIL> y;
-    y.row = (k == 1) ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + ((size_t)q * n + v) * n;
+    y.first = k == 1;
+    y.row = y.first ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + q * C::QS + v * C::LD;
+    y.col = state + q * C::QS + v;
     y.jq = jq; y.t = lane & 3;
     return y;
 }
@@ -307,30 +312,19 @@ __device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const Hs
     }
 }
 
-// write the computed tiles of a panel: directly, and transposed for the strictly-upper tiles
+// write the computed tiles of a panel (its rows, the columns of tiles >= its own and the tail columns)
 template <bool TAIL, int TAU>
 __device__ __forceinline__ void hs_store(double2* __restrict__ state, int i, int lane, const HafRow<HS_TF, TAIL>& w) {
     using C = HsCfg<TAIL>;
-    constexpr int TF = HS_TF, m = C::M, n = C::N;
+    constexpr int TF = HS_TF, m = C::M;
     const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
-    const int v = i + half * m;
-    double2* base = state + (size_t)q * n * n;
+    double2* row = state + q * C::QS + (i + half * m) * C::LD;
 #pragma unroll
     for (int tau = TAU; tau < TF; ++tau) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int c = 4 * tau + t + r * m;
-            const double2 val = make_double2(w.wr[tau][r], w.wi[tau][r]);
-            base[(size_t)v * n + c] = val;
-            if (tau > TAU) base[(size_t)c * n + v] = val;
-        }
+        for (int r = 0; r < 2; ++r) row[4 * tau + t + r * m] = make_double2(w.wr[tau][r], w.wi[tau][r]);
     }
-    if (TAIL && (t >> 1) < 1) {
-        const int c = 4 * TF + (t & 1) * m;
-        const double2 val = make_double2(w.wtr, w.wti);
-        base[(size_t)v * n + c] = val;
-        if (TAU < TF) base[(size_t)c * n + v] = val;
-    }
+    if (TAIL && t < 2) row[4 * TF + (t & 1) * m] = make_double2(w.wtr, w.wti);
 }
 
 // one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ the tail panel on warp 0)
@@ -345,7 +339,7 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     HsY<TAIL> yC;
     if (tailpanel) {
         yC = hs_rows<TAIL>(state, A, 4 * TF, k, jq, lane);
-        hs_step<TAIL, TF>(sfrag, lane, yC, wC);
+        hs_step_tail<TAIL>(sfrag, lane, yC, wC);
         hs_traces<TAIL, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
     }
     const HsY<TAIL> yA = hs_rows<TAIL>(state, A, iA, k, jq, lane), yB = hs_rows<TAIL>(state, A, iB, k, jq, lane);
@@ -368,18 +362,18 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     extern __shared__ __align__(16) double smem[];
     double2* sfrag = reinterpret_cast<double2*>(smem);
     double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D);
-    double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[j][q] complex
-    double* Ck = Pk + C::P_D;
-    double* ptmp = Ck + C::P_D;                                        // [kind][warp][row] complex
+    double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[q][j] complex
+    double* ptmp = Pk + C::P_D;                                        // [kind][warp][row] complex
     haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
+    const int g = lane >> 2, t = lane & 3, q = g & 3;
     const int rho = warp >> 2, sub = warp & 3;
     const int nprod = (m - 1) >> 1, K = nprod + 1;
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
 
+    const double inv_lane = 1.0 / (double)(lane ? lane : 1);
     cdd acc;
     acc.re = {0.0, 0.0};
     acc.im = {0.0, 0.0};
@@ -396,7 +390,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
                     sr += d * __ldg(A + 2 * ((size_t)i * n + i + m));
                     si += d * __ldg(A + 2 * ((size_t)i * n + i + m) + 1);
                 }
-                Pk[(1 * 4 + lane) * 2] = sr; Pk[(1 * 4 + lane) * 2 + 1] = si;
+                Pk[(lane * (m + 2) + 1) * 2] = sr; Pk[(lane * (m + 2) + 1) * 2 + 1] = si;
             }
             __syncwarp();
         }
@@ -428,35 +422,43 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
                 for (int off = 16; off >= 1; off >>= 1) { e.x += shfl_xor_d(e.x, off); e.y += shfl_xor_d(e.y, off); }
                 const int j = kind == 0 ? k + 1 : (kind == 1 ? 2 * k + 1 : 2 * k + 2);
                 const bool want = kind == 0 || (kind == 1 ? needO : needE);
-                if (lane == 0 && want && j <= m) reinterpret_cast<double2*>(Pk)[j * 4 + qq] = e;
+                if (lane == 0 && want && j <= m) reinterpret_cast<double2*>(Pk)[qq * (m + 2) + j] = e;
             }
         }
         __syncthreads();                       // the last step's traces are in P
-        // ---- series c_t = (1/t) sum_i (p_i / 2) c_(t-i), the eight lanes of a subset split the sum (warp 0 only)
+        // ---- series c_s = (1/s) sum_i (p_i / 2) c_(s-i), warp 0, "push" form: lane l holds the partial sum of target index l
+        // for each of the four subsets (four independent chains); step s: lane s finishes c_s, one broadcast, and every lane
+        // l > s adds F_(l-s) c_s.  (The first version split each inner sum over 8 lanes with two FP64 divisions and three
+        // shuffle levels per step: 28 k cycles per group, 8 % of the kernel.)
         if (warp == 0) {
-            __syncwarp();
-            if (lane < 4) { Ck[lane * 2] = 1.0; Ck[lane * 2 + 1] = 0.0; }
-            __syncwarp();
-            const int l8 = half * 4 + t;
-            for (int sidx = 1; sidx <= m; ++sidx) {
-                double sr = 0.0, si = 0.0;
-                for (int i = 1 + l8; i <= sidx; i += 8) {
-                    const double fr = 0.5 * Pk[(i * 4 + q) * 2], fi = 0.5 * Pk[(i * 4 + q) * 2 + 1];
-                    const double c_r = Ck[((sidx - i) * 4 + q) * 2], c_i = Ck[((sidx - i) * 4 + q) * 2 + 1];
-                    sr = fma(fr, c_r, sr); sr = fma(-fi, c_i, sr);
-                    si = fma(fr, c_i, si); si = fma(fi, c_r, si);
-                }
-                sr += shfl_xor_d(sr, 1); si += shfl_xor_d(si, 1);
-                sr += shfl_xor_d(sr, 2); si += shfl_xor_d(si, 2);
-                sr += shfl_xor_d(sr, 16); si += shfl_xor_d(si, 16);
-                if (l8 == 0) { Ck[(sidx * 4 + q) * 2] = sr / sidx; Ck[(sidx * 4 + q) * 2 + 1] = si / sidx; }
-                __syncwarp();
+            const double2* P2 = reinterpret_cast<const double2*>(Pk);
+            double ar[4], ai[4];
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const double2 f = (lane >= 1 && lane <= m) ? P2[qq * (m + 2) + lane] : make_double2(0.0, 0.0);
+                ar[qq] = 0.5 * f.x; ai[qq] = 0.5 * f.y;                    // c_0 = 1
             }
-            if (l8 == 0 && jq < j1) {
-                const int nk = __popcll(jq);
-                const double sg = ((m - nk) & 1) ? -1.0 : 1.0;
-                dd_add(acc.re, sg * Ck[(m * 4 + q) * 2]);
-                dd_add(acc.im, sg * Ck[(m * 4 + q) * 2 + 1]);
+            for (int sidx = 1; sidx < m; ++sidx) {
+                const bool tgt = lane > sidx && lane <= m;
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const double cr = shfl_d(ar[qq] * inv_lane, sidx), ci = shfl_d(ai[qq] * inv_lane, sidx);
+                    const double2 f = tgt ? P2[qq * (m + 2) + lane - sidx] : make_double2(0.0, 0.0);
+                    const double fr = 0.5 * f.x, fi = 0.5 * f.y;
+                    ar[qq] = fma(fr, cr, ar[qq]); ar[qq] = fma(-fi, ci, ar[qq]);
+                    ai[qq] = fma(fr, ci, ai[qq]); ai[qq] = fma(fi, cr, ai[qq]);
+                }
+            }
+            if (lane == m) {
+#pragma unroll
+                for (int qq = 0; qq < 4; ++qq) {
+                    const uint64_t jj = j0 + 4 * G + qq;
+                    if (jj < j1) {
+                        const double sg = ((m - __popcll(jj)) & 1) ? -1.0 : 1.0;
+                        dd_add(acc.re, sg * ar[qq] * inv_lane);
+                        dd_add(acc.im, sg * ai[qq] * inv_lane);
+                    }
+                }
             }
             __syncwarp();
         }
