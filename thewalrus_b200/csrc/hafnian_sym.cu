@@ -47,7 +47,8 @@ struct HsCfg {
     static constexpr int STATE_D2 = 4 * QS;                        // double2: state[q][row][col], only tiles >= the row's tile valid
     static constexpr int P_D = (M + 2) * 4 * 2;                    // P[q][j] complex (doubles)
     static constexpr int TMP_D = 3 * HS_WARPS * 8 * 2;             // ptmp[kind][warp][row] complex (doubles)
-    static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + P_D + TMP_D);
+    static constexpr int TAILC_D = TAIL ? HS_WARPS * 32 * 2 : 0;   // partial tail tiles of the K-split tail panel (doubles)
+    static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + P_D + TMP_D + TAILC_D);
 };
 
 // sign mask of vertex pair p in subset jq: delta = +1 (bit set) -> 0, delta = -1 -> sign bit
@@ -107,45 +108,31 @@ struct HsCur {
     }
 };
 
-// The tail panel (the one vertex pair beyond the full tiles, n = 50): W <- Y * A' for the tail tile only; every other
-// entry of its rows arrives by symmetry.  Two accumulators (the panel alone would be one chain of dependent DMMAs).
+// The tail panel (the one vertex pair beyond the full tiles, n = 50): only its 2 x 2 tail block has to be computed, every
+// other entry of its rows arrives by symmetry.  That is 25 DMMAs in one dependent chain - on one warp it made that warp
+// late at every barrier - so the K range is SPLIT over the 12 warps: warp w multiplies K chunk w (warp 0 also the packed
+// tail chunk), the partial tiles meet in shared memory and warp 0 sums them in warp order while the others store.
 template <bool TAIL>
-__device__ __forceinline__ void hs_step_tail(const double2* __restrict__ sfrag, int lane, const HsY<TAIL>& y,
-                                             HafRow<HS_TF, TAIL>& w) {
-    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M;
-    w.wtr = w.wti = 0.0;
-    double u2r = 0.0, u2i = 0.0;
-    const double2* fr = sfrag + lane + TF * 32;
-    HsCur<TAIL, TF> cur;
-    cur.init(y);
-    int sh = m - 1 - y.t;
-    double2 a0 = cur.p[cur.d], a1 = cur.p[0];
-#pragma unroll 1
-    for (int tau = 0; tau < TF; ++tau) {
-        const unsigned s = ((unsigned)(y.jq >> sh) & 1u) ? 0u : 0x80000000u;
-        const bool last = tau == TF - 1;
-        cur.next(y, tau + 1);
-        double2 n0 = make_double2(0.0, 0.0), n1 = n0;
-        if (!last) { n0 = cur.p[cur.d]; n1 = cur.p[0]; }
-        else n0 = cur.tail(y);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
-            const double2 b = fr[0];
-            dmma884(w.wtr, w.wti, ar, b.x);
-            dmma884(u2r, u2i, ai, b.y);
-            fr += NT * 32;
-        }
-        a0 = n0; a1 = n1;
-        sh -= 4;
+__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int warp, const HsY<TAIL>& y) {
+    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
+    const int tau = warp >> 1, h = warp & 1;
+    const int c = 4 * tau + y.t + (1 - h) * m;                      // Y[v][chunk position] = delta B[v][c]
+    const double2 a = y.first ? y.row[c] : y.col[c * LD];
+    const unsigned s = hs_sign<TAIL>(y.jq, 4 * tau + y.t);
+    const double2 b = sfrag[(warp * NT + TF) * 32 + lane];
+    double pr = 0.0, pi = 0.0;
+    dmma884(pr, pi, flipsign(a.x, s), b.x);
+    dmma884(pr, pi, flipsign(a.y, s), b.y);
+    if (warp == 0) {
+        const double2 at = y.row[4 * TF + (1 - (y.t & 1)) * m];
+        const unsigned st = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
+        const double ar = (y.t < 2) ? flipsign(at.x, st) : 0.0, ai = (y.t < 2) ? flipsign(at.y, st) : 0.0;
+        const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
+        const double ap = (lane & 2) ? yi2 : ar;
+        const double2 bt = sfrag[(2 * TF * NT + TF) * 32 + lane];
+        dmma884(pr, pi, ap, bt.x);
     }
-    const unsigned s = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
-    const double ar = (y.t < 2) ? flipsign(a0.x, s) : 0.0, ai = (y.t < 2) ? flipsign(a0.y, s) : 0.0;
-    const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
-    const double ap = (lane & 2) ? yi2 : ar;
-    const double2 b = fr[0];
-    dmma884(w.wtr, w.wti, ap, b.x);
-    w.wtr += u2r; w.wti += u2i;
+    return make_double2(pr, pi);
 }
 
 // The two panels of a warp (tiles RHO and 5 - RHO) in ONE pass over K: the panel of the later tile needs a subset of the
@@ -327,30 +314,35 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int i, int
     if (TAIL && t < 2) row[4 * TF + (t & 1) * m] = make_double2(w.wtr, w.wti);
 }
 
-// one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ the tail panel on warp 0)
+// one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ its K chunk of the tail panel)
 template <bool TAIL, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, int k, bool needO, bool needE, bool store, uint64_t jq,
-                                             int lane, int warp, double (&tr)[6]) {
+                                             int lane, int warp, double2* __restrict__ tailC, double (&tr)[6]) {
     constexpr int TF = HS_TF;
     const int iA = 4 * RHO + sub, iB = 4 * (TF - 1 - RHO) + sub;
-    HafRow<TF, TAIL> wA, wB, wC;
-    const bool tailpanel = TAIL && warp == 0;
+    HafRow<TF, TAIL> wA, wB;
     HsY<TAIL> yC;
-    if (tailpanel) {
+    if (TAIL) {
         yC = hs_rows<TAIL>(state, A, 4 * TF, k, jq, lane);
-        hs_step_tail<TAIL>(sfrag, lane, yC, wC);
-        hs_traces<TAIL, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+        tailC[warp * 32 + lane] = hs_tail_chunk<TAIL>(sfrag, lane, warp, yC);
     }
     const HsY<TAIL> yA = hs_rows<TAIL>(state, A, iA, k, jq, lane), yB = hs_rows<TAIL>(state, A, iB, k, jq, lane);
     hs_step2<TAIL, RHO>(sfrag, lane, yA, yB, wA, wB);
     hs_traces<TAIL, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
     hs_traces<TAIL, RHO>(wA, yA, iA, needO, needE, lane, tr);
-    __syncthreads();                       // every panel has read its rows of B_k
+    __syncthreads();                       // every panel has read its rows of B_k; the partial tail tiles are in shared memory
     if (store) {
         hs_store<TAIL, RHO>(state, iA, lane, wA);
         hs_store<TAIL, TF - 1 - RHO>(state, iB, lane, wB);
-        if (tailpanel) hs_store<TAIL, TF>(state, 4 * TF, lane, wC);
+    }
+    if (TAIL && warp == 0) {
+        HafRow<TF, TAIL> wC;
+        wC.wtr = wC.wti = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < HS_WARPS; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
+        hs_traces<TAIL, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+        if (store) hs_store<TAIL, TF>(state, 4 * TF, lane, wC);
     }
 }
 
@@ -364,6 +356,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D);
     double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[q][j] complex
     double* ptmp = Pk + C::P_D;                                        // [kind][warp][row] complex
+    double2* tailC = reinterpret_cast<double2*>(ptmp + C::TMP_D);      // [warp][lane]
     haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
     __syncthreads();
 
@@ -399,9 +392,9 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             const bool needE = (2 * k + 2 > K) && (2 * k + 2 <= m);
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
-            if (rho == 0) hs_warp_step<TAIL, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tr);
-            else if (rho == 1) hs_warp_step<TAIL, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tr);
-            else hs_warp_step<TAIL, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tr);
+            if (rho == 0) hs_warp_step<TAIL, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tailC, tr);
+            else if (rho == 1) hs_warp_step<TAIL, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tailC, tr);
+            else hs_warp_step<TAIL, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tailC, tr);
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for warp 0
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
