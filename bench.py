@@ -133,12 +133,32 @@ def tor_tree_flops(N, DC=9, aug=0):
     return prefixes * per_prefix + (prefixes / 32.0) * lead
 
 
+def haf_sym_entries(n):
+    """Entries of one n x n product the symmetric-half kernel computes (hafnian_sym.cu; 0 = shape not covered): the
+    row panel of a vertex pair in tile T (tiles = 4 vertex pairs = 8 rows/columns) computes the columns of tiles >= T
+    and of the tail pair; the tail pair's panel only its own 2 x 2 block."""
+    m = n // 2
+    if n % 2 or m not in (24, 25):
+        return 0
+    tail = m - 24
+    return sum(8 * (8 * (6 - T) + 2 * tail) for T in range(6)) + 4 * tail
+
+
 def units_and_flops(kind, n):
     """(units per step, executed-algorithm flops per unit of THIS implementation, reference-algorithm flops per
     unit, text of the model, FP64 pipe the kernel issues to)."""
     if kind in ("hafnian", "lhaf"):
         m = n // 2
         nprod = (m - 1) // 2
+        if kind == "hafnian" and haf_sym_entries(n) and os.environ.get("WB200_HAF_SYM", "1") != "0":
+            # symmetric-half kernel (hafnian_sym.cu): of every product only the tiles on and above the diagonal
+            return (1 << (m - 1), 8.0 * n * haf_sym_entries(n) * nprod, 8.0 * n**3 * (m - 1),
+                    "EXECUTED useful flops of haf_sym_kernel: 8 n E floor((n/2-1)/2) per subset, E = %d of the n^2 = %d entries of "
+                    "a product (B_k = M^(k-1) A' is symmetric: only the 8 x 8 tiles on and above the diagonal are computed); "
+                    "trace pairing halves the reference's n/2-1 products.  The row-panel kernel of round 1 executes 8 n^3 "
+                    "floor((n/2-1)/2) = %.3g per subset, the reference's algorithm 8 n^3 (n/2-1) = %.3g"
+                    % (haf_sym_entries(n), n * n, 8.0 * n**3 * nprod, 8.0 * n**3 * (m - 1)),
+                    "FP64 DMMA.8x8x4 (tensor pipe; same flop rate as the FP64 FMA pipe)")
         return (1 << (m - 1), 8.0 * n**3 * nprod, 8.0 * n**3 * (m - 1),
                 "8 n^3 floor((n/2-1)/2) per subset: trace pairing halves the reference's 8 n^3 (n/2-1) product chain",
                 "FP64 DMMA.8x8x4 (tensor pipe; same flop rate as the FP64 FMA pipe)")

@@ -9,19 +9,31 @@
 //
 // That couples the panels of a group: all of them must finish product k before any starts product k + 1, and every
 // panel needs entries other panels computed.  So the iterates of ONE group of four subsets live in shared memory
-// (4 x n x n complex = 160 KB at n = 50, next to the 46 KB fragment table of A') and the 12 warps of the CTA advance
+// (4 x n x (n + 1) complex = 164 KB at n = 50, next to the 46 KB fragment table of A') and the 12 warps of the CTA advance
 // that group together, two barriers per product: [all panels read their rows of B_k and compute] | barrier |
-// [write the computed tiles, directly and transposed] | barrier.  Each warp owns two row panels whose tile counts add
-// up to the same number (tau and 5 - tau: 6.5 - tau + tau + 1.5 = 8 tile units with the tail tile), so the warps are
-// balanced; the tail panel (vertex pair 24 at n = 50: one packed tile, everything else arrives by transposition) rides
-// along on warp 0.
+// [write the computed tiles] | barrier.  A panel writes ONLY what it computed (its rows, the columns of tiles >= its own
+// and the tail columns); the entries of earlier tiles are read column-wise from the rows of the panels that computed
+// them (row stride n + 1, subset stride = 16 words mod 32: both access patterns are bank-conflict free).
+//
+// Work split: each warp owns two row panels whose tile counts add up to the same number (tau and 5 - tau: 8 tile units
+// with the tail tile) and walks K ONCE for both - the later tile's panel needs a subset of the other's fragments, so
+// every 16-byte fragment load feeds both and two independent panels' DMMAs interleave.  The K loop is rolled (one
+// iteration = one K tile = 64 DMMAs, the next tile's row entries prefetched): fully unrolled, ptxas hoists ~30 fragment
+// loads and spills the accumulators.  The tail panel (vertex pair 24 at n = 50: only its 2 x 2 tail block is new) is
+// split over K across the 12 warps and summed by warp 0 while the others store.
 //
 // The power traces stay warp-local although no warp ever sees a whole row of B_(k+1): with U = B_a S, V = B_b,
 //     tr(M^(a+b)) = sum_(x,y) V[x][y] delta_x U[sigma(x)][y]
 // and the term of (y, x) equals the term of (x, y) (both B_a and B_b are symmetric), so every COMPUTED entry (x, y) of
-// a strictly-upper tile counts twice and the entries of the diagonal tiles once — the same partner-row inner products
+// a strictly-upper tile counts twice and the entries of the diagonal tiles once - the same partner-row inner products
 // as haf_advance, restricted to the computed tiles, with a weight.  (NumPy emulation of exactly this bookkeeping
-// against the oracle: 3e-15)
+// against the oracle: 3e-15)  Per product every warp leaves its trace shares in shared memory; after
+// the barrier warp w sums the 24 shares of one (trace kind, subset) in a fixed shuffle tree.  The series of a group
+// (thewalrus/_hafnian.py:183-214, f) runs on warp 0 in "push" form, four subsets as four independent chains.
+//
+// Measured on B200 (profiles/r02_haf_sym_*.txt): n = 50: 3.79e6 subsets/s against 2.75e6 of the row-panel kernel
+// (1.38x) at 0.59 of its DMMAs - tensor pipe 75 % busy (row-panel kernel: 92 %): the two barriers per product, the
+// store phase and the pairing phase of all warps at once cost what the row-panel kernel overlaps.
 //
 // Shape: TF = 6 full tiles (24 vertex pairs = 12 warps x 2 panels) with no tail (n = 48) or a one-pair packed tail
 // (n = 50).  Everything else, and the loop hafnian, stays on haf_dmma_kernel.
