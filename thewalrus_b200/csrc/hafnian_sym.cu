@@ -56,11 +56,36 @@ struct HsCfg {
     static constexpr int LD = N + 1;                               // row stride of the state (entries): 4 LD = 12 (mod 32) words
     static constexpr int QS = ((N * LD + 7) / 8) * 8 + 4;          // subset stride: 4 QS = 16 (mod 32) words -> the two subsets of a
                                                                    // quarter warp never share a bank, row-wise or column-wise
-    static constexpr int STATE_D2 = 4 * QS;                        // double2: state[q][row][col], only tiles >= the row's tile valid
-    static constexpr int P_D = (M + 2) * 4 * 2;                    // P[q][j] complex (doubles)
-    static constexpr int TMP_D = 3 * HS_WARPS * 8 * 2;             // ptmp[kind][warp][row] complex (doubles)
+    static constexpr int STATE_D2 = 4 * QS;                        // double2: state[subset][row][col], only tiles >= the row's tile valid
+    static constexpr int P_D = (M + 2) * 4 * 2;                    // P[subset][j] complex (doubles)
+    static constexpr int TMP_D = 3 * HS_WARPS * 8 * 2;             // ptmp[team][kind][warp in team][row] complex (doubles)
     static constexpr int TAILC_D = TAIL ? HS_WARPS * 32 * 2 : 0;   // partial tail tiles of the K-split tail panel (doubles)
     static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + P_D + TMP_D + TAILC_D);
+};
+
+// Teams.  NQ = 4: the 12 warps advance one group of four subsets (a DMMA's 8 rows = 4 subsets x the two vertices of a pair).
+// NQ = 2 (default): two teams of 6 warps, each on its own group of TWO subsets (8 rows = 2 subsets x two vertex pairs x 2):
+// same shared memory, same registers, same DMMAs per warp and product, but every barrier spans 6 warps instead of 12.
+// The hope was more: teams running out of step, one team's barriers / store / pairing phases under the other's DMMAs.
+// Measured (profiles/r02_haf_sym_skew.txt): holding the second team back by any fraction of a product changes n = 50 by
+// +1 % and n = 48 by -5 % - six warps cannot be spread evenly over four schedulers (2 + 1 + 2 + 1), so while one team is
+// in a phase the other team's warps on the 2-warp schedulers set its pace and the 1-warp schedulers idle.  Two teams of 8
+// warps (128 registers) would balance; the phases left to hide are 12 % of the kernel and the 6.5 / 6.0 tile-unit split
+// of 8 warps costs 7 %, so it was not built.
+template <int NQ>
+struct HsTeam {
+    static constexpr int TEAMS = 4 / NQ;                 // 1 or 2
+    static constexpr int TW = HS_WARPS / TEAMS;          // warps per team = 3 NQ
+    static constexpr int PP = 4 / NQ;                    // vertex pairs per row panel
+    static constexpr int SUBS = 4 / PP;                  // panels per tile
+    __device__ static __forceinline__ int team(int warp) { return NQ == 4 ? 0 : (((warp >> 2) + warp) & 1); }
+    __device__ static __forceinline__ int wl(int warp) { return NQ == 4 ? warp : (warp >> 1); }
+    __device__ static __forceinline__ int q(int lane) { return (lane >> 2) & (NQ - 1); }
+    __device__ static __forceinline__ int ps(int lane) { return NQ == 4 ? 0 : ((lane >> 3) & 1); }
+    __device__ static __forceinline__ void sync(int team) {
+        if (NQ == 4) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" :: "r"(1 + team), "r"(32 * TW) : "memory");
+    }
 };
 
 // sign mask of vertex pair p in subset jq: delta = +1 (bit set) -> 0, delta = -1 -> sign bit
@@ -122,20 +147,24 @@ struct HsCur {
 
 // The tail panel (the one vertex pair beyond the full tiles, n = 50): only its 2 x 2 tail block has to be computed, every
 // other entry of its rows arrives by symmetry.  That is 25 DMMAs in one dependent chain - on one warp it made that warp
-// late at every barrier - so the K range is SPLIT over the 12 warps: warp w multiplies K chunk w (warp 0 also the packed
-// tail chunk), the partial tiles meet in shared memory and warp 0 sums them in warp order while the others store.
-template <bool TAIL>
-__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int warp, const HsY<TAIL>& y) {
+// late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies K chunks w CH .. w CH + CH - 1
+// (the first warp also the packed tail chunk), the partial tiles meet in shared memory and the first warp sums them in
+// warp order while the others store.
+template <bool TAIL, int CH>
+__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<TAIL>& y) {
     constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
-    const int tau = warp >> 1, h = warp & 1;
-    const int c = 4 * tau + y.t + (1 - h) * m;                      // Y[v][chunk position] = delta B[v][c]
-    const double2 a = y.first ? y.row[c] : y.col[c * LD];
-    const unsigned s = hs_sign<TAIL>(y.jq, 4 * tau + y.t);
-    const double2 b = sfrag[(warp * NT + TF) * 32 + lane];
-    double pr = 0.0, pi = 0.0;
-    dmma884(pr, pi, flipsign(a.x, s), b.x);
-    dmma884(pr, pi, flipsign(a.y, s), b.y);
-    if (warp == 0) {
+    double pr = 0.0, pi = 0.0, p2r = 0.0, p2i = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < CH; ++cc) {
+        const int kap = wl * CH + cc, tau = kap >> 1, h = kap & 1;
+        const int c = 4 * tau + y.t + (1 - h) * m;                      // Y[v][chunk position] = delta B[v][c]
+        const double2 a = y.first ? y.row[c] : y.col[c * LD];
+        const unsigned s = hs_sign<TAIL>(y.jq, 4 * tau + y.t);
+        const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
+        dmma884(pr, pi, flipsign(a.x, s), b.x);
+        dmma884(p2r, p2i, flipsign(a.y, s), b.y);
+    }
+    if (wl == 0) {
         const double2 at = y.row[4 * TF + (1 - (y.t & 1)) * m];
         const unsigned st = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
         const double ar = (y.t < 2) ? flipsign(at.x, st) : 0.0, ai = (y.t < 2) ? flipsign(at.y, st) : 0.0;
@@ -144,7 +173,7 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
         const double2 bt = sfrag[(2 * TF * NT + TF) * 32 + lane];
         dmma884(pr, pi, ap, bt.x);
     }
-    return make_double2(pr, pi);
+    return make_double2(pr + p2r, pi + p2i);
 }
 
 // The two panels of a warp (tiles RHO and 5 - RHO) in ONE pass over K: the panel of the later tile needs a subset of the
@@ -270,31 +299,35 @@ __device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const H
     }
 }
 
-// the rows of Y_k = B_k S of a panel (vertex pair i) as seen by this lane: from A' at k = 1 (B_1 = A', read through the
-// generic path), else from the shared-memory state
-template <bool TAIL>
-__device__ __forceinline__ HsY<TAIL> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int i, int k, uint64_t jq, int lane) {
+// the rows of Y_k = B_k S of a panel (first vertex pair ibase) as seen by this lane: from A' at k = 1 (B_1 = A', read
+// through the generic path), else from the team's shared-memory state
+template <bool TAIL, int NQ>
+__device__ __forceinline__ HsY<TAIL> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
+                                             int k, uint64_t jq, int lane) {
     using C = HsCfg<TAIL>;
+    using T = HsTeam<NQ>;
     constexpr int m = C::M, n = C::N;
-    const int g = lane >> 2, q = g & 3, half = g >> 2;
-    const int v = i + half * m;
+    const int half = lane >> 4;
+    const int v = ibase + (tailrows ? 0 : T::ps(lane)) + half * m;      // tail panel: the rows of the second pair slot repeat the first
     HsY<TAIL> y;
     y.first = k == 1;
-    y.row = y.first ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + q * C::QS + v * C::LD;
-    y.col = state + q * C::QS + v;
+    y.row = y.first ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + T::q(lane) * C::QS + v * C::LD;
+    y.col = state + T::q(lane) * C::QS + v;
     y.jq = jq; y.t = lane & 3;
     return y;
 }
 
-// trace shares of one computed panel (vertex pair i, tile TAU), added to the per-lane sums
-template <bool TAIL, int TAU>
-__device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL>& y, int i, bool needO, bool needE, int lane,
+// trace shares of one computed panel (first vertex pair ibase, tile TAU), added to the per-lane sums
+template <bool TAIL, int NQ, int TAU>
+__device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL>& y, int ibase, bool needO, bool needE, int lane,
                                           double (&tr)[6]) {
     constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
+    constexpr bool in_tail = TAIL && TAU == TF;
     const int t = lane & 3, half = lane >> 4;
-    const double rs = ((y.jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;      // delta of the panel's vertex pair
+    const int i = ibase + (in_tail ? 0 : HsTeam<NQ>::ps(lane));
+    double rs = ((y.jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;            // delta of the row's vertex pair
+    if (in_tail && HsTeam<NQ>::ps(lane)) rs = 0.0;                      // repeated rows of the tail panel
     {   // tr(M^(k+1)) share: element sigma(v) of this row, in the diagonal tile
-        const bool in_tail = TAIL && (i >= 4 * TF);
         const int own_t = in_tail ? (1 - half) : (i & 3);
         if (t == own_t) {
             double dr, di;
@@ -312,12 +345,14 @@ __device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const Hs
 }
 
 // write the computed tiles of a panel (its rows, the columns of tiles >= its own and the tail columns)
-template <bool TAIL, int TAU>
-__device__ __forceinline__ void hs_store(double2* __restrict__ state, int i, int lane, const HafRow<HS_TF, TAIL>& w) {
+template <bool TAIL, int NQ, int TAU>
+__device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase, int lane, const HafRow<HS_TF, TAIL>& w) {
     using C = HsCfg<TAIL>;
+    using T = HsTeam<NQ>;
     constexpr int TF = HS_TF, m = C::M;
-    const int g = lane >> 2, t = lane & 3, q = g & 3, half = g >> 2;
-    double2* row = state + q * C::QS + (i + half * m) * C::LD;
+    const int t = lane & 3, half = lane >> 4;
+    if (TAU == TF && T::ps(lane)) return;                               // repeated rows of the tail panel
+    double2* row = state + T::q(lane) * C::QS + (ibase + (TAU == TF ? 0 : T::ps(lane)) + half * m) * C::LD;
 #pragma unroll
     for (int tau = TAU; tau < TF; ++tau) {
 #pragma unroll
@@ -326,76 +361,84 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int i, int
     if (TAIL && t < 2) row[4 * TF + (t & 1) * m] = make_double2(w.wtr, w.wti);
 }
 
-// one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ its K chunk of the tail panel)
-template <bool TAIL, int RHO>
+// one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ its K chunks of the tail panel)
+template <bool TAIL, int NQ, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, int k, bool needO, bool needE, bool store, uint64_t jq,
-                                             int lane, int warp, double2* __restrict__ tailC, double (&tr)[6]) {
+                                             int lane, int team, int wl, double2* __restrict__ tailC, double (&tr)[6]) {
+    using T = HsTeam<NQ>;
     constexpr int TF = HS_TF;
-    const int iA = 4 * RHO + sub, iB = 4 * (TF - 1 - RHO) + sub;
+    const int iA = 4 * RHO + T::PP * sub, iB = 4 * (TF - 1 - RHO) + T::PP * sub;
     HafRow<TF, TAIL> wA, wB;
     HsY<TAIL> yC;
     if (TAIL) {
-        yC = hs_rows<TAIL>(state, A, 4 * TF, k, jq, lane);
-        tailC[warp * 32 + lane] = hs_tail_chunk<TAIL>(sfrag, lane, warp, yC);
+        yC = hs_rows<TAIL, NQ>(state, A, 4 * TF, true, k, jq, lane);
+        tailC[wl * 32 + lane] = hs_tail_chunk<TAIL, 2 * TF / T::TW>(sfrag, lane, wl, yC);
     }
-    const HsY<TAIL> yA = hs_rows<TAIL>(state, A, iA, k, jq, lane), yB = hs_rows<TAIL>(state, A, iB, k, jq, lane);
+    const HsY<TAIL> yA = hs_rows<TAIL, NQ>(state, A, iA, false, k, jq, lane), yB = hs_rows<TAIL, NQ>(state, A, iB, false, k, jq, lane);
     hs_step2<TAIL, RHO>(sfrag, lane, yA, yB, wA, wB);
-    hs_traces<TAIL, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
-    hs_traces<TAIL, RHO>(wA, yA, iA, needO, needE, lane, tr);
-    __syncthreads();                       // every panel has read its rows of B_k; the partial tail tiles are in shared memory
+    hs_traces<TAIL, NQ, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
+    hs_traces<TAIL, NQ, RHO>(wA, yA, iA, needO, needE, lane, tr);
+    T::sync(team);                         // every panel has read its rows of B_k; the partial tail tiles are in shared memory
     if (store) {
-        hs_store<TAIL, RHO>(state, iA, lane, wA);
-        hs_store<TAIL, TF - 1 - RHO>(state, iB, lane, wB);
+        hs_store<TAIL, NQ, RHO>(state, iA, lane, wA);
+        hs_store<TAIL, NQ, TF - 1 - RHO>(state, iB, lane, wB);
     }
-    if (TAIL && warp == 0) {
+    if (TAIL && wl == 0) {
         HafRow<TF, TAIL> wC;
         wC.wtr = wC.wti = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < HS_WARPS; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
-        hs_traces<TAIL, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
-        if (store) hs_store<TAIL, TF>(state, 4 * TF, lane, wC);
+        for (int wv = 0; wv < T::TW; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
+        hs_traces<TAIL, NQ, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+        if (store) hs_store<TAIL, NQ, TF>(state, 4 * TF, lane, wC);
     }
 }
 
-template <bool TAIL>
+template <bool TAIL, int NQ>
 __global__ void __launch_bounds__(32 * HS_WARPS, 1)
-haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials) {
+haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, long long skew_cycles) {
     using C = HsCfg<TAIL>;
-    constexpr int TF = HS_TF, m = C::M, n = C::N;
+    using T = HsTeam<NQ>;
+    constexpr int TF = HS_TF, m = C::M, n = C::N, TW = T::TW;
     extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int team = T::team(warp), wl = T::wl(warp);
     double2* sfrag = reinterpret_cast<double2*>(smem);
-    double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D);
-    double* Pk = smem + C::FRAG_D + 2 * (size_t)C::STATE_D2;          // P[q][j] complex
-    double* ptmp = Pk + C::P_D;                                        // [kind][warp][row] complex
-    double2* tailC = reinterpret_cast<double2*>(ptmp + C::TMP_D);      // [warp][lane]
+    double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D) + team * NQ * C::QS;                    // [subset][row][col]
+    double2* P2 = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2) + team * NQ * (m + 2);   // P[subset][j]
+    double2* ptmp = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2 + C::P_D) + team * 3 * TW * 8;   // [kind][warp][row]
+    double2* tailC = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2 + C::P_D + C::TMP_D) + team * TW * 32;   // [warp][lane]
     haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
     __syncthreads();
+    // optional start skew of the second team (see HsTeam): n = 50 gains 1 % from ~ a product's length, n = 48 loses 5 %
+    if (NQ == 2 && team == 1) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < skew_cycles) __nanosleep(200);
+    }
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3, q = g & 3;
-    const int rho = warp >> 2, sub = warp & 3;
+    const int g = lane >> 2, t = lane & 3, q = T::q(lane);
+    const int rho = wl / T::SUBS, sub = wl % T::SUBS;
     const int nprod = (m - 1) >> 1, K = nprod + 1;
-    const uint64_t ngroups = (j1 - j0 + 3) >> 2;
+    const uint64_t ngroups = (j1 - j0 + NQ - 1) / NQ;
 
     const double inv_lane = 1.0 / (double)(lane ? lane : 1);
     cdd acc;
     acc.re = {0.0, 0.0};
     acc.im = {0.0, 0.0};
 
-    for (uint64_t G = blockIdx.x; G < ngroups; G += gridDim.x) {
-        const uint64_t jq = j0 + 4 * G + q;
-        if (warp == 0) {
+    for (uint64_t G = (uint64_t)blockIdx.x * T::TEAMS + team; G < ngroups; G += (uint64_t)gridDim.x * T::TEAMS) {
+        const uint64_t jq = j0 + NQ * G + q;
+        if (wl == 0) {
             // tr(M^1) = sum_r delta_r A'[r][sigma(r)] = 2 sum_i delta_i A'[i][i + m]; every P[1..m] is rewritten for every group
-            if (lane < 4) {
-                const uint64_t jj = j0 + 4 * G + lane;
+            if (lane < NQ) {
+                const uint64_t jj = j0 + NQ * G + lane;
                 double sr = 0.0, si = 0.0;
                 for (int i = 0; i < m; ++i) {
                     const double d = ((jj >> (m - 1 - i)) & 1ull) ? 2.0 : -2.0;
                     sr += d * __ldg(A + 2 * ((size_t)i * n + i + m));
                     si += d * __ldg(A + 2 * ((size_t)i * n + i + m) + 1);
                 }
-                Pk[(lane * (m + 2) + 1) * 2] = sr; Pk[(lane * (m + 2) + 1) * 2 + 1] = si;
+                P2[lane * (m + 2) + 1] = make_double2(sr, si);
             }
             __syncwarp();
         }
@@ -404,10 +447,10 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             const bool needE = (2 * k + 2 > K) && (2 * k + 2 <= m);
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
-            if (rho == 0) hs_warp_step<TAIL, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tailC, tr);
-            else if (rho == 1) hs_warp_step<TAIL, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tailC, tr);
-            else hs_warp_step<TAIL, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, warp, tailC, tr);
-            // per-row trace shares of this warp: reduce over the four lanes of a row, park them for warp 0
+            if (rho == 0) hs_warp_step<TAIL, NQ, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, tr);
+            else if (rho == 1) hs_warp_step<TAIL, NQ, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, tr);
+            else hs_warp_step<TAIL, NQ, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, tr);
+            // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
                 tr[c] += shfl_xor_d(tr[c], 1);
@@ -415,38 +458,38 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             }
             if (t == 0) {
 #pragma unroll
-                for (int kind = 0; kind < 3; ++kind)
-                    reinterpret_cast<double2*>(ptmp)[(kind * HS_WARPS + warp) * 8 + g] = make_double2(tr[2 * kind], tr[2 * kind + 1]);
+                for (int kind = 0; kind < 3; ++kind) ptmp[(kind * TW + wl) * 8 + g] = make_double2(tr[2 * kind], tr[2 * kind + 1]);
             }
-            __syncthreads();                   // B_(k+1) is complete in shared memory; so are this step's trace shares
-            {   // warp w sums the 24 shares (12 warps x the two rows of a subset) of ONE (kind, subset) in a fixed shuffle tree
-                const int kind = warp >> 2, qq = warp & 3;
+            T::sync(team);                     // B_(k+1) is complete in shared memory; so are this step's trace shares
+            {   // warp w of the team sums the 24 shares (TW warps x the 8 / NQ rows of a subset) of ONE (kind, subset) in a fixed
+                // shuffle tree
+                constexpr int RPS = 8 / NQ;    // rows per subset in a panel
+                const int kind = wl / NQ, qq = wl % NQ;
                 double2 e = make_double2(0.0, 0.0);
-                if (lane < 2 * HS_WARPS) e = reinterpret_cast<const double2*>(ptmp)[(kind * HS_WARPS + (lane >> 1)) * 8 + qq + 4 * (lane & 1)];
+                if (lane < TW * RPS) e = ptmp[(kind * TW + lane / RPS) * 8 + qq + NQ * (lane % RPS)];
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) { e.x += shfl_xor_d(e.x, off); e.y += shfl_xor_d(e.y, off); }
                 const int j = kind == 0 ? k + 1 : (kind == 1 ? 2 * k + 1 : 2 * k + 2);
                 const bool want = kind == 0 || (kind == 1 ? needO : needE);
-                if (lane == 0 && want && j <= m) reinterpret_cast<double2*>(Pk)[qq * (m + 2) + j] = e;
+                if (lane == 0 && want && j <= m) P2[qq * (m + 2) + j] = e;
             }
         }
-        __syncthreads();                       // the last step's traces are in P
-        // ---- series c_s = (1/s) sum_i (p_i / 2) c_(s-i), warp 0, "push" form: lane l holds the partial sum of target index l
-        // for each of the four subsets (four independent chains); step s: lane s finishes c_s, one broadcast, and every lane
-        // l > s adds F_(l-s) c_s.  (The first version split each inner sum over 8 lanes with two FP64 divisions and three
+        T::sync(team);                         // the last step's traces are in P
+        // ---- series c_s = (1/s) sum_i (p_i / 2) c_(s-i), first warp of the team, "push" form: lane l holds the partial sum of
+        // target index l for each of the NQ subsets (independent chains); step s: lane s finishes c_s, one broadcast, and every
+        // lane l > s adds F_(l-s) c_s.  (The first version split each inner sum over 8 lanes with two FP64 divisions and three
         // shuffle levels per step: 28 k cycles per group, 8 % of the kernel.)
-        if (warp == 0) {
-            const double2* P2 = reinterpret_cast<const double2*>(Pk);
-            double ar[4], ai[4];
+        if (wl == 0) {
+            double ar[NQ], ai[NQ];
 #pragma unroll
-            for (int qq = 0; qq < 4; ++qq) {
+            for (int qq = 0; qq < NQ; ++qq) {
                 const double2 f = (lane >= 1 && lane <= m) ? P2[qq * (m + 2) + lane] : make_double2(0.0, 0.0);
                 ar[qq] = 0.5 * f.x; ai[qq] = 0.5 * f.y;                    // c_0 = 1
             }
             for (int sidx = 1; sidx < m; ++sidx) {
                 const bool tgt = lane > sidx && lane <= m;
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
+                for (int qq = 0; qq < NQ; ++qq) {
                     const double cr = shfl_d(ar[qq] * inv_lane, sidx), ci = shfl_d(ai[qq] * inv_lane, sidx);
                     const double2 f = tgt ? P2[qq * (m + 2) + lane - sidx] : make_double2(0.0, 0.0);
                     const double fr = 0.5 * f.x, fi = 0.5 * f.y;
@@ -456,8 +499,8 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             }
             if (lane == m) {
 #pragma unroll
-                for (int qq = 0; qq < 4; ++qq) {
-                    const uint64_t jj = j0 + 4 * G + qq;
+                for (int qq = 0; qq < NQ; ++qq) {
+                    const uint64_t jj = j0 + NQ * G + qq;
                     if (jj < j1) {
                         const double sg = ((m - __popcll(jj)) & 1) ? -1.0 : 1.0;
                         dd_add(acc.re, sg * ar[qq] * inv_lane);
@@ -472,24 +515,30 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     block_reduce_store(acc, red, partials);
 }
 
-template <bool TAIL>
+template <bool TAIL, int NQ>
 static int launch_haf_sym(const double* dA, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
     using C = HsCfg<TAIL>;
-    auto kern = haf_sym_kernel<TAIL>;
+    auto kern = haf_sym_kernel<TAIL, NQ>;
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
     const int grid = (int)(ngroups < (uint64_t)sms ? (ngroups ? ngroups : 1) : (uint64_t)sms);
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
-    kern<<<grid, 32 * HS_WARPS, C::BYTES, st>>>(dA, j0, j1, partials);
+    const char* ek = getenv("WB200_HS_SKEW");
+    const long long skew = ek ? atoll(ek) : (TAIL ? 20000 : 0);
+    kern<<<grid, 32 * HS_WARPS, C::BYTES, st>>>(dA, j0, j1, partials, skew);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
 }
 
-// Used by wb200_hafnian_dev for n = 48 / 50 without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel).
-// Returns WB200_ENOSUP when the shape is not one of the two this kernel is built for.
+// Used by wb200_hafnian_dev for n = 48 / 50 without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the one-team
+// shape of the symmetric-half kernel).  Returns WB200_ENOSUP when the shape is not one of the two this kernel is built for.
 int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
-    if (n == 48) return launch_haf_sym<false>(dA, j0, j1, partials, sms, grid_out, st);
-    if (n == 50) return launch_haf_sym<true>(dA, j0, j1, partials, sms, grid_out, st);
+    const char* es = getenv("WB200_HAF_SYM");
+    const bool one_team = es && atoi(es) == 4;
+    if (n == 48) return one_team ? launch_haf_sym<false, 4>(dA, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<false, 2>(dA, j0, j1, partials, sms, grid_out, st);
+    if (n == 50) return one_team ? launch_haf_sym<true, 4>(dA, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<true, 2>(dA, j0, j1, partials, sms, grid_out, st);
     return WB200_ENOSUP;
 }
 
