@@ -145,6 +145,24 @@ struct HsCur {
     }
 };
 
+// Split-phase barrier (mbarrier in shared memory, one arrival per warp): "every panel has read its rows of B_k" is true
+// when every warp has LEFT its K loop, but a warp needs it only when it is about to store - after its trace pairing,
+// which reads nothing but the warp's own rows.  Arriving before the pairing and waiting after it hides the skew between
+// the warps' K loops under the pairing phase.
+__device__ __forceinline__ void hs_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void hs_mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.release.cta.shared::cta.b64 st, [%0]; }" :: "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void hs_mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+
 // The tail panel (the one vertex pair beyond the full tiles, n = 50): only its 2 x 2 tail block has to be computed, every
 // other entry of its rows arrives by symmetry.  That is 25 DMMAs in one dependent chain - on one warp it made that warp
 // late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies K chunks w CH .. w CH + CH - 1
@@ -365,7 +383,7 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase,
 template <bool TAIL, int NQ, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, int k, bool needO, bool needE, bool store, uint64_t jq,
-                                             int lane, int team, int wl, double2* __restrict__ tailC, double (&tr)[6]) {
+                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
     using T = HsTeam<NQ>;
     constexpr int TF = HS_TF;
     const int iA = 4 * RHO + T::PP * sub, iB = 4 * (TF - 1 - RHO) + T::PP * sub;
@@ -377,9 +395,11 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     }
     const HsY<TAIL> yA = hs_rows<TAIL, NQ>(state, A, iA, false, k, jq, lane), yB = hs_rows<TAIL, NQ>(state, A, iB, false, k, jq, lane);
     hs_step2<TAIL, RHO>(sfrag, lane, yA, yB, wA, wB);
+    __syncwarp();
+    if (lane == 0) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
     hs_traces<TAIL, NQ, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
     hs_traces<TAIL, NQ, RHO>(wA, yA, iA, needO, needE, lane, tr);
-    T::sync(team);                         // every panel has read its rows of B_k; the partial tail tiles are in shared memory
+    hs_mbar_wait(barA, parity);           // every panel has read its rows of B_k; the partial tail tiles are in shared memory
     if (store) {
         hs_store<TAIL, NQ, RHO>(state, iA, lane, wA);
         hs_store<TAIL, NQ, TF - 1 - RHO>(state, iB, lane, wB);
@@ -408,6 +428,9 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     double2* P2 = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2) + team * NQ * (m + 2);   // P[subset][j]
     double2* ptmp = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2 + C::P_D) + team * 3 * TW * 8;   // [kind][warp][row]
     double2* tailC = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2 + C::P_D + C::TMP_D) + team * TW * 32;   // [warp][lane]
+    __shared__ uint64_t bars[2];
+    uint64_t* barA = bars + team;
+    if (threadIdx.x < T::TEAMS) hs_mbar_init(bars + threadIdx.x, TW);
     haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
     __syncthreads();
     // optional start skew of the second team (see HsTeam): n = 50 gains 1 % from ~ a product's length, n = 48 loses 5 %
@@ -422,6 +445,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     const uint64_t ngroups = (j1 - j0 + NQ - 1) / NQ;
 
     const double inv_lane = 1.0 / (double)(lane ? lane : 1);
+    unsigned uses = 0;
     cdd acc;
     acc.re = {0.0, 0.0};
     acc.im = {0.0, 0.0};
@@ -447,9 +471,10 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             const bool needE = (2 * k + 2 > K) && (2 * k + 2 <= m);
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
-            if (rho == 0) hs_warp_step<TAIL, NQ, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, tr);
-            else if (rho == 1) hs_warp_step<TAIL, NQ, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, tr);
-            else hs_warp_step<TAIL, NQ, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, tr);
+            const unsigned parity = uses++ & 1u;            // phase of the split barrier: one use per product
+            if (rho == 0) hs_warp_step<TAIL, NQ, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
+            else if (rho == 1) hs_warp_step<TAIL, NQ, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
+            else hs_warp_step<TAIL, NQ, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
