@@ -97,13 +97,14 @@ __device__ __forceinline__ unsigned hs_sign(uint64_t jq, int p) {
 // One row of Y_k = B_k S, read just in time: chunk kap, position t of the lane.  Y_k[v][c] = delta_c B_k[v][sigma(c)], with
 // B_1 = A' (global memory, k = 1) or B_k in the shared-memory state.  Holding the row in registers (as haf_dmma_kernel
 // does) on top of the accumulators of two panels does not fit 168 registers.
-template <bool TAIL>
+template <bool TAIL, bool FIRST>
 struct HsY {
     const double2* row;      // row of this lane's (subset, vertex): state (stride LD) or A' (stride n, k = 1)
     const double2* col;      // the same vertex as a COLUMN of the state: entry [c][v] = col[c * LD]
     uint64_t jq;
     int t;
-    bool first;              // k = 1: B_1 = A', every entry is there, read row-wise
+    static constexpr bool first = FIRST;   // k = 1: B_1 = A' (global memory), every entry is there, read row-wise;
+                                           // a compile-time property, so that the loads of k > 1 are plain LDS
     __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {   // computed tiles only (row-wise)
         constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
         if (kap < 2 * TF) {
@@ -126,21 +127,21 @@ struct HsY {
 // A panel of tile T computed and stored only the columns of tiles >= T of its rows; the entries of earlier tiles were
 // computed by other panels as THEIR rows, and B_k is symmetric: read them column-wise (conflict-free with the padded
 // strides).  Nothing is stored twice (the first version stored every strictly-upper tile also transposed: 6 % of the kernel).
-template <bool TAIL, int T>
+template <bool TAIL, bool FIRST, int T>
 struct HsCur {
     const double2* p;
     int d, inc;
-    __device__ __forceinline__ void init(const HsY<TAIL>& y) {
+    __device__ __forceinline__ void init(const HsY<TAIL, FIRST>& y) {
         constexpr int m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
         if (y.first || T == 0) { p = y.row + y.t; d = m; inc = 4; }
         else { p = y.col + y.t * LD; d = m * LD; inc = 4 * LD; }
     }
-    __device__ __forceinline__ void next(const HsY<TAIL>& y, int tau_next) {
+    __device__ __forceinline__ void next(const HsY<TAIL, FIRST>& y, int tau_next) {
         constexpr int m = HsCfg<TAIL>::M;
         if (T > 0 && T < HS_TF && !y.first && tau_next == T) { p = y.row + 4 * T + y.t; d = m; inc = 4; }
         else p += inc;
     }
-    __device__ __forceinline__ double2 tail(const HsY<TAIL>& y) const {    // tail columns: every panel computes them itself
+    __device__ __forceinline__ double2 tail(const HsY<TAIL, FIRST>& y) const {    // tail columns: every panel computes them itself
         return y.row[4 * HS_TF + (1 - (y.t & 1)) * HsCfg<TAIL>::M];
     }
 };
@@ -168,8 +169,8 @@ __device__ __forceinline__ void hs_mbar_wait(uint64_t* bar, unsigned parity) {
 // late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies K chunks w CH .. w CH + CH - 1
 // (the first warp also the packed tail chunk), the partial tiles meet in shared memory and the first warp sums them in
 // warp order while the others store.
-template <bool TAIL, int CH>
-__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<TAIL>& y) {
+template <bool TAIL, bool FIRST, int CH>
+__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<TAIL, FIRST>& y) {
     constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
     double pr = 0.0, pi = 0.0, p2r = 0.0, p2i = 0.0;
 #pragma unroll
@@ -197,8 +198,8 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
 // The two panels of a warp (tiles RHO and 5 - RHO) in ONE pass over K: the panel of the later tile needs a subset of the
 // fragments of the other, so every 16-byte fragment load feeds both, and the DMMAs of two independent panels interleave
 // (a one-tile panel alone is a chain of dependent DMMAs).
-template <bool TAIL, int RHO>
-__device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<TAIL>& yA, const HsY<TAIL>& yB,
+template <bool TAIL, bool FIRST, int RHO>
+__device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<TAIL, FIRST>& yA, const HsY<TAIL, FIRST>& yB,
                                          HafRow<HS_TF, TAIL>& wA, HafRow<HS_TF, TAIL>& wB) {
     constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, TB = TF - 1 - RHO;
 #pragma unroll
@@ -214,8 +215,8 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
     wA.wtr = wA.wti = 0.0;
     wB.wtr = wB.wti = 0.0;
     const double2* fr = sfrag + lane;
-    HsCur<TAIL, RHO> curA;
-    HsCur<TAIL, TB> curB;
+    HsCur<TAIL, FIRST, RHO> curA;
+    HsCur<TAIL, FIRST, TB> curB;
     curA.init(yA); curB.init(yB);
     int sh = m - 1 - yA.t;
     double2 a0 = curA.p[curA.d], a1 = curA.p[0], c0 = curB.p[curB.d], c1 = curB.p[0];     // fetched one iteration ahead
@@ -286,8 +287,8 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
 
 // Local pairing sums of one panel over its computed tiles: odd = <W(partner row), Y_old(own row)>, even = the same with
 // Y_new = S W(own row); strictly-upper tiles weigh 2, the diagonal tile 1 (see the header).  Not reduced over lanes.
-template <bool TAIL, int TAU>
-__device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL>& y,
+template <bool TAIL, bool FIRST, int TAU>
+__device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL, FIRST>& y,
                                            double& orr, double& oi, double& er, double& ei) {
     constexpr int TF = HS_TF;
     orr = oi = er = ei = 0.0;
@@ -319,25 +320,24 @@ __device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const H
 
 // the rows of Y_k = B_k S of a panel (first vertex pair ibase) as seen by this lane: from A' at k = 1 (B_1 = A', read
 // through the generic path), else from the team's shared-memory state
-template <bool TAIL, int NQ>
-__device__ __forceinline__ HsY<TAIL> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
-                                             int k, uint64_t jq, int lane) {
+template <bool TAIL, bool FIRST, int NQ>
+__device__ __forceinline__ HsY<TAIL, FIRST> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
+                                             uint64_t jq, int lane) {
     using C = HsCfg<TAIL>;
     using T = HsTeam<NQ>;
     constexpr int m = C::M, n = C::N;
     const int half = lane >> 4;
     const int v = ibase + (tailrows ? 0 : T::ps(lane)) + half * m;      // tail panel: the rows of the second pair slot repeat the first
-    HsY<TAIL> y;
-    y.first = k == 1;
-    y.row = y.first ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + T::q(lane) * C::QS + v * C::LD;
+    HsY<TAIL, FIRST> y;
+    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + T::q(lane) * C::QS + v * C::LD;
     y.col = state + T::q(lane) * C::QS + v;
     y.jq = jq; y.t = lane & 3;
     return y;
 }
 
 // trace shares of one computed panel (first vertex pair ibase, tile TAU), added to the per-lane sums
-template <bool TAIL, int NQ, int TAU>
-__device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL>& y, int ibase, bool needO, bool needE, int lane,
+template <bool TAIL, bool FIRST, int NQ, int TAU>
+__device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL, FIRST>& y, int ibase, bool needO, bool needE, int lane,
                                           double (&tr)[6]) {
     constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
     constexpr bool in_tail = TAIL && TAU == TF;
@@ -356,7 +356,7 @@ __device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const Hs
     }
     if (needO || needE) {
         double orr, oi, er, ei;
-        hs_pairing<TAIL, TAU>(w, y, orr, oi, er, ei);
+        hs_pairing<TAIL, FIRST, TAU>(w, y, orr, oi, er, ei);
         tr[2] += rs * orr; tr[3] += rs * oi;
         tr[4] += rs * er; tr[5] += rs * ei;
     }
@@ -380,25 +380,25 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase,
 }
 
 // one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ its K chunks of the tail panel)
-template <bool TAIL, int NQ, int RHO>
+template <bool TAIL, bool FIRST, int NQ, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
-                                             int sub, int k, bool needO, bool needE, bool store, uint64_t jq,
+                                             int sub, bool needO, bool needE, bool store, uint64_t jq,
                                              int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
     using T = HsTeam<NQ>;
     constexpr int TF = HS_TF;
     const int iA = 4 * RHO + T::PP * sub, iB = 4 * (TF - 1 - RHO) + T::PP * sub;
     HafRow<TF, TAIL> wA, wB;
-    HsY<TAIL> yC;
+    HsY<TAIL, FIRST> yC;
     if (TAIL) {
-        yC = hs_rows<TAIL, NQ>(state, A, 4 * TF, true, k, jq, lane);
-        tailC[wl * 32 + lane] = hs_tail_chunk<TAIL, 2 * TF / T::TW>(sfrag, lane, wl, yC);
+        yC = hs_rows<TAIL, FIRST, NQ>(state, A, 4 * TF, true, jq, lane);
+        tailC[wl * 32 + lane] = hs_tail_chunk<TAIL, FIRST, 2 * TF / T::TW>(sfrag, lane, wl, yC);
     }
-    const HsY<TAIL> yA = hs_rows<TAIL, NQ>(state, A, iA, false, k, jq, lane), yB = hs_rows<TAIL, NQ>(state, A, iB, false, k, jq, lane);
-    hs_step2<TAIL, RHO>(sfrag, lane, yA, yB, wA, wB);
+    const HsY<TAIL, FIRST> yA = hs_rows<TAIL, FIRST, NQ>(state, A, iA, false, jq, lane), yB = hs_rows<TAIL, FIRST, NQ>(state, A, iB, false, jq, lane);
+    hs_step2<TAIL, FIRST, RHO>(sfrag, lane, yA, yB, wA, wB);
     __syncwarp();
     if (lane == 0) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
-    hs_traces<TAIL, NQ, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
-    hs_traces<TAIL, NQ, RHO>(wA, yA, iA, needO, needE, lane, tr);
+    hs_traces<TAIL, FIRST, NQ, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
+    hs_traces<TAIL, FIRST, NQ, RHO>(wA, yA, iA, needO, needE, lane, tr);
     hs_mbar_wait(barA, parity);           // every panel has read its rows of B_k; the partial tail tiles are in shared memory
     if (store) {
         hs_store<TAIL, NQ, RHO>(state, iA, lane, wA);
@@ -409,7 +409,7 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
         wC.wtr = wC.wti = 0.0;
 #pragma unroll
         for (int wv = 0; wv < T::TW; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
-        hs_traces<TAIL, NQ, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+        hs_traces<TAIL, FIRST, NQ, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
         if (store) hs_store<TAIL, NQ, TF>(state, 4 * TF, lane, wC);
     }
 }
@@ -472,9 +472,13 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
             const unsigned parity = uses++ & 1u;            // phase of the split barrier: one use per product
-            if (rho == 0) hs_warp_step<TAIL, NQ, 0>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
-            else if (rho == 1) hs_warp_step<TAIL, NQ, 1>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
-            else hs_warp_step<TAIL, NQ, 2>(sfrag, state, A, sub, k, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
+#define WB_HS_STEP(first, r) hs_warp_step<TAIL, first, NQ, r>(sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr)
+            if (k == 1) {                      // B_1 = A' is read from global memory
+                if (rho == 0) WB_HS_STEP(true, 0); else if (rho == 1) WB_HS_STEP(true, 1); else WB_HS_STEP(true, 2);
+            } else {
+                if (rho == 0) WB_HS_STEP(false, 0); else if (rho == 1) WB_HS_STEP(false, 1); else WB_HS_STEP(false, 2);
+            }
+#undef WB_HS_STEP
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
