@@ -138,10 +138,10 @@ def haf_sym_entries(n):
     row panel of a vertex pair in tile T (tiles = 4 vertex pairs = 8 rows/columns) computes the columns of tiles >= T
     and of the tail pair; the tail pair's panel only its own 2 x 2 block."""
     m = n // 2
-    if n % 2 or m not in (24, 25):
+    if n % 2 or m not in (24, 25, 28):
         return 0
-    tail = m - 24
-    return sum(8 * (8 * (6 - T) + 2 * tail) for T in range(6)) + 4 * tail
+    TF, tail = m // 4, m % 4
+    return sum(8 * (8 * (TF - T) + 2 * tail) for T in range(TF)) + 4 * tail
 
 
 def units_and_flops(kind, n):

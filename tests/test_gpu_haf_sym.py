@@ -1,7 +1,7 @@
-"""Symmetric-half hafnian kernel (thewalrus_b200/csrc/hafnian_sym.cu; n = 48 / 50, no loops, large ranges) against
+"""Symmetric-half hafnian kernel (thewalrus_b200/csrc/hafnian_sym.cu; n = 48 / 50 / 56, no loops, large ranges) against
 (i) the C oracle's restatement of the reference sum (thewalrus/_hafnian.py:416-467) on the same subset ranges,
 (ii) the row-panel kernel on the same ranges (WB200_HAF_SYM=0), (iii) exact closed forms of complete hafnians.
-The complete n = 50 goldens of tests/test_gpu_fullsize.py run through this kernel too (it is the default for n = 50).
+The complete n = 50 / 56 goldens of tests/test_gpu_fullsize.py run through this kernel too (it is the default for these sizes).
 
 Tolerance 1e-10 relative (north_star); measured gaps are printed."""
 import math
@@ -29,7 +29,7 @@ def _input(n, seed, real=False):
 
 def _range(Ax, j0, j1, sym):
     old = os.environ.get("WB200_HAF_SYM")
-    os.environ["WB200_HAF_SYM"] = "1" if sym else "0"
+    os.environ["WB200_HAF_SYM"] = str(int(sym))
     try:
         return _engine.combine4([_engine.hafnian_range(Ax, None, j0, j1)])
     finally:
@@ -39,7 +39,7 @@ def _range(Ax, j0, j1, sym):
             os.environ["WB200_HAF_SYM"] = old
 
 
-@pytest.mark.parametrize("n", [48, 50])
+@pytest.mark.parametrize("n", [48, 50, 56])
 @pytest.mark.parametrize("real", [False, True])
 def test_sym_kernel_ranges_match_oracle_and_row_panel_kernel(n, real):
     """Aligned, ragged and offset ranges (the kernel works on groups of four subsets; a range need not be a multiple)."""
@@ -89,10 +89,15 @@ def test_complete_hafnian_48_block_factorisation():
     assert rel(got, h1 * h2) <= 1e-9      # the product of two sums of 2^11 cancelling terms each; measured ~1e-12
 
 
-def test_row_panel_kernel_still_serves_n50_when_asked():
-    """WB200_HAF_SYM=0 keeps the round-1 kernel on the complete n = 50 sum: both kernels, same bits of input, 1e-10."""
-    Ax = _input(50, 5050)
+@pytest.mark.parametrize("n", [50, 56])
+def test_row_panel_kernel_still_serves_when_asked(n):
+    """WB200_HAF_SYM=0 keeps the round-1 kernel: both kernels on 2^20 subsets of the same input, 1e-10; =4 the one-team shape."""
+    Ax = _input(n, 5000 + n)
     s = _range(Ax, 0, 1 << 20, True)
     p = _range(Ax, 0, 1 << 20, False)
-    print(f"\n[haf_sym] n=50, 2^20 subsets: sym vs panel {rel(s, p):.2e}")
+    print(f"\n[haf_sym] n={n}, 2^20 subsets: sym vs panel {rel(s, p):.2e}")
     assert rel(s, p) <= TOL
+    if n == 50:
+        one = _range(Ax, 0, 1 << 20, 4)
+        print(f"[haf_sym] n={n}: one team of 12 warps vs two teams of 6: {rel(one, s):.2e}")
+        assert rel(one, s) <= TOL

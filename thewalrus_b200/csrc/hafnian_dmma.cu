@@ -292,7 +292,8 @@ static int launch_haf(const double* dA, const double* dD, int n, int m, uint64_t
 
 constexpr int HAF_MAX_GRID = 4096;
 
-// hafnian_sym.cu: symmetric-half kernel for n = 48 / 50 (WB200_ENOSUP for other shapes)
+// hafnian_sym.cu: symmetric-half kernel for n = 48 / 50 / 56 (WB200_ENOSUP for other shapes)
+bool haf_sym_supports(int n);
 int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st);
 
 }  // namespace wb
@@ -324,10 +325,10 @@ extern "C" int wb200_hafnian_dev(const double* dA, const double* dD, int n, uint
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
     int grid = 1;
     int rc = WB200_ENOSUP;
-    {   // full-size hafnians of n = 48 / 50 without loops: only the tiles on and above the diagonal of every product
+    {   // full-size hafnians of n = 48 / 50 / 56 without loops: only the tiles on and above the diagonal of every product
         const char* es = getenv("WB200_HAF_SYM");
         const bool want = !(es && atoi(es) == 0);
-        if (want && !dD && (n == 48 || n == 50) && ngroups >= 8ull * (uint64_t)sms) {
+        if (want && !dD && haf_sym_supports(n) && ngroups >= 8ull * (uint64_t)sms) {
             rc = haf_sym_launch(dA, n, j0, j1, partials, sms, &grid, st);
             if (rc) return rc;
             final_reduce_kernel<<<1, 32, 0, st>>>(partials, grid, d_out4);

@@ -43,61 +43,64 @@
 
 namespace wb {
 
-constexpr int HS_TF = 6;
-constexpr int HS_WARPS = 12;
-
-template <bool TAIL>
-struct HsCfg {
-    static constexpr int NK = 2 * HS_TF + (TAIL ? 1 : 0);
-    static constexpr int NT = HS_TF + (TAIL ? 1 : 0);
-    static constexpr int M = 4 * HS_TF + (TAIL ? 1 : 0);          // vertex pairs
+// Shape of an instance: TF full tiles of four vertex pairs (+ a one-pair packed tail), NQ subsets per group.
+//
+// Teams.  NQ = 4: the warps advance one group of four subsets (a DMMA's 8 rows = 4 subsets x the two vertices of a pair).
+// NQ = 2: 8 rows = 2 subsets x two vertex pairs x 2 - half the shared memory per group, so either two teams per CTA, each on
+// its own group (TF = 6, the default for n = 48 / 50: every barrier spans 6 warps instead of 12), or a size that does not
+// fit with four subsets at all (TF = 7, n = 56: one team).
+// The hope for two teams was more: teams running out of step, one team's barriers / store / pairing phases under the
+// other's DMMAs.  Measured (profiles/r02_haf_sym_skew.txt): holding the second team back by any fraction of a product changes
+// n = 50 by +1 % and n = 48 by -5 % - six warps cannot be spread evenly over four schedulers (2 + 1 + 2 + 1), so while one
+// team is in a phase the other team's warps on the 2-warp schedulers set its pace and the 1-warp schedulers idle.
+//
+// Roles.  A warp owns the panels of two tiles whose computed-tile counts add up to the same number for every warp:
+// TF even: tiles r and TF - 1 - r (TF + 1 tile units); TF odd: tile 0 alone, then tiles r and TF - r (TF tile units).
+template <int TF_, bool TAIL_, int NQ_>
+struct HsShape {
+    static constexpr int TF = TF_, NQ = NQ_;
+    static constexpr bool TAIL = TAIL_;
+    static constexpr int NK = 2 * TF + (TAIL ? 1 : 0);
+    static constexpr int NT = TF + (TAIL ? 1 : 0);
+    static constexpr int M = 4 * TF + (TAIL ? 1 : 0);              // vertex pairs
     static constexpr int N = 2 * M;
+    static constexpr int PP = 4 / NQ;                              // vertex pairs per row panel
+    static constexpr int SUBS = NQ;                                // panels per tile
+    static constexpr int ROLES = (TF + 1) / 2;
+    static constexpr int TW = ROLES * SUBS;                        // warps per team
+    static constexpr int TEAMS = (TF <= 6) ? 4 / NQ : 1;           // groups in flight per CTA (shared memory decides)
+    static constexpr int WARPS = TEAMS * TW;
     static constexpr int FRAG_D = NK * NT * 64;                    // doubles
-    static constexpr int LD = N + 1;                               // row stride of the state (entries): 4 LD = 12 (mod 32) words
+    static constexpr int LD = N + 1;                               // row stride of the state (entries): 4 LD = 4 or 12 (mod 32) words
     static constexpr int QS = ((N * LD + 7) / 8) * 8 + 4;          // subset stride: 4 QS = 16 (mod 32) words -> the two subsets of a
                                                                    // quarter warp never share a bank, row-wise or column-wise
-    static constexpr int STATE_D2 = 4 * QS;                        // double2: state[subset][row][col], only tiles >= the row's tile valid
-    static constexpr int P_D = (M + 2) * 4 * 2;                    // P[subset][j] complex (doubles)
-    static constexpr int TMP_D = 3 * HS_WARPS * 8 * 2;             // ptmp[team][kind][warp in team][row] complex (doubles)
-    static constexpr int TAILC_D = TAIL ? HS_WARPS * 32 * 2 : 0;   // partial tail tiles of the K-split tail panel (doubles)
+    static constexpr int STATE_D2 = TEAMS * NQ * QS;               // double2: state[team][subset][row][col], only tiles >= the row's tile valid
+    static constexpr int P_D = TEAMS * NQ * (M + 2) * 2;           // P[team][subset][j] complex (doubles)
+    static constexpr int TMP_D = TEAMS * 3 * TW * 8 * 2;           // ptmp[team][kind][warp in team][row] complex (doubles)
+    static constexpr int TAILC_D = TAIL ? WARPS * 32 * 2 : 0;      // partial tail tiles of the K-split tail panel (doubles)
     static constexpr size_t BYTES = sizeof(double) * ((size_t)FRAG_D + 2 * (size_t)STATE_D2 + P_D + TMP_D + TAILC_D);
-};
-
-// Teams.  NQ = 4: the 12 warps advance one group of four subsets (a DMMA's 8 rows = 4 subsets x the two vertices of a pair).
-// NQ = 2 (default): two teams of 6 warps, each on its own group of TWO subsets (8 rows = 2 subsets x two vertex pairs x 2):
-// same shared memory, same registers, same DMMAs per warp and product, but every barrier spans 6 warps instead of 12.
-// The hope was more: teams running out of step, one team's barriers / store / pairing phases under the other's DMMAs.
-// Measured (profiles/r02_haf_sym_skew.txt): holding the second team back by any fraction of a product changes n = 50 by
-// +1 % and n = 48 by -5 % - six warps cannot be spread evenly over four schedulers (2 + 1 + 2 + 1), so while one team is
-// in a phase the other team's warps on the 2-warp schedulers set its pace and the 1-warp schedulers idle.  Two teams of 8
-// warps (128 registers) would balance; the phases left to hide are 12 % of the kernel and the 6.5 / 6.0 tile-unit split
-// of 8 warps costs 7 %, so it was not built.
-template <int NQ>
-struct HsTeam {
-    static constexpr int TEAMS = 4 / NQ;                 // 1 or 2
-    static constexpr int TW = HS_WARPS / TEAMS;          // warps per team = 3 NQ
-    static constexpr int PP = 4 / NQ;                    // vertex pairs per row panel
-    static constexpr int SUBS = 4 / PP;                  // panels per tile
-    __device__ static __forceinline__ int team(int warp) { return NQ == 4 ? 0 : (((warp >> 2) + warp) & 1); }
-    __device__ static __forceinline__ int wl(int warp) { return NQ == 4 ? warp : (warp >> 1); }
+    __host__ __device__ static constexpr int roleA(int r) { return r; }
+    __host__ __device__ static constexpr int roleB(int r) { return (TF & 1) ? (r == 0 ? TF : TF - r) : TF - 1 - r; }      // TF: no second panel
+    __device__ static __forceinline__ int team(int warp) { return TEAMS == 1 ? 0 : (((warp >> 2) + warp) & 1); }
+    __device__ static __forceinline__ int wl(int warp) { return TEAMS == 1 ? warp : (warp >> 1); }
     __device__ static __forceinline__ int q(int lane) { return (lane >> 2) & (NQ - 1); }
     __device__ static __forceinline__ int ps(int lane) { return NQ == 4 ? 0 : ((lane >> 3) & 1); }
     __device__ static __forceinline__ void sync(int team) {
-        if (NQ == 4) __syncthreads();
+        if (TEAMS == 1) __syncthreads();
         else asm volatile("bar.sync %0, %1;" :: "r"(1 + team), "r"(32 * TW) : "memory");
     }
 };
 
 // sign mask of vertex pair p in subset jq: delta = +1 (bit set) -> 0, delta = -1 -> sign bit
-template <bool TAIL>
+template <class S>
 __device__ __forceinline__ unsigned hs_sign(uint64_t jq, int p) {
-    return ((unsigned)(jq >> (HsCfg<TAIL>::M - 1 - p)) & 1u) ? 0u : 0x80000000u;
+    return ((unsigned)(jq >> (S::M - 1 - p)) & 1u) ? 0u : 0x80000000u;
 }
 
 // One row of Y_k = B_k S, read just in time: chunk kap, position t of the lane.  Y_k[v][c] = delta_c B_k[v][sigma(c)], with
 // B_1 = A' (global memory, k = 1) or B_k in the shared-memory state.  Holding the row in registers (as haf_dmma_kernel
 // does) on top of the accumulators of two panels does not fit 168 registers.
-template <bool TAIL, bool FIRST>
+template <class S, bool FIRST>
 struct HsY {
     const double2* row;      // row of this lane's (subset, vertex): state (stride LD) or A' (stride n, k = 1)
     const double2* col;      // the same vertex as a COLUMN of the state: entry [c][v] = col[c * LD]
@@ -106,17 +109,17 @@ struct HsY {
     static constexpr bool first = FIRST;   // k = 1: B_1 = A' (global memory), every entry is there, read row-wise;
                                            // a compile-time property, so that the loads of k > 1 are plain LDS
     __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {   // computed tiles only (row-wise)
-        constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
+        constexpr int TF = S::TF, m = S::M;
         if (kap < 2 * TF) {
             const int tau = kap >> 1;
             const double2 a = row[4 * tau + t + (1 - (kap & 1)) * m];
-            const unsigned s = hs_sign<TAIL>(jq, 4 * tau + t);
+            const unsigned s = hs_sign<S>(jq, 4 * tau + t);
             yr = flipsign(a.x, s); yi = flipsign(a.y, s);
         } else {
             yr = yi = 0.0;
-            if (TAIL && t < 2) {
+            if (S::TAIL && t < 2) {
                 const double2 a = row[4 * TF + (1 - (t & 1)) * m];
-                const unsigned s = hs_sign<TAIL>(jq, 4 * TF);
+                const unsigned s = hs_sign<S>(jq, 4 * TF);
                 yr = flipsign(a.x, s); yi = flipsign(a.y, s);
             }
         }
@@ -127,22 +130,22 @@ struct HsY {
 // A panel of tile T computed and stored only the columns of tiles >= T of its rows; the entries of earlier tiles were
 // computed by other panels as THEIR rows, and B_k is symmetric: read them column-wise (conflict-free with the padded
 // strides).  Nothing is stored twice (the first version stored every strictly-upper tile also transposed: 6 % of the kernel).
-template <bool TAIL, bool FIRST, int T>
+template <class S, bool FIRST, int T>
 struct HsCur {
     const double2* p;
     int d, inc;
-    __device__ __forceinline__ void init(const HsY<TAIL, FIRST>& y) {
-        constexpr int m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
+    __device__ __forceinline__ void init(const HsY<S, FIRST>& y) {
+        constexpr int m = S::M, LD = S::LD;
         if (y.first || T == 0) { p = y.row + y.t; d = m; inc = 4; }
         else { p = y.col + y.t * LD; d = m * LD; inc = 4 * LD; }
     }
-    __device__ __forceinline__ void next(const HsY<TAIL, FIRST>& y, int tau_next) {
-        constexpr int m = HsCfg<TAIL>::M;
-        if (T > 0 && T < HS_TF && !y.first && tau_next == T) { p = y.row + 4 * T + y.t; d = m; inc = 4; }
+    __device__ __forceinline__ void next(const HsY<S, FIRST>& y, int tau_next) {
+        constexpr int m = S::M;
+        if (T > 0 && T < S::TF && !y.first && tau_next == T) { p = y.row + 4 * T + y.t; d = m; inc = 4; }
         else p += inc;
     }
-    __device__ __forceinline__ double2 tail(const HsY<TAIL, FIRST>& y) const {    // tail columns: every panel computes them itself
-        return y.row[4 * HS_TF + (1 - (y.t & 1)) * HsCfg<TAIL>::M];
+    __device__ __forceinline__ double2 tail(const HsY<S, FIRST>& y) const {    // tail columns: every panel computes them itself
+        return y.row[4 * S::TF + (1 - (y.t & 1)) * S::M];
     }
 };
 
@@ -169,23 +172,23 @@ __device__ __forceinline__ void hs_mbar_wait(uint64_t* bar, unsigned parity) {
 // late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies K chunks w CH .. w CH + CH - 1
 // (the first warp also the packed tail chunk), the partial tiles meet in shared memory and the first warp sums them in
 // warp order while the others store.
-template <bool TAIL, bool FIRST, int CH>
-__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<TAIL, FIRST>& y) {
-    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, LD = HsCfg<TAIL>::LD;
+template <class S, bool FIRST, int CH>
+__device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<S, FIRST>& y) {
+    constexpr int TF = S::TF, NT = S::NT, m = S::M, LD = S::LD;
     double pr = 0.0, pi = 0.0, p2r = 0.0, p2i = 0.0;
 #pragma unroll
     for (int cc = 0; cc < CH; ++cc) {
         const int kap = wl * CH + cc, tau = kap >> 1, h = kap & 1;
         const int c = 4 * tau + y.t + (1 - h) * m;                      // Y[v][chunk position] = delta B[v][c]
         const double2 a = y.first ? y.row[c] : y.col[c * LD];
-        const unsigned s = hs_sign<TAIL>(y.jq, 4 * tau + y.t);
+        const unsigned s = hs_sign<S>(y.jq, 4 * tau + y.t);
         const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
         dmma884(pr, pi, flipsign(a.x, s), b.x);
         dmma884(p2r, p2i, flipsign(a.y, s), b.y);
     }
     if (wl == 0) {
         const double2 at = y.row[4 * TF + (1 - (y.t & 1)) * m];
-        const unsigned st = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
+        const unsigned st = (y.t < 2) ? hs_sign<S>(y.jq, 4 * TF) : 0u;
         const double ar = (y.t < 2) ? flipsign(at.x, st) : 0.0, ai = (y.t < 2) ? flipsign(at.y, st) : 0.0;
         const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
         const double ap = (lane & 2) ? yi2 : ar;
@@ -195,15 +198,18 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
     return make_double2(pr + p2r, pi + p2i);
 }
 
-// The two panels of a warp (tiles RHO and 5 - RHO) in ONE pass over K: the panel of the later tile needs a subset of the
-// fragments of the other, so every 16-byte fragment load feeds both, and the DMMAs of two independent panels interleave
-// (a one-tile panel alone is a chain of dependent DMMAs).
-template <bool TAIL, bool FIRST, int RHO>
-__device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<TAIL, FIRST>& yA, const HsY<TAIL, FIRST>& yB,
-                                         HafRow<HS_TF, TAIL>& wA, HafRow<HS_TF, TAIL>& wB) {
-    constexpr int TF = HS_TF, NT = TF + (TAIL ? 1 : 0), m = HsCfg<TAIL>::M, TB = TF - 1 - RHO;
+// The two panels of a warp (tiles TA and TB > TA; TB == TF: only one panel) in ONE pass over K: the panel of the later tile
+// needs a subset of the fragments of the other, so every 16-byte fragment load feeds both, and the DMMAs of two independent
+// panels interleave (a one-tile panel alone is a chain of dependent DMMAs).
+// The loop over the K tiles is deliberately NOT unrolled: fully unrolled, ptxas hoists some thirty 16-byte fragment
+// loads to the top of the block (130 registers) and spills the accumulators.
+template <class S, bool FIRST, int TA, int TB>
+__device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<S, FIRST>& yA, const HsY<S, FIRST>& yB,
+                                         HafRow<S::TF, S::TAIL>& wA, HafRow<S::TF, S::TAIL>& wB) {
+    constexpr int TF = S::TF, NT = S::NT, m = S::M;
+    constexpr bool TAIL = S::TAIL, HASB = TB < TF;
 #pragma unroll
-    for (int tp = RHO; tp < TF; ++tp) {
+    for (int tp = TA; tp < TF; ++tp) {
         wA.wr[tp][0] = wA.wr[tp][1] = 0.0;
         wA.wi[tp][0] = wA.wi[tp][1] = 0.0;
     }
@@ -215,26 +221,33 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
     wA.wtr = wA.wti = 0.0;
     wB.wtr = wB.wti = 0.0;
     const double2* fr = sfrag + lane;
-    HsCur<TAIL, FIRST, RHO> curA;
-    HsCur<TAIL, FIRST, TB> curB;
+    HsCur<S, FIRST, TA> curA;
+    HsCur<S, FIRST, HASB ? TB : TA> curB;
     curA.init(yA); curB.init(yB);
     int sh = m - 1 - yA.t;
-    double2 a0 = curA.p[curA.d], a1 = curA.p[0], c0 = curB.p[curB.d], c1 = curB.p[0];     // fetched one iteration ahead
+    double2 a0 = curA.p[curA.d], a1 = curA.p[0], c0 = make_double2(0.0, 0.0), c1 = c0;     // fetched one iteration ahead
+    if (HASB) { c0 = curB.p[curB.d]; c1 = curB.p[0]; }
 #pragma unroll 1
     for (int tau = 0; tau < TF; ++tau) {
         const unsigned s = ((unsigned)(yA.jq >> sh) & 1u) ? 0u : 0x80000000u;
         // next K tile; after the last one: the tail element of lanes t = 0, 1 (an address every lane may read)
         const bool last = tau == TF - 1;
-        curA.next(yA, tau + 1); curB.next(yB, tau + 1);
+        curA.next(yA, tau + 1);
+        if (HASB) curB.next(yB, tau + 1);
         double2 n0 = make_double2(0.0, 0.0), n1 = n0, d0 = n0, d1 = n0;
-        if (!last) { n0 = curA.p[curA.d]; n1 = curA.p[0]; d0 = curB.p[curB.d]; d1 = curB.p[0]; }
-        else if (TAIL) { n0 = curA.tail(yA); d0 = curB.tail(yB); }
+        if (!last) {
+            n0 = curA.p[curA.d]; n1 = curA.p[0];
+            if (HASB) { d0 = curB.p[curB.d]; d1 = curB.p[0]; }
+        } else if (TAIL) {
+            n0 = curA.tail(yA);
+            if (HASB) d0 = curB.tail(yB);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const double ar = flipsign(h ? a1.x : a0.x, s), ai = flipsign(h ? a1.y : a0.y, s);
             const double cr = flipsign(h ? c1.x : c0.x, s), ci = flipsign(h ? c1.y : c0.y, s);
 #pragma unroll
-            for (int tp = RHO; tp < TF; ++tp) {
+            for (int tp = TA; tp < TF; ++tp) {
                 const double2 b = fr[tp * 32];
                 const double nbi = -b.y;
                 dmma884(wA.wr[tp][0], wA.wr[tp][1], ar, b.x);
@@ -253,9 +266,9 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
             if (TAIL) {
                 const double2 b = fr[TF * 32];
                 dmma884(wA.wtr, wA.wti, ar, b.x);
-                dmma884(wB.wtr, wB.wti, cr, b.x);
+                if (HASB) dmma884(wB.wtr, wB.wti, cr, b.x);
                 dmma884(wA.wtr, wA.wti, ai, b.y);
-                dmma884(wB.wtr, wB.wti, ci, b.y);
+                if (HASB) dmma884(wB.wtr, wB.wti, ci, b.y);
             }
             fr += NT * 32;
         }
@@ -264,13 +277,13 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
     }
     if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
         const bool own = yA.t < 2;
-        const unsigned s = own ? hs_sign<TAIL>(yA.jq, 4 * TF) : 0u;
+        const unsigned s = own ? hs_sign<S>(yA.jq, 4 * TF) : 0u;
         const double ar = own ? flipsign(a0.x, s) : 0.0, ai = own ? flipsign(a0.y, s) : 0.0;
         const double cr = own ? flipsign(c0.x, s) : 0.0, ci = own ? flipsign(c0.y, s) : 0.0;
         const double ai2 = __shfl_sync(0xffffffffu, ai, lane & ~2), ci2 = __shfl_sync(0xffffffffu, ci, lane & ~2);
         const double ap = (lane & 2) ? ai2 : ar, cp = (lane & 2) ? ci2 : cr;
 #pragma unroll
-        for (int tp = RHO; tp < TF; ++tp) {
+        for (int tp = TA; tp < TF; ++tp) {
             const double2 b = fr[tp * 32];
             dmma884(wA.wr[tp][0], wA.wr[tp][1], ap, b.x);
             dmma884(wA.wi[tp][0], wA.wi[tp][1], ap, b.y);
@@ -281,23 +294,23 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
         }
         const double2 b = fr[TF * 32];
         dmma884(wA.wtr, wA.wti, ap, b.x);
-        dmma884(wB.wtr, wB.wti, cp, b.x);
+        if (HASB) dmma884(wB.wtr, wB.wti, cp, b.x);
     }
 }
 
 // Local pairing sums of one panel over its computed tiles: odd = <W(partner row), Y_old(own row)>, even = the same with
 // Y_new = S W(own row); strictly-upper tiles weigh 2, the diagonal tile 1 (see the header).  Not reduced over lanes.
-template <bool TAIL, bool FIRST, int TAU>
-__device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL, FIRST>& y,
+template <class S, bool FIRST, int TAU>
+__device__ __forceinline__ void hs_pairing(const HafRow<S::TF, S::TAIL>& w, const HsY<S, FIRST>& y,
                                            double& orr, double& oi, double& er, double& ei) {
-    constexpr int TF = HS_TF;
+    constexpr int TF = S::TF;
     orr = oi = er = ei = 0.0;
 #pragma unroll
     for (int tau = TAU; tau < TF; ++tau) {
         const double wgt = tau == TAU ? 1.0 : 2.0;        // strictly-upper tiles count twice (their transposes are never computed)
         const double x0r = wgt * shfl_xor_d(w.wr[tau][0], 16), x0i = wgt * shfl_xor_d(w.wi[tau][0], 16);
         const double x1r = wgt * shfl_xor_d(w.wr[tau][1], 16), x1i = wgt * shfl_xor_d(w.wi[tau][1], 16);
-        const unsigned s = hs_sign<TAIL>(y.jq, 4 * tau + y.t);
+        const unsigned s = hs_sign<S>(y.jq, 4 * tau + y.t);
         double yr, yi;
         y.get(2 * tau, yr, yi);
         WB_CFMA(orr, oi, x0r, x0i, yr, yi);
@@ -306,10 +319,10 @@ __device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const H
         WB_CFMA(er, ei, x0r, x0i, flipsign(w.wr[tau][1], s), flipsign(w.wi[tau][1], s));   // Y_new, chunk 2 tau
         WB_CFMA(er, ei, x1r, x1i, flipsign(w.wr[tau][0], s), flipsign(w.wi[tau][0], s));   // Y_new, chunk 2 tau + 1
     }
-    if (TAIL) {
+    if (S::TAIL) {
         const double wgt = TAU == TF ? 1.0 : 2.0;
         const double xr = wgt * shfl_xor_d(w.wtr, 16), xi = wgt * shfl_xor_d(w.wti, 16);
-        const unsigned smt = (y.t < 2) ? hs_sign<TAIL>(y.jq, 4 * TF) : 0u;
+        const unsigned smt = (y.t < 2) ? hs_sign<S>(y.jq, 4 * TF) : 0u;
         const double nr = flipsign(shfl_xor_d(w.wtr, 1), smt), ni = flipsign(shfl_xor_d(w.wti, 1), smt);
         double ytr, yti;
         y.get(2 * TF, ytr, yti);
@@ -318,33 +331,31 @@ __device__ __forceinline__ void hs_pairing(const HafRow<HS_TF, TAIL>& w, const H
     }
 }
 
-// the rows of Y_k = B_k S of a panel (first vertex pair ibase) as seen by this lane: from A' at k = 1 (B_1 = A', read
-// through the generic path), else from the team's shared-memory state
-template <bool TAIL, bool FIRST, int NQ>
-__device__ __forceinline__ HsY<TAIL, FIRST> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
-                                             uint64_t jq, int lane) {
-    using C = HsCfg<TAIL>;
-    using T = HsTeam<NQ>;
-    constexpr int m = C::M, n = C::N;
+// the rows of Y_k = B_k S of a panel (first vertex pair ibase) as seen by this lane: from A' at k = 1 (B_1 = A', global
+// memory), else from the team's shared-memory state
+template <class S, bool FIRST>
+__device__ __forceinline__ HsY<S, FIRST> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
+                                                 uint64_t jq, int lane) {
+    constexpr int m = S::M, n = S::N;
     const int half = lane >> 4;
-    const int v = ibase + (tailrows ? 0 : T::ps(lane)) + half * m;      // tail panel: the rows of the second pair slot repeat the first
-    HsY<TAIL, FIRST> y;
-    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + T::q(lane) * C::QS + v * C::LD;
-    y.col = state + T::q(lane) * C::QS + v;
+    const int v = ibase + (tailrows ? 0 : S::ps(lane)) + half * m;      // tail panel: the rows of the second pair slot repeat the first
+    HsY<S, FIRST> y;
+    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + S::q(lane) * S::QS + v * S::LD;
+    y.col = state + S::q(lane) * S::QS + v;
     y.jq = jq; y.t = lane & 3;
     return y;
 }
 
 // trace shares of one computed panel (first vertex pair ibase, tile TAU), added to the per-lane sums
-template <bool TAIL, bool FIRST, int NQ, int TAU>
-__device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const HsY<TAIL, FIRST>& y, int ibase, bool needO, bool needE, int lane,
+template <class S, bool FIRST, int TAU>
+__device__ __forceinline__ void hs_traces(const HafRow<S::TF, S::TAIL>& w, const HsY<S, FIRST>& y, int ibase, bool needO, bool needE, int lane,
                                           double (&tr)[6]) {
-    constexpr int TF = HS_TF, m = HsCfg<TAIL>::M;
-    constexpr bool in_tail = TAIL && TAU == TF;
+    constexpr int TF = S::TF, m = S::M;
+    constexpr bool in_tail = S::TAIL && TAU == TF;
     const int t = lane & 3, half = lane >> 4;
-    const int i = ibase + (in_tail ? 0 : HsTeam<NQ>::ps(lane));
+    const int i = ibase + (in_tail ? 0 : S::ps(lane));
     double rs = ((y.jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;            // delta of the row's vertex pair
-    if (in_tail && HsTeam<NQ>::ps(lane)) rs = 0.0;                      // repeated rows of the tail panel
+    if (in_tail && S::ps(lane)) rs = 0.0;                               // repeated rows of the tail panel
     {   // tr(M^(k+1)) share: element sigma(v) of this row, in the diagonal tile
         const int own_t = in_tail ? (1 - half) : (i & 3);
         if (t == own_t) {
@@ -356,91 +367,100 @@ __device__ __forceinline__ void hs_traces(const HafRow<HS_TF, TAIL>& w, const Hs
     }
     if (needO || needE) {
         double orr, oi, er, ei;
-        hs_pairing<TAIL, FIRST, TAU>(w, y, orr, oi, er, ei);
+        hs_pairing<S, FIRST, TAU>(w, y, orr, oi, er, ei);
         tr[2] += rs * orr; tr[3] += rs * oi;
         tr[4] += rs * er; tr[5] += rs * ei;
     }
 }
 
 // write the computed tiles of a panel (its rows, the columns of tiles >= its own and the tail columns)
-template <bool TAIL, int NQ, int TAU>
-__device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase, int lane, const HafRow<HS_TF, TAIL>& w) {
-    using C = HsCfg<TAIL>;
-    using T = HsTeam<NQ>;
-    constexpr int TF = HS_TF, m = C::M;
+template <class S, int TAU>
+__device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase, int lane, const HafRow<S::TF, S::TAIL>& w) {
+    constexpr int TF = S::TF, m = S::M;
     const int t = lane & 3, half = lane >> 4;
-    if (TAU == TF && T::ps(lane)) return;                               // repeated rows of the tail panel
-    double2* row = state + T::q(lane) * C::QS + (ibase + (TAU == TF ? 0 : T::ps(lane)) + half * m) * C::LD;
+    if (TAU == TF && S::ps(lane)) return;                               // repeated rows of the tail panel
+    double2* row = state + S::q(lane) * S::QS + (ibase + (TAU == TF ? 0 : S::ps(lane)) + half * m) * S::LD;
 #pragma unroll
     for (int tau = TAU; tau < TF; ++tau) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) row[4 * tau + t + r * m] = make_double2(w.wr[tau][r], w.wi[tau][r]);
     }
-    if (TAIL && t < 2) row[4 * TF + (t & 1) * m] = make_double2(w.wtr, w.wti);
+    if (S::TAIL && t < 2) row[4 * TF + (t & 1) * m] = make_double2(w.wtr, w.wti);
 }
 
-// one product step of a warp with role RHO: panels in tiles RHO and 5 - RHO (+ its K chunks of the tail panel)
-template <bool TAIL, bool FIRST, int NQ, int RHO>
+// one product step of a warp with role RHO: its two panels (+ its K chunks of the tail panel)
+template <class S, bool FIRST, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, bool needO, bool needE, bool store, uint64_t jq,
                                              int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
-    using T = HsTeam<NQ>;
-    constexpr int TF = HS_TF;
-    const int iA = 4 * RHO + T::PP * sub, iB = 4 * (TF - 1 - RHO) + T::PP * sub;
+    constexpr int TF = S::TF, TA = S::roleA(RHO), TB = S::roleB(RHO);
+    constexpr bool TAIL = S::TAIL, HASB = TB < TF;
+    const int iA = 4 * TA + S::PP * sub, iB = HASB ? 4 * TB + S::PP * sub : iA;
     HafRow<TF, TAIL> wA, wB;
-    HsY<TAIL, FIRST> yC;
+    HsY<S, FIRST> yC;
     if (TAIL) {
-        yC = hs_rows<TAIL, FIRST, NQ>(state, A, 4 * TF, true, jq, lane);
-        tailC[wl * 32 + lane] = hs_tail_chunk<TAIL, FIRST, 2 * TF / T::TW>(sfrag, lane, wl, yC);
+        yC = hs_rows<S, FIRST>(state, A, 4 * TF, true, jq, lane);
+        tailC[wl * 32 + lane] = hs_tail_chunk<S, FIRST, (2 * TF) / S::TW>(sfrag, lane, wl, yC);
     }
-    const HsY<TAIL, FIRST> yA = hs_rows<TAIL, FIRST, NQ>(state, A, iA, false, jq, lane), yB = hs_rows<TAIL, FIRST, NQ>(state, A, iB, false, jq, lane);
-    hs_step2<TAIL, FIRST, RHO>(sfrag, lane, yA, yB, wA, wB);
+    const HsY<S, FIRST> yA = hs_rows<S, FIRST>(state, A, iA, false, jq, lane), yB = hs_rows<S, FIRST>(state, A, iB, false, jq, lane);
+    hs_step2<S, FIRST, TA, TB>(sfrag, lane, yA, yB, wA, wB);
     __syncwarp();
     if (lane == 0) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
-    hs_traces<TAIL, FIRST, NQ, TF - 1 - RHO>(wB, yB, iB, needO, needE, lane, tr);
-    hs_traces<TAIL, FIRST, NQ, RHO>(wA, yA, iA, needO, needE, lane, tr);
-    hs_mbar_wait(barA, parity);           // every panel has read its rows of B_k; the partial tail tiles are in shared memory
+    if (HASB) hs_traces<S, FIRST, HASB ? TB : TA>(wB, yB, iB, needO, needE, lane, tr);
+    hs_traces<S, FIRST, TA>(wA, yA, iA, needO, needE, lane, tr);
+    hs_mbar_wait(barA, parity);            // every panel has read its rows of B_k; the partial tail tiles are in shared memory
     if (store) {
-        hs_store<TAIL, NQ, RHO>(state, iA, lane, wA);
-        hs_store<TAIL, NQ, TF - 1 - RHO>(state, iB, lane, wB);
+        hs_store<S, TA>(state, iA, lane, wA);
+        if (HASB) hs_store<S, HASB ? TB : TA>(state, iB, lane, wB);
     }
     if (TAIL && wl == 0) {
         HafRow<TF, TAIL> wC;
         wC.wtr = wC.wti = 0.0;
 #pragma unroll
-        for (int wv = 0; wv < T::TW; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
-        hs_traces<TAIL, FIRST, NQ, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
-        if (store) hs_store<TAIL, NQ, TF>(state, 4 * TF, lane, wC);
+        for (int wv = 0; wv < S::TW; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
+        hs_traces<S, FIRST, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+        if (store) hs_store<S, TF>(state, 4 * TF, lane, wC);
     }
 }
 
-template <bool TAIL, int NQ>
-__global__ void __launch_bounds__(32 * HS_WARPS, 1)
+template <class S, bool FIRST>
+__device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
+                                             int sub, bool needO, bool needE, bool store, uint64_t jq,
+                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
+#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr)
+    if (rho == 0) WB_HS_STEP(0);
+    else if (rho == 1) WB_HS_STEP(1);
+    else if (rho == 2 || S::ROLES == 3) WB_HS_STEP(2);
+    else WB_HS_STEP(3);
+#undef WB_HS_STEP
+}
+
+template <class S>
+__global__ void __launch_bounds__(32 * S::WARPS, 1)
 haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, long long skew_cycles) {
-    using C = HsCfg<TAIL>;
-    using T = HsTeam<NQ>;
-    constexpr int TF = HS_TF, m = C::M, n = C::N, TW = T::TW;
+    constexpr int TF = S::TF, m = S::M, n = S::N, TW = S::TW, NQ = S::NQ;
+    constexpr bool TAIL = S::TAIL;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int team = T::team(warp), wl = T::wl(warp);
+    const int team = S::team(warp), wl = S::wl(warp);
     double2* sfrag = reinterpret_cast<double2*>(smem);
-    double2* state = reinterpret_cast<double2*>(smem + C::FRAG_D) + team * NQ * C::QS;                    // [subset][row][col]
-    double2* P2 = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2) + team * NQ * (m + 2);   // P[subset][j]
-    double2* ptmp = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2 + C::P_D) + team * 3 * TW * 8;   // [kind][warp][row]
-    double2* tailC = reinterpret_cast<double2*>(smem + C::FRAG_D + 2 * (size_t)C::STATE_D2 + C::P_D + C::TMP_D) + team * TW * 32;   // [warp][lane]
+    double2* state = reinterpret_cast<double2*>(smem + S::FRAG_D) + team * NQ * S::QS;                    // [subset][row][col]
+    double2* P2 = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2) + team * NQ * (m + 2);   // P[subset][j]
+    double2* ptmp = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2 + S::P_D) + team * 3 * TW * 8;   // [kind][warp][row]
+    double2* tailC = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2 + S::P_D + S::TMP_D) + team * TW * 32;   // [warp][lane]
     __shared__ uint64_t bars[2];
     uint64_t* barA = bars + team;
-    if (threadIdx.x < T::TEAMS) hs_mbar_init(bars + threadIdx.x, TW);
-    haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * HS_WARPS);
+    if (threadIdx.x < S::TEAMS) hs_mbar_init(bars + threadIdx.x, TW);
+    haf_build_frag(A, n, m, TF, TAIL ? 1 : 0, sfrag, threadIdx.x, 32 * S::WARPS);
     __syncthreads();
-    // optional start skew of the second team (see HsTeam): n = 50 gains 1 % from ~ a product's length, n = 48 loses 5 %
-    if (NQ == 2 && team == 1) {
+    // optional start skew of the second team (see HsShape): n = 50 gains 1 % from ~ a product's length, n = 48 loses 5 %
+    if (S::TEAMS == 2 && team == 1) {
         const long long t0 = clock64();
         while (clock64() - t0 < skew_cycles) __nanosleep(200);
     }
 
-    const int g = lane >> 2, t = lane & 3, q = T::q(lane);
-    const int rho = wl / T::SUBS, sub = wl % T::SUBS;
+    const int g = lane >> 2, t = lane & 3, q = S::q(lane);
+    const int rho = wl / S::SUBS, sub = wl % S::SUBS;
     const int nprod = (m - 1) >> 1, K = nprod + 1;
     const uint64_t ngroups = (j1 - j0 + NQ - 1) / NQ;
 
@@ -450,7 +470,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     acc.re = {0.0, 0.0};
     acc.im = {0.0, 0.0};
 
-    for (uint64_t G = (uint64_t)blockIdx.x * T::TEAMS + team; G < ngroups; G += (uint64_t)gridDim.x * T::TEAMS) {
+    for (uint64_t G = (uint64_t)blockIdx.x * S::TEAMS + team; G < ngroups; G += (uint64_t)gridDim.x * S::TEAMS) {
         const uint64_t jq = j0 + NQ * G + q;
         if (wl == 0) {
             // tr(M^1) = sum_r delta_r A'[r][sigma(r)] = 2 sum_i delta_i A'[i][i + m]; every P[1..m] is rewritten for every group
@@ -472,13 +492,8 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
             const unsigned parity = uses++ & 1u;            // phase of the split barrier: one use per product
-#define WB_HS_STEP(first, r) hs_warp_step<TAIL, first, NQ, r>(sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr)
-            if (k == 1) {                      // B_1 = A' is read from global memory
-                if (rho == 0) WB_HS_STEP(true, 0); else if (rho == 1) WB_HS_STEP(true, 1); else WB_HS_STEP(true, 2);
-            } else {
-                if (rho == 0) WB_HS_STEP(false, 0); else if (rho == 1) WB_HS_STEP(false, 1); else WB_HS_STEP(false, 2);
-            }
-#undef WB_HS_STEP
+            if (k == 1) hs_role_step<S, true>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);   // B_1 = A' from global memory
+            else hs_role_step<S, false>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
@@ -489,9 +504,9 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
 #pragma unroll
                 for (int kind = 0; kind < 3; ++kind) ptmp[(kind * TW + wl) * 8 + g] = make_double2(tr[2 * kind], tr[2 * kind + 1]);
             }
-            T::sync(team);                     // B_(k+1) is complete in shared memory; so are this step's trace shares
-            {   // warp w of the team sums the 24 shares (TW warps x the 8 / NQ rows of a subset) of ONE (kind, subset) in a fixed
-                // shuffle tree
+            S::sync(team);                     // B_(k+1) is complete in shared memory; so are this step's trace shares
+            if (wl < 3 * NQ) {   // warp w of the team sums the shares (TW warps x the 8 / NQ rows of a subset) of ONE (kind, subset) in a
+                                 // fixed shuffle tree
                 constexpr int RPS = 8 / NQ;    // rows per subset in a panel
                 const int kind = wl / NQ, qq = wl % NQ;
                 double2 e = make_double2(0.0, 0.0);
@@ -503,7 +518,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
                 if (lane == 0 && want && j <= m) P2[qq * (m + 2) + j] = e;
             }
         }
-        T::sync(team);                         // the last step's traces are in P
+        S::sync(team);                         // the last step's traces are in P
         // ---- series c_s = (1/s) sum_i (p_i / 2) c_(s-i), first warp of the team, "push" form: lane l holds the partial sum of
         // target index l for each of the NQ subsets (independent chains); step s: lane s finishes c_s, one broadcast, and every
         // lane l > s adds F_(l-s) c_s.  (The first version split each inner sum over 8 lanes with two FP64 divisions and three
@@ -540,34 +555,36 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             __syncwarp();
         }
     }
-    __shared__ double red[HS_WARPS * 4];
+    __shared__ double red[S::WARPS * 4];
     block_reduce_store(acc, red, partials);
 }
 
-template <bool TAIL, int NQ>
+template <class S>
 static int launch_haf_sym(const double* dA, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
-    using C = HsCfg<TAIL>;
-    auto kern = haf_sym_kernel<TAIL, NQ>;
+    auto kern = haf_sym_kernel<S>;
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
     const int grid = (int)(ngroups < (uint64_t)sms ? (ngroups ? ngroups : 1) : (uint64_t)sms);
-    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::BYTES));
+    WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
     const char* ek = getenv("WB200_HS_SKEW");
-    const long long skew = ek ? atoll(ek) : (TAIL ? 20000 : 0);
-    kern<<<grid, 32 * HS_WARPS, C::BYTES, st>>>(dA, j0, j1, partials, skew);
+    const long long skew = ek ? atoll(ek) : (S::TAIL ? 20000 : 0);
+    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, skew);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
 }
 
-// Used by wb200_hafnian_dev for n = 48 / 50 without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the one-team
-// shape of the symmetric-half kernel).  Returns WB200_ENOSUP when the shape is not one of the two this kernel is built for.
+// Used by wb200_hafnian_dev for n = 48 / 50 / 56 without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
+// one-team shape for n = 48 / 50).  Returns WB200_ENOSUP when the shape is not one this kernel is built for.
+bool haf_sym_supports(int n) { return n == 48 || n == 50 || n == 56; }
+
 int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
     const char* es = getenv("WB200_HAF_SYM");
     const bool one_team = es && atoi(es) == 4;
-    if (n == 48) return one_team ? launch_haf_sym<false, 4>(dA, j0, j1, partials, sms, grid_out, st)
-                                 : launch_haf_sym<false, 2>(dA, j0, j1, partials, sms, grid_out, st);
-    if (n == 50) return one_team ? launch_haf_sym<true, 4>(dA, j0, j1, partials, sms, grid_out, st)
-                                 : launch_haf_sym<true, 2>(dA, j0, j1, partials, sms, grid_out, st);
+    if (n == 48) return one_team ? launch_haf_sym<HsShape<6, false, 4>>(dA, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<HsShape<6, false, 2>>(dA, j0, j1, partials, sms, grid_out, st);
+    if (n == 50) return one_team ? launch_haf_sym<HsShape<6, true, 4>>(dA, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<HsShape<6, true, 2>>(dA, j0, j1, partials, sms, grid_out, st);
+    if (n == 56) return launch_haf_sym<HsShape<7, false, 2>>(dA, j0, j1, partials, sms, grid_out, st);
     return WB200_ENOSUP;
 }
 
