@@ -138,7 +138,7 @@ def haf_sym_entries(n):
     row panel of a vertex pair in tile T (tiles = 4 vertex pairs = 8 rows/columns) computes the columns of tiles >= T
     and of the tail pair; the tail pair's panel only its own 2 x 2 block."""
     m = n // 2
-    if n % 2 or m not in (24, 25, 28):
+    if n not in (40, 42, 48, 50, 56, 58):
         return 0
     TF, tail = m // 4, m % 4
     return sum(8 * (8 * (TF - T) + 2 * tail) for T in range(TF)) + 4 * tail

@@ -56,7 +56,7 @@ namespace wb {
 //
 // Roles.  A warp owns the panels of two tiles whose computed-tile counts add up to the same number for every warp:
 // TF even: tiles r and TF - 1 - r (TF + 1 tile units); TF odd: tile 0 alone, then tiles r and TF - r (TF tile units).
-template <int TF_, bool TAIL_, int NQ_>
+template <int TF_, bool TAIL_, int NQ_, int TEAMS_>
 struct HsShape {
     static constexpr int TF = TF_, NQ = NQ_;
     static constexpr bool TAIL = TAIL_;
@@ -68,7 +68,7 @@ struct HsShape {
     static constexpr int SUBS = NQ;                                // panels per tile
     static constexpr int ROLES = (TF + 1) / 2;
     static constexpr int TW = ROLES * SUBS;                        // warps per team
-    static constexpr int TEAMS = (TF <= 6) ? 4 / NQ : 1;           // groups in flight per CTA (shared memory decides)
+    static constexpr int TEAMS = TEAMS_;                           // groups in flight per CTA (shared memory decides)
     static constexpr int WARPS = TEAMS * TW;
     static constexpr int FRAG_D = NK * NT * 64;                    // doubles
     static constexpr int LD = N + 1;                               // row stride of the state (entries): 4 LD = 4 or 12 (mod 32) words
@@ -169,22 +169,24 @@ __device__ __forceinline__ void hs_mbar_wait(uint64_t* bar, unsigned parity) {
 
 // The tail panel (the one vertex pair beyond the full tiles, n = 50): only its 2 x 2 tail block has to be computed, every
 // other entry of its rows arrives by symmetry.  That is 25 DMMAs in one dependent chain - on one warp it made that warp
-// late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies K chunks w CH .. w CH + CH - 1
+// late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies the K chunks w, w + TW, ...
 // (the first warp also the packed tail chunk), the partial tiles meet in shared memory and the first warp sums them in
 // warp order while the others store.
-template <class S, bool FIRST, int CH>
+template <class S, bool FIRST>
 __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<S, FIRST>& y) {
-    constexpr int TF = S::TF, NT = S::NT, m = S::M, LD = S::LD;
+    constexpr int TF = S::TF, NT = S::NT, m = S::M, LD = S::LD, CH = (2 * TF + S::TW - 1) / S::TW;
     double pr = 0.0, pi = 0.0, p2r = 0.0, p2i = 0.0;
 #pragma unroll
     for (int cc = 0; cc < CH; ++cc) {
-        const int kap = wl * CH + cc, tau = kap >> 1, h = kap & 1;
-        const int c = 4 * tau + y.t + (1 - h) * m;                      // Y[v][chunk position] = delta B[v][c]
-        const double2 a = y.first ? y.row[c] : y.col[c * LD];
-        const unsigned s = hs_sign<S>(y.jq, 4 * tau + y.t);
-        const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
-        dmma884(pr, pi, flipsign(a.x, s), b.x);
-        dmma884(p2r, p2i, flipsign(a.y, s), b.y);
+        const int kap = wl + cc * S::TW, tau = kap >> 1, h = kap & 1;
+        if (kap < 2 * TF) {
+            const int c = 4 * tau + y.t + (1 - h) * m;                  // Y[v][chunk position] = delta B[v][c]
+            const double2 a = y.first ? y.row[c] : y.col[c * LD];
+            const unsigned s = hs_sign<S>(y.jq, 4 * tau + y.t);
+            const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
+            dmma884(pr, pi, flipsign(a.x, s), b.x);
+            dmma884(p2r, p2i, flipsign(a.y, s), b.y);
+        }
     }
     if (wl == 0) {
         const double2 at = y.row[4 * TF + (1 - (y.t & 1)) * m];
@@ -400,7 +402,7 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     HsY<S, FIRST> yC;
     if (TAIL) {
         yC = hs_rows<S, FIRST>(state, A, 4 * TF, true, jq, lane);
-        tailC[wl * 32 + lane] = hs_tail_chunk<S, FIRST, (2 * TF) / S::TW>(sfrag, lane, wl, yC);
+        tailC[wl * 32 + lane] = hs_tail_chunk<S, FIRST>(sfrag, lane, wl, yC);
     }
     const HsY<S, FIRST> yA = hs_rows<S, FIRST>(state, A, iA, false, jq, lane), yB = hs_rows<S, FIRST>(state, A, iB, false, jq, lane);
     hs_step2<S, FIRST, TA, TB>(sfrag, lane, yA, yB, wA, wB);
@@ -573,19 +575,26 @@ static int launch_haf_sym(const double* dA, uint64_t j0, uint64_t j1, double* pa
     return WB200_OK;
 }
 
-// Used by wb200_hafnian_dev for n = 48 / 50 / 56 without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
-// one-team shape for n = 48 / 50).  Returns WB200_ENOSUP when the shape is not one this kernel is built for.
-bool haf_sym_supports(int n) { return n == 48 || n == 50 || n == 56; }
+// Used by wb200_hafnian_dev for the sizes below without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
+// one-team shape for n = 48 / 50).  Sizes: m = n / 2 = 0 or 1 (mod 4) - whole tiles of four vertex pairs plus at most
+// one tail pair - that fit: two teams of two subsets up to n = 50, one team of two subsets for n = 56 / 58.
+// Returns WB200_ENOSUP when the shape is not one this kernel is built for.
+bool haf_sym_supports(int n) { return n == 40 || n == 42 || n == 48 || n == 50 || n == 56 || n == 58; }
 
 int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
     const char* es = getenv("WB200_HAF_SYM");
     const bool one_team = es && atoi(es) == 4;
-    if (n == 48) return one_team ? launch_haf_sym<HsShape<6, false, 4>>(dA, j0, j1, partials, sms, grid_out, st)
-                                 : launch_haf_sym<HsShape<6, false, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-    if (n == 50) return one_team ? launch_haf_sym<HsShape<6, true, 4>>(dA, j0, j1, partials, sms, grid_out, st)
-                                 : launch_haf_sym<HsShape<6, true, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-    if (n == 56) return launch_haf_sym<HsShape<7, false, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-    return WB200_ENOSUP;
+    switch (n) {
+        case 40: return launch_haf_sym<HsShape<5, false, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
+        case 42: return launch_haf_sym<HsShape<5, true, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
+        case 48: return one_team ? launch_haf_sym<HsShape<6, false, 4, 1>>(dA, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<HsShape<6, false, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
+        case 50: return one_team ? launch_haf_sym<HsShape<6, true, 4, 1>>(dA, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<HsShape<6, true, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
+        case 56: return launch_haf_sym<HsShape<7, false, 2, 1>>(dA, j0, j1, partials, sms, grid_out, st);
+        case 58: return launch_haf_sym<HsShape<7, true, 2, 1>>(dA, j0, j1, partials, sms, grid_out, st);
+        default: return WB200_ENOSUP;
+    }
 }
 
 }  // namespace wb
