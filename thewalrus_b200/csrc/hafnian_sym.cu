@@ -394,7 +394,7 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase,
 template <class S, bool FIRST, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, bool needO, bool needE, bool store, uint64_t jq,
-                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
+                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, bool plainbar, double (&tr)[6]) {
     constexpr int TF = S::TF, TA = S::roleA(RHO), TB = S::roleB(RHO);
     constexpr bool TAIL = S::TAIL, HASB = TB < TF;
     const int iA = 4 * TA + S::PP * sub, iB = HASB ? 4 * TB + S::PP * sub : iA;
@@ -407,10 +407,13 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     const HsY<S, FIRST> yA = hs_rows<S, FIRST>(state, A, iA, false, jq, lane), yB = hs_rows<S, FIRST>(state, A, iB, false, jq, lane);
     hs_step2<S, FIRST, TA, TB>(sfrag, lane, yA, yB, wA, wB);
     __syncwarp();
-    if (lane == 0) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
+    if (lane == 0 && !plainbar) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
     if (HASB) hs_traces<S, FIRST, HASB ? TB : TA>(wB, yB, iB, needO, needE, lane, tr);
     hs_traces<S, FIRST, TA>(wA, yA, iA, needO, needE, lane, tr);
-    hs_mbar_wait(barA, parity);            // every panel has read its rows of B_k; the partial tail tiles are in shared memory
+    // every panel has read its rows of B_k; the partial tail tiles are in shared memory.  (plainbar: an ordinary team barrier
+    // at the same place - what compute-sanitizer's racecheck can follow; it does not model mbarrier ordering.)
+    if (plainbar) S::sync(team);
+    else hs_mbar_wait(barA, parity);
     if (store) {
         hs_store<S, TA>(state, iA, lane, wA);
         if (HASB) hs_store<S, HASB ? TB : TA>(state, iB, lane, wB);
@@ -421,6 +424,7 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
 #pragma unroll
         for (int wv = 0; wv < S::TW; ++wv) { const double2 e = tailC[wv * 32 + lane]; wC.wtr += e.x; wC.wti += e.y; }
         hs_traces<S, FIRST, TF>(wC, yC, 4 * TF, needO, needE, lane, tr);
+        __syncwarp();                      // the pairing read the tail block across lanes (t = 0 <-> 1) before it is overwritten
         if (store) hs_store<S, TF>(state, 4 * TF, lane, wC);
     }
 }
@@ -428,8 +432,8 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
 template <class S, bool FIRST>
 __device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, bool needO, bool needE, bool store, uint64_t jq,
-                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
-#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr)
+                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, bool plainbar, double (&tr)[6]) {
+#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, plainbar, tr)
     if (rho == 0) WB_HS_STEP(0);
     else if (rho == 1) WB_HS_STEP(1);
     else if (rho == 2 || S::ROLES == 3) WB_HS_STEP(2);
@@ -439,7 +443,7 @@ __device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict_
 
 template <class S>
 __global__ void __launch_bounds__(32 * S::WARPS, 1)
-haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, long long skew_cycles) {
+haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, long long skew_cycles, int plainbar_i) {
     constexpr int TF = S::TF, m = S::M, n = S::N, TW = S::TW, NQ = S::NQ;
     constexpr bool TAIL = S::TAIL;
     extern __shared__ __align__(16) double smem[];
@@ -461,6 +465,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
         while (clock64() - t0 < skew_cycles) __nanosleep(200);
     }
 
+    const bool plainbar = plainbar_i != 0;
     const int g = lane >> 2, t = lane & 3, q = S::q(lane);
     const int rho = wl / S::SUBS, sub = wl % S::SUBS;
     const int nprod = (m - 1) >> 1, K = nprod + 1;
@@ -494,8 +499,8 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
             const unsigned parity = uses++ & 1u;            // phase of the split barrier: one use per product
-            if (k == 1) hs_role_step<S, true>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);   // B_1 = A' from global memory
-            else hs_role_step<S, false>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, tr);
+            if (k == 1) hs_role_step<S, true>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, plainbar, tr);   // B_1 = A' from global memory
+            else hs_role_step<S, false>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, plainbar, tr);
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
@@ -569,7 +574,8 @@ static int launch_haf_sym(const double* dA, uint64_t j0, uint64_t j1, double* pa
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
     const char* ek = getenv("WB200_HS_SKEW");
     const long long skew = ek ? atoll(ek) : (S::TAIL ? 20000 : 0);
-    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, skew);
+    const char* ep = getenv("WB200_HS_PLAINBAR");
+    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, skew, ep ? atoi(ep) : 0);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
