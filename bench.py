@@ -137,14 +137,17 @@ def tor_tree_flops(N, DC=9, aug=0):
 
 
 def haf_sym_entries(n):
-    """Entries of one n x n product the symmetric-half kernel computes (hafnian_sym.cu; 0 = shape not covered): the
+    """Useful entries of one n x n product the symmetric-half kernel computes (hafnian_sym.cu; 0 = size not covered): the
     row panel of a vertex pair in tile T (tiles = 4 vertex pairs = 8 rows/columns) computes the columns of tiles >= T
-    and of the tail pair; the tail pair's panel only its own 2 x 2 block."""
+    and of the tail pair; the tail pair's panel only its own 2 x 2 block.  Sizes with n/2 = 2, 3 (mod 4) run zero-padded in
+    the next whole-tile shape: only the entries of real vertices are counted."""
     m = n // 2
-    if n not in (40, 42, 48, 50, 56, 58):
+    if n % 2 or not 36 <= n <= 58:
         return 0
-    TF, tail = m // 4, m % 4
-    return sum(8 * (8 * (TF - T) + 2 * tail) for T in range(TF)) + 4 * tail
+    if m % 4 == 1:                                   # whole tiles + one tail pair
+        TF = m // 4
+        return sum(8 * (8 * (TF - T) + 2) for T in range(TF)) + 4
+    return 4 * sum(1 for i in range(m) for p in range(m) if p // 4 >= i // 4)
 
 
 def units_and_flops(kind, n):

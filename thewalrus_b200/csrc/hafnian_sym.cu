@@ -91,10 +91,17 @@ struct HsShape {
     }
 };
 
-// sign mask of vertex pair p in subset jq: delta = +1 (bit set) -> 0, delta = -1 -> sign bit
+// sign mask of vertex pair p: neg has bit p set where delta_p = -1 (pairs beyond the true size: delta = +1)
 template <class S>
-__device__ __forceinline__ unsigned hs_sign(uint64_t jq, int p) {
-    return ((unsigned)(jq >> (S::M - 1 - p)) & 1u) ? 0u : 0x80000000u;
+__device__ __forceinline__ unsigned hs_sign(unsigned neg, int p) {
+    return ((neg >> p) & 1u) << 31;
+}
+// Sizes between the shapes: a matrix of mt < S::M vertex pairs runs in the next shape with whole tiles as if padded with
+// zero rows and columns (they change no trace); only the first product, which reads A' itself, the signs and the series
+// know the true size.
+__device__ __forceinline__ unsigned hs_negmask(uint64_t jq, int mt) {
+    const unsigned kept = __brev((unsigned)jq) >> (32 - mt);         // bit p = bit mt - 1 - p of jq (thewalrus/_hafnian.py:162-180)
+    return ~kept & ((1u << mt) - 1u);
 }
 
 // One row of Y_k = B_k S, read just in time: chunk kap, position t of the lane.  Y_k[v][c] = delta_c B_k[v][sigma(c)], with
@@ -104,22 +111,26 @@ template <class S, bool FIRST>
 struct HsY {
     const double2* row;      // row of this lane's (subset, vertex): state (stride LD) or A' (stride n, k = 1)
     const double2* col;      // the same vertex as a COLUMN of the state: entry [c][v] = col[c * LD]
-    uint64_t jq;
+    unsigned neg;            // bit p: delta of vertex pair p is -1
     int t;
+    int mt;                  // FIRST only: true number of vertex pairs (partner offset and row length in A')
+    bool rowok;              // FIRST only: this lane's row is a real vertex (not padding)
     static constexpr bool first = FIRST;   // k = 1: B_1 = A' (global memory), every entry is there, read row-wise;
                                            // a compile-time property, so that the loads of k > 1 are plain LDS
     __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {   // computed tiles only (row-wise)
-        constexpr int TF = S::TF, m = S::M;
+        constexpr int TF = S::TF;
+        const int m = FIRST ? mt : S::M;
         if (kap < 2 * TF) {
             const int tau = kap >> 1;
-            const double2 a = row[4 * tau + t + (1 - (kap & 1)) * m];
-            const unsigned s = hs_sign<S>(jq, 4 * tau + t);
+            const bool ok = !FIRST || (rowok && 4 * tau + t < mt);
+            const double2 a = ok ? row[4 * tau + t + (1 - (kap & 1)) * m] : make_double2(0.0, 0.0);
+            const unsigned s = hs_sign<S>(neg, 4 * tau + t);
             yr = flipsign(a.x, s); yi = flipsign(a.y, s);
         } else {
             yr = yi = 0.0;
             if (S::TAIL && t < 2) {
                 const double2 a = row[4 * TF + (1 - (t & 1)) * m];
-                const unsigned s = hs_sign<S>(jq, 4 * TF);
+                const unsigned s = hs_sign<S>(neg, 4 * TF);
                 yr = flipsign(a.x, s); yi = flipsign(a.y, s);
             }
         }
@@ -136,8 +147,16 @@ struct HsCur {
     int d, inc;
     __device__ __forceinline__ void init(const HsY<S, FIRST>& y) {
         constexpr int m = S::M, LD = S::LD;
-        if (y.first || T == 0) { p = y.row + y.t; d = m; inc = 4; }
+        if (FIRST) { p = y.row + y.t; d = y.mt; inc = 4; }
+        else if (T == 0) { p = y.row + y.t; d = m; inc = 4; }
         else { p = y.col + y.t * LD; d = m * LD; inc = 4 * LD; }
+    }
+    // entries of K tile tau: a0 = column 4 tau + t + m (the partner half), a1 = column 4 tau + t
+    __device__ __forceinline__ double2 a0(const HsY<S, FIRST>& y, int tau) const {
+        return (!FIRST || (y.rowok && 4 * tau + y.t < y.mt)) ? p[d] : make_double2(0.0, 0.0);
+    }
+    __device__ __forceinline__ double2 a1(const HsY<S, FIRST>& y, int tau) const {
+        return (!FIRST || (y.rowok && 4 * tau + y.t < y.mt)) ? p[0] : make_double2(0.0, 0.0);
     }
     __device__ __forceinline__ void next(const HsY<S, FIRST>& y, int tau_next) {
         constexpr int m = S::M;
@@ -182,7 +201,7 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
         if (kap < 2 * TF) {
             const int c = 4 * tau + y.t + (1 - h) * m;                  // Y[v][chunk position] = delta B[v][c]
             const double2 a = y.first ? y.row[c] : y.col[c * LD];
-            const unsigned s = hs_sign<S>(y.jq, 4 * tau + y.t);
+            const unsigned s = hs_sign<S>(y.neg, 4 * tau + y.t);
             const double2 b = sfrag[(kap * NT + TF) * 32 + lane];
             dmma884(pr, pi, flipsign(a.x, s), b.x);
             dmma884(p2r, p2i, flipsign(a.y, s), b.y);
@@ -190,7 +209,7 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
     }
     if (wl == 0) {
         const double2 at = y.row[4 * TF + (1 - (y.t & 1)) * m];
-        const unsigned st = (y.t < 2) ? hs_sign<S>(y.jq, 4 * TF) : 0u;
+        const unsigned st = (y.t < 2) ? hs_sign<S>(y.neg, 4 * TF) : 0u;
         const double ar = (y.t < 2) ? flipsign(at.x, st) : 0.0, ai = (y.t < 2) ? flipsign(at.y, st) : 0.0;
         const double yi2 = __shfl_sync(0xffffffffu, ai, lane & ~2);
         const double ap = (lane & 2) ? yi2 : ar;
@@ -208,7 +227,7 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
 template <class S, bool FIRST, int TA, int TB>
 __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<S, FIRST>& yA, const HsY<S, FIRST>& yB,
                                          HafRow<S::TF, S::TAIL>& wA, HafRow<S::TF, S::TAIL>& wB) {
-    constexpr int TF = S::TF, NT = S::NT, m = S::M;
+    constexpr int TF = S::TF, NT = S::NT;
     constexpr bool TAIL = S::TAIL, HASB = TB < TF;
 #pragma unroll
     for (int tp = TA; tp < TF; ++tp) {
@@ -226,20 +245,20 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
     HsCur<S, FIRST, TA> curA;
     HsCur<S, FIRST, HASB ? TB : TA> curB;
     curA.init(yA); curB.init(yB);
-    int sh = m - 1 - yA.t;
-    double2 a0 = curA.p[curA.d], a1 = curA.p[0], c0 = make_double2(0.0, 0.0), c1 = c0;     // fetched one iteration ahead
-    if (HASB) { c0 = curB.p[curB.d]; c1 = curB.p[0]; }
+    unsigned nb = yA.neg >> yA.t;                // bit 0: delta of the lane's column pair in the current K tile
+    double2 a0 = curA.a0(yA, 0), a1 = curA.a1(yA, 0), c0 = make_double2(0.0, 0.0), c1 = c0;     // fetched one iteration ahead
+    if (HASB) { c0 = curB.a0(yB, 0); c1 = curB.a1(yB, 0); }
 #pragma unroll 1
     for (int tau = 0; tau < TF; ++tau) {
-        const unsigned s = ((unsigned)(yA.jq >> sh) & 1u) ? 0u : 0x80000000u;
+        const unsigned s = (nb & 1u) << 31;
         // next K tile; after the last one: the tail element of lanes t = 0, 1 (an address every lane may read)
         const bool last = tau == TF - 1;
         curA.next(yA, tau + 1);
         if (HASB) curB.next(yB, tau + 1);
         double2 n0 = make_double2(0.0, 0.0), n1 = n0, d0 = n0, d1 = n0;
         if (!last) {
-            n0 = curA.p[curA.d]; n1 = curA.p[0];
-            if (HASB) { d0 = curB.p[curB.d]; d1 = curB.p[0]; }
+            n0 = curA.a0(yA, tau + 1); n1 = curA.a1(yA, tau + 1);
+            if (HASB) { d0 = curB.a0(yB, tau + 1); d1 = curB.a1(yB, tau + 1); }
         } else if (TAIL) {
             n0 = curA.tail(yA);
             if (HASB) d0 = curB.tail(yB);
@@ -275,11 +294,11 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
             fr += NT * 32;
         }
         a0 = n0; a1 = n1; c0 = d0; c1 = d1;
-        sh -= 4;
+        nb >>= 4;
     }
     if (TAIL) {                                  // K-packed tail chunk (one vertex pair in the tail): 2 DMMAs per tile
         const bool own = yA.t < 2;
-        const unsigned s = own ? hs_sign<S>(yA.jq, 4 * TF) : 0u;
+        const unsigned s = own ? hs_sign<S>(yA.neg, 4 * TF) : 0u;
         const double ar = own ? flipsign(a0.x, s) : 0.0, ai = own ? flipsign(a0.y, s) : 0.0;
         const double cr = own ? flipsign(c0.x, s) : 0.0, ci = own ? flipsign(c0.y, s) : 0.0;
         const double ai2 = __shfl_sync(0xffffffffu, ai, lane & ~2), ci2 = __shfl_sync(0xffffffffu, ci, lane & ~2);
@@ -312,7 +331,7 @@ __device__ __forceinline__ void hs_pairing(const HafRow<S::TF, S::TAIL>& w, cons
         const double wgt = tau == TAU ? 1.0 : 2.0;        // strictly-upper tiles count twice (their transposes are never computed)
         const double x0r = wgt * shfl_xor_d(w.wr[tau][0], 16), x0i = wgt * shfl_xor_d(w.wi[tau][0], 16);
         const double x1r = wgt * shfl_xor_d(w.wr[tau][1], 16), x1i = wgt * shfl_xor_d(w.wi[tau][1], 16);
-        const unsigned s = hs_sign<S>(y.jq, 4 * tau + y.t);
+        const unsigned s = hs_sign<S>(y.neg, 4 * tau + y.t);
         double yr, yi;
         y.get(2 * tau, yr, yi);
         WB_CFMA(orr, oi, x0r, x0i, yr, yi);
@@ -324,7 +343,7 @@ __device__ __forceinline__ void hs_pairing(const HafRow<S::TF, S::TAIL>& w, cons
     if (S::TAIL) {
         const double wgt = TAU == TF ? 1.0 : 2.0;
         const double xr = wgt * shfl_xor_d(w.wtr, 16), xi = wgt * shfl_xor_d(w.wti, 16);
-        const unsigned smt = (y.t < 2) ? hs_sign<S>(y.jq, 4 * TF) : 0u;
+        const unsigned smt = (y.t < 2) ? hs_sign<S>(y.neg, 4 * TF) : 0u;
         const double nr = flipsign(shfl_xor_d(w.wtr, 1), smt), ni = flipsign(shfl_xor_d(w.wti, 1), smt);
         double ytr, yti;
         y.get(2 * TF, ytr, yti);
@@ -337,14 +356,17 @@ __device__ __forceinline__ void hs_pairing(const HafRow<S::TF, S::TAIL>& w, cons
 // memory), else from the team's shared-memory state
 template <class S, bool FIRST>
 __device__ __forceinline__ HsY<S, FIRST> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
-                                                 uint64_t jq, int lane) {
-    constexpr int m = S::M, n = S::N;
+                                                 unsigned neg, int mt, int lane) {
+    constexpr int m = S::M;
     const int half = lane >> 4;
-    const int v = ibase + (tailrows ? 0 : S::ps(lane)) + half * m;      // tail panel: the rows of the second pair slot repeat the first
+    const int i = ibase + (tailrows ? 0 : S::ps(lane));                 // tail panel: the rows of the second pair slot repeat the first
+    const int v = i + half * m;
     HsY<S, FIRST> y;
-    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (size_t)v * n : state + S::q(lane) * S::QS + v * S::LD;
+    y.mt = mt; y.rowok = i < mt;
+    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (y.rowok ? (size_t)(i + half * mt) * (2 * mt) : 0)
+                  : state + S::q(lane) * S::QS + v * S::LD;
     y.col = state + S::q(lane) * S::QS + v;
-    y.jq = jq; y.t = lane & 3;
+    y.neg = neg; y.t = lane & 3;
     return y;
 }
 
@@ -352,11 +374,11 @@ __device__ __forceinline__ HsY<S, FIRST> hs_rows(const double2* __restrict__ sta
 template <class S, bool FIRST, int TAU>
 __device__ __forceinline__ void hs_traces(const HafRow<S::TF, S::TAIL>& w, const HsY<S, FIRST>& y, int ibase, bool needO, bool needE, int lane,
                                           double (&tr)[6]) {
-    constexpr int TF = S::TF, m = S::M;
+    constexpr int TF = S::TF;
     constexpr bool in_tail = S::TAIL && TAU == TF;
     const int t = lane & 3, half = lane >> 4;
     const int i = ibase + (in_tail ? 0 : S::ps(lane));
-    double rs = ((y.jq >> (m - 1 - i)) & 1ull) ? 1.0 : -1.0;            // delta of the row's vertex pair
+    double rs = ((y.neg >> i) & 1u) ? -1.0 : 1.0;                       // delta of the row's vertex pair
     if (in_tail && S::ps(lane)) rs = 0.0;                               // repeated rows of the tail panel
     {   // tr(M^(k+1)) share: element sigma(v) of this row, in the diagonal tile
         const int own_t = in_tail ? (1 - half) : (i & 3);
@@ -393,7 +415,7 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase,
 // one product step of a warp with role RHO: its two panels (+ its K chunks of the tail panel)
 template <class S, bool FIRST, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
-                                             int sub, bool needO, bool needE, bool store, uint64_t jq,
+                                             int sub, bool needO, bool needE, bool store, unsigned neg, int mt,
                                              int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, bool plainbar, double (&tr)[6]) {
     constexpr int TF = S::TF, TA = S::roleA(RHO), TB = S::roleB(RHO);
     constexpr bool TAIL = S::TAIL, HASB = TB < TF;
@@ -401,10 +423,10 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     HafRow<TF, TAIL> wA, wB;
     HsY<S, FIRST> yC;
     if (TAIL) {
-        yC = hs_rows<S, FIRST>(state, A, 4 * TF, true, jq, lane);
+        yC = hs_rows<S, FIRST>(state, A, 4 * TF, true, neg, mt, lane);
         tailC[wl * 32 + lane] = hs_tail_chunk<S, FIRST>(sfrag, lane, wl, yC);
     }
-    const HsY<S, FIRST> yA = hs_rows<S, FIRST>(state, A, iA, false, jq, lane), yB = hs_rows<S, FIRST>(state, A, iB, false, jq, lane);
+    const HsY<S, FIRST> yA = hs_rows<S, FIRST>(state, A, iA, false, neg, mt, lane), yB = hs_rows<S, FIRST>(state, A, iB, false, neg, mt, lane);
     hs_step2<S, FIRST, TA, TB>(sfrag, lane, yA, yB, wA, wB);
     __syncwarp();
     if (lane == 0 && !plainbar) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
@@ -431,9 +453,9 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
 
 template <class S, bool FIRST>
 __device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
-                                             int sub, bool needO, bool needE, bool store, uint64_t jq,
+                                             int sub, bool needO, bool needE, bool store, unsigned neg, int mt,
                                              int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, bool plainbar, double (&tr)[6]) {
-#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, plainbar, tr)
+#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, neg, mt, lane, team, wl, tailC, barA, parity, plainbar, tr)
     if (rho == 0) WB_HS_STEP(0);
     else if (rho == 1) WB_HS_STEP(1);
     else if (rho == 2 || S::ROLES == 3) WB_HS_STEP(2);
@@ -441,17 +463,21 @@ __device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict_
 #undef WB_HS_STEP
 }
 
-template <class S>
+template <class S, bool PAD>
 __global__ void __launch_bounds__(32 * S::WARPS, 1)
-haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, long long skew_cycles, int plainbar_i) {
-    constexpr int TF = S::TF, m = S::M, n = S::N, TW = S::TW, NQ = S::NQ;
+haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, int m_true, long long skew_cycles, int plainbar_i) {
+    // m: the TRUE number of vertex pairs (PAD: smaller than S::M, the matrix is treated as padded with zero rows / columns;
+    // a run-time m costs the exact shapes 2 - 3 %, hence the separate instances)
+    constexpr int TF = S::TF, PM = S::M, TW = S::TW, NQ = S::NQ;
+    const int m = PAD ? m_true : PM;
+    const int n = 2 * m;
     constexpr bool TAIL = S::TAIL;
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int team = S::team(warp), wl = S::wl(warp);
     double2* sfrag = reinterpret_cast<double2*>(smem);
     double2* state = reinterpret_cast<double2*>(smem + S::FRAG_D) + team * NQ * S::QS;                    // [subset][row][col]
-    double2* P2 = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2) + team * NQ * (m + 2);   // P[subset][j]
+    double2* P2 = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2) + team * NQ * (PM + 2);   // P[subset][j]
     double2* ptmp = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2 + S::P_D) + team * 3 * TW * 8;   // [kind][warp][row]
     double2* tailC = reinterpret_cast<double2*>(smem + S::FRAG_D + 2 * (size_t)S::STATE_D2 + S::P_D + S::TMP_D) + team * TW * 32;   // [warp][lane]
     __shared__ uint64_t bars[2];
@@ -479,6 +505,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
 
     for (uint64_t G = (uint64_t)blockIdx.x * S::TEAMS + team; G < ngroups; G += (uint64_t)gridDim.x * S::TEAMS) {
         const uint64_t jq = j0 + NQ * G + q;
+        const unsigned neg = hs_negmask(jq, m);
         if (wl == 0) {
             // tr(M^1) = sum_r delta_r A'[r][sigma(r)] = 2 sum_i delta_i A'[i][i + m]; every P[1..m] is rewritten for every group
             if (lane < NQ) {
@@ -489,7 +516,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
                     sr += d * __ldg(A + 2 * ((size_t)i * n + i + m));
                     si += d * __ldg(A + 2 * ((size_t)i * n + i + m) + 1);
                 }
-                P2[lane * (m + 2) + 1] = make_double2(sr, si);
+                P2[lane * (PM + 2) + 1] = make_double2(sr, si);
             }
             __syncwarp();
         }
@@ -499,8 +526,8 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
             const unsigned parity = uses++ & 1u;            // phase of the split barrier: one use per product
-            if (k == 1) hs_role_step<S, true>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, plainbar, tr);   // B_1 = A' from global memory
-            else hs_role_step<S, false>(rho, sfrag, state, A, sub, needO, needE, store, jq, lane, team, wl, tailC, barA, parity, plainbar, tr);
+            if (k == 1) hs_role_step<S, true>(rho, sfrag, state, A, sub, needO, needE, store, neg, m, lane, team, wl, tailC, barA, parity, plainbar, tr);   // B_1 = A' from global memory
+            else hs_role_step<S, false>(rho, sfrag, state, A, sub, needO, needE, store, neg, m, lane, team, wl, tailC, barA, parity, plainbar, tr);
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
@@ -522,7 +549,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
                 for (int off = 16; off >= 1; off >>= 1) { e.x += shfl_xor_d(e.x, off); e.y += shfl_xor_d(e.y, off); }
                 const int j = kind == 0 ? k + 1 : (kind == 1 ? 2 * k + 1 : 2 * k + 2);
                 const bool want = kind == 0 || (kind == 1 ? needO : needE);
-                if (lane == 0 && want && j <= m) P2[qq * (m + 2) + j] = e;
+                if (lane == 0 && want && j <= m) P2[qq * (PM + 2) + j] = e;
             }
         }
         S::sync(team);                         // the last step's traces are in P
@@ -534,7 +561,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             double ar[NQ], ai[NQ];
 #pragma unroll
             for (int qq = 0; qq < NQ; ++qq) {
-                const double2 f = (lane >= 1 && lane <= m) ? P2[qq * (m + 2) + lane] : make_double2(0.0, 0.0);
+                const double2 f = (lane >= 1 && lane <= m) ? P2[qq * (PM + 2) + lane] : make_double2(0.0, 0.0);
                 ar[qq] = 0.5 * f.x; ai[qq] = 0.5 * f.y;                    // c_0 = 1
             }
             for (int sidx = 1; sidx < m; ++sidx) {
@@ -542,7 +569,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
 #pragma unroll
                 for (int qq = 0; qq < NQ; ++qq) {
                     const double cr = shfl_d(ar[qq] * inv_lane, sidx), ci = shfl_d(ai[qq] * inv_lane, sidx);
-                    const double2 f = tgt ? P2[qq * (m + 2) + lane - sidx] : make_double2(0.0, 0.0);
+                    const double2 f = tgt ? P2[qq * (PM + 2) + lane - sidx] : make_double2(0.0, 0.0);
                     const double fr = 0.5 * f.x, fi = 0.5 * f.y;
                     ar[qq] = fma(fr, cr, ar[qq]); ar[qq] = fma(-fi, ci, ar[qq]);
                     ai[qq] = fma(fr, ci, ai[qq]); ai[qq] = fma(fi, cr, ai[qq]);
@@ -567,38 +594,42 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
 }
 
 template <class S>
-static int launch_haf_sym(const double* dA, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
-    auto kern = haf_sym_kernel<S>;
+static int launch_haf_sym(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
+    auto kern = (n == S::N || S::TAIL) ? haf_sym_kernel<S, false> : haf_sym_kernel<S, !S::TAIL>;   // padding: whole-tile shapes only
     const uint64_t ngroups = (j1 - j0 + 3) >> 2;
     const int grid = (int)(ngroups < (uint64_t)sms ? (ngroups ? ngroups : 1) : (uint64_t)sms);
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
     const char* ek = getenv("WB200_HS_SKEW");
     const long long skew = ek ? atoll(ek) : (S::TAIL ? 20000 : 0);
     const char* ep = getenv("WB200_HS_PLAINBAR");
-    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, skew, ep ? atoi(ep) : 0);
+    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, n / 2, skew, ep ? atoi(ep) : 0);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
 }
 
-// Used by wb200_hafnian_dev for the sizes below without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
-// one-team shape for n = 48 / 50).  Sizes: m = n / 2 = 0 or 1 (mod 4) - whole tiles of four vertex pairs plus at most
-// one tail pair - that fit: two teams of two subsets up to n = 50, one team of two subsets for n = 56 / 58.
-// Returns WB200_ENOSUP when the shape is not one this kernel is built for.
-bool haf_sym_supports(int n) { return n == 40 || n == 42 || n == 48 || n == 50 || n == 56 || n == 58; }
+// Used by wb200_hafnian_dev for even n in [36, 58] without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
+// one-team shape for n = 48 / 50).  Shapes: m = n / 2 = 0 or 1 (mod 4) - whole tiles of four vertex pairs plus at most one
+// tail pair - that fit in shared memory: two teams of two subsets up to n = 50, one team of two subsets for n = 56 / 58;
+// m = 2 or 3 (mod 4) run zero-padded in the next whole-tile shape (n = 46 as 48, 54 as 56: 1.40x / 1.43x the row-panel
+// kernel; two padded pairs - 36, 44, 52 - still 1.03x / 1.13x / 1.20x).  Returns WB200_ENOSUP for other sizes.
+bool haf_sym_supports(int n) { return n >= 36 && n <= 58 && (n & 1) == 0; }
 
 int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
     const char* es = getenv("WB200_HAF_SYM");
     const bool one_team = es && atoi(es) == 4;
     switch (n) {
-        case 40: return launch_haf_sym<HsShape<5, false, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-        case 42: return launch_haf_sym<HsShape<5, true, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-        case 48: return one_team ? launch_haf_sym<HsShape<6, false, 4, 1>>(dA, j0, j1, partials, sms, grid_out, st)
-                                 : launch_haf_sym<HsShape<6, false, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-        case 50: return one_team ? launch_haf_sym<HsShape<6, true, 4, 1>>(dA, j0, j1, partials, sms, grid_out, st)
-                                 : launch_haf_sym<HsShape<6, true, 2, 2>>(dA, j0, j1, partials, sms, grid_out, st);
-        case 56: return launch_haf_sym<HsShape<7, false, 2, 1>>(dA, j0, j1, partials, sms, grid_out, st);
-        case 58: return launch_haf_sym<HsShape<7, true, 2, 1>>(dA, j0, j1, partials, sms, grid_out, st);
+        case 36: case 38:                      // one or two vertex pairs short of whole tiles: run padded in the next shape
+        case 40: return launch_haf_sym<HsShape<5, false, 2, 2>>(dA, n, j0, j1, partials, sms, grid_out, st);
+        case 42: return launch_haf_sym<HsShape<5, true, 2, 2>>(dA, n, j0, j1, partials, sms, grid_out, st);
+        case 44: case 46:
+        case 48: return one_team ? launch_haf_sym<HsShape<6, false, 4, 1>>(dA, n, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<HsShape<6, false, 2, 2>>(dA, n, j0, j1, partials, sms, grid_out, st);
+        case 50: return one_team ? launch_haf_sym<HsShape<6, true, 4, 1>>(dA, n, j0, j1, partials, sms, grid_out, st)
+                                 : launch_haf_sym<HsShape<6, true, 2, 2>>(dA, n, j0, j1, partials, sms, grid_out, st);
+        case 52: case 54:
+        case 56: return launch_haf_sym<HsShape<7, false, 2, 1>>(dA, n, j0, j1, partials, sms, grid_out, st);
+        case 58: return launch_haf_sym<HsShape<7, true, 2, 1>>(dA, n, j0, j1, partials, sms, grid_out, st);
         default: return WB200_ENOSUP;
     }
 }
