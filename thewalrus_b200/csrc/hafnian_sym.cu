@@ -107,7 +107,7 @@ __device__ __forceinline__ unsigned hs_negmask(uint64_t jq, int mt) {
 // One row of Y_k = B_k S, read just in time: chunk kap, position t of the lane.  Y_k[v][c] = delta_c B_k[v][sigma(c)], with
 // B_1 = A' (global memory, k = 1) or B_k in the shared-memory state.  Holding the row in registers (as haf_dmma_kernel
 // does) on top of the accumulators of two panels does not fit 168 registers.
-template <class S, bool FIRST>
+template <class S, int FIRST>
 struct HsY {
     const double2* row;      // row of this lane's (subset, vertex): state (stride LD) or A' (stride n, k = 1)
     const double2* col;      // the same vertex as a COLUMN of the state: entry [c][v] = col[c * LD]
@@ -115,14 +115,14 @@ struct HsY {
     int t;
     int mt;                  // FIRST only: true number of vertex pairs (partner offset and row length in A')
     bool rowok;              // FIRST only: this lane's row is a real vertex (not padding)
-    static constexpr bool first = FIRST;   // k = 1: B_1 = A' (global memory), every entry is there, read row-wise;
+    static constexpr bool first = FIRST != 0;   // k = 1 (FIRST = 1; 2: of a zero-padded size): B_1 = A' (global memory), every entry is there, read row-wise;
                                            // a compile-time property, so that the loads of k > 1 are plain LDS
     __device__ __forceinline__ void get(int kap, double& yr, double& yi) const {   // computed tiles only (row-wise)
         constexpr int TF = S::TF;
         const int m = FIRST ? mt : S::M;
         if (kap < 2 * TF) {
             const int tau = kap >> 1;
-            const bool ok = !FIRST || (rowok && 4 * tau + t < mt);
+            const bool ok = FIRST != 2 || (rowok && 4 * tau + t < mt);
             const double2 a = ok ? row[4 * tau + t + (1 - (kap & 1)) * m] : make_double2(0.0, 0.0);
             const unsigned s = hs_sign<S>(neg, 4 * tau + t);
             yr = flipsign(a.x, s); yi = flipsign(a.y, s);
@@ -141,7 +141,7 @@ struct HsY {
 // A panel of tile T computed and stored only the columns of tiles >= T of its rows; the entries of earlier tiles were
 // computed by other panels as THEIR rows, and B_k is symmetric: read them column-wise (conflict-free with the padded
 // strides).  Nothing is stored twice (the first version stored every strictly-upper tile also transposed: 6 % of the kernel).
-template <class S, bool FIRST, int T>
+template <class S, int FIRST, int T>
 struct HsCur {
     const double2* p;
     int d, inc;
@@ -153,10 +153,10 @@ struct HsCur {
     }
     // entries of K tile tau: a0 = column 4 tau + t + m (the partner half), a1 = column 4 tau + t
     __device__ __forceinline__ double2 a0(const HsY<S, FIRST>& y, int tau) const {
-        return (!FIRST || (y.rowok && 4 * tau + y.t < y.mt)) ? p[d] : make_double2(0.0, 0.0);
+        return (FIRST != 2 || (y.rowok && 4 * tau + y.t < y.mt)) ? p[d] : make_double2(0.0, 0.0);
     }
     __device__ __forceinline__ double2 a1(const HsY<S, FIRST>& y, int tau) const {
-        return (!FIRST || (y.rowok && 4 * tau + y.t < y.mt)) ? p[0] : make_double2(0.0, 0.0);
+        return (FIRST != 2 || (y.rowok && 4 * tau + y.t < y.mt)) ? p[0] : make_double2(0.0, 0.0);
     }
     __device__ __forceinline__ void next(const HsY<S, FIRST>& y, int tau_next) {
         constexpr int m = S::M;
@@ -191,7 +191,7 @@ __device__ __forceinline__ void hs_mbar_wait(uint64_t* bar, unsigned parity) {
 // late at every barrier - so the K range is SPLIT over the warps of the team: warp w multiplies the K chunks w, w + TW, ...
 // (the first warp also the packed tail chunk), the partial tiles meet in shared memory and the first warp sums them in
 // warp order while the others store.
-template <class S, bool FIRST>
+template <class S, int FIRST>
 __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfrag, int lane, int wl, const HsY<S, FIRST>& y) {
     constexpr int TF = S::TF, NT = S::NT, m = S::M, LD = S::LD, CH = (2 * TF + S::TW - 1) / S::TW;
     double pr = 0.0, pi = 0.0, p2r = 0.0, p2i = 0.0;
@@ -224,7 +224,7 @@ __device__ __forceinline__ double2 hs_tail_chunk(const double2* __restrict__ sfr
 // panels interleave (a one-tile panel alone is a chain of dependent DMMAs).
 // The loop over the K tiles is deliberately NOT unrolled: fully unrolled, ptxas hoists some thirty 16-byte fragment
 // loads to the top of the block (130 registers) and spills the accumulators.
-template <class S, bool FIRST, int TA, int TB>
+template <class S, int FIRST, int TA, int TB>
 __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int lane, const HsY<S, FIRST>& yA, const HsY<S, FIRST>& yB,
                                          HafRow<S::TF, S::TAIL>& wA, HafRow<S::TF, S::TAIL>& wB) {
     constexpr int TF = S::TF, NT = S::NT;
@@ -321,7 +321,7 @@ __device__ __forceinline__ void hs_step2(const double2* __restrict__ sfrag, int 
 
 // Local pairing sums of one panel over its computed tiles: odd = <W(partner row), Y_old(own row)>, even = the same with
 // Y_new = S W(own row); strictly-upper tiles weigh 2, the diagonal tile 1 (see the header).  Not reduced over lanes.
-template <class S, bool FIRST, int TAU>
+template <class S, int FIRST, int TAU>
 __device__ __forceinline__ void hs_pairing(const HafRow<S::TF, S::TAIL>& w, const HsY<S, FIRST>& y,
                                            double& orr, double& oi, double& er, double& ei) {
     constexpr int TF = S::TF;
@@ -354,7 +354,7 @@ __device__ __forceinline__ void hs_pairing(const HafRow<S::TF, S::TAIL>& w, cons
 
 // the rows of Y_k = B_k S of a panel (first vertex pair ibase) as seen by this lane: from A' at k = 1 (B_1 = A', global
 // memory), else from the team's shared-memory state
-template <class S, bool FIRST>
+template <class S, int FIRST>
 __device__ __forceinline__ HsY<S, FIRST> hs_rows(const double2* __restrict__ state, const double* __restrict__ A, int ibase, bool tailrows,
                                                  unsigned neg, int mt, int lane) {
     constexpr int m = S::M;
@@ -362,8 +362,8 @@ __device__ __forceinline__ HsY<S, FIRST> hs_rows(const double2* __restrict__ sta
     const int i = ibase + (tailrows ? 0 : S::ps(lane));                 // tail panel: the rows of the second pair slot repeat the first
     const int v = i + half * m;
     HsY<S, FIRST> y;
-    y.mt = mt; y.rowok = i < mt;
-    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (y.rowok ? (size_t)(i + half * mt) * (2 * mt) : 0)
+    y.mt = FIRST == 2 ? mt : m; y.rowok = FIRST != 2 || i < mt;
+    y.row = FIRST ? reinterpret_cast<const double2*>(A) + (y.rowok ? (size_t)(i + half * y.mt) * (2 * y.mt) : 0)
                   : state + S::q(lane) * S::QS + v * S::LD;
     y.col = state + S::q(lane) * S::QS + v;
     y.neg = neg; y.t = lane & 3;
@@ -371,7 +371,7 @@ __device__ __forceinline__ HsY<S, FIRST> hs_rows(const double2* __restrict__ sta
 }
 
 // trace shares of one computed panel (first vertex pair ibase, tile TAU), added to the per-lane sums
-template <class S, bool FIRST, int TAU>
+template <class S, int FIRST, int TAU>
 __device__ __forceinline__ void hs_traces(const HafRow<S::TF, S::TAIL>& w, const HsY<S, FIRST>& y, int ibase, bool needO, bool needE, int lane,
                                           double (&tr)[6]) {
     constexpr int TF = S::TF;
@@ -413,10 +413,10 @@ __device__ __forceinline__ void hs_store(double2* __restrict__ state, int ibase,
 }
 
 // one product step of a warp with role RHO: its two panels (+ its K chunks of the tail panel)
-template <class S, bool FIRST, int RHO>
+template <class S, int FIRST, int RHO>
 __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, bool needO, bool needE, bool store, unsigned neg, int mt,
-                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, bool plainbar, double (&tr)[6]) {
+                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
     constexpr int TF = S::TF, TA = S::roleA(RHO), TB = S::roleB(RHO);
     constexpr bool TAIL = S::TAIL, HASB = TB < TF;
     const int iA = 4 * TA + S::PP * sub, iB = HASB ? 4 * TB + S::PP * sub : iA;
@@ -429,13 +429,19 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     const HsY<S, FIRST> yA = hs_rows<S, FIRST>(state, A, iA, false, neg, mt, lane), yB = hs_rows<S, FIRST>(state, A, iB, false, neg, mt, lane);
     hs_step2<S, FIRST, TA, TB>(sfrag, lane, yA, yB, wA, wB);
     __syncwarp();
-    if (lane == 0 && !plainbar) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
+#ifndef WB_HS_PLAINBAR
+    if (lane == 0) hs_mbar_arrive(barA);   // this warp has read everything it needs from other panels' rows
+#endif
     if (HASB) hs_traces<S, FIRST, HASB ? TB : TA>(wB, yB, iB, needO, needE, lane, tr);
     hs_traces<S, FIRST, TA>(wA, yA, iA, needO, needE, lane, tr);
-    // every panel has read its rows of B_k; the partial tail tiles are in shared memory.  (plainbar: an ordinary team barrier
-    // at the same place - what compute-sanitizer's racecheck can follow; it does not model mbarrier ordering.)
-    if (plainbar) S::sync(team);
-    else hs_mbar_wait(barA, parity);
+    // every panel has read its rows of B_k; the partial tail tiles are in shared memory.  (-DWB_HS_PLAINBAR: an ordinary team
+    // barrier at the same place - what compute-sanitizer's racecheck can follow; it does not model mbarrier ordering.  A
+    // run-time switch cost the kernel 1 %.)
+#ifdef WB_HS_PLAINBAR
+    S::sync(team);
+#else
+    hs_mbar_wait(barA, parity);
+#endif
     if (store) {
         hs_store<S, TA>(state, iA, lane, wA);
         if (HASB) hs_store<S, HASB ? TB : TA>(state, iB, lane, wB);
@@ -451,11 +457,11 @@ __device__ __forceinline__ void hs_warp_step(const double2* __restrict__ sfrag, 
     }
 }
 
-template <class S, bool FIRST>
+template <class S, int FIRST>
 __device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict__ sfrag, double2* __restrict__ state, const double* __restrict__ A,
                                              int sub, bool needO, bool needE, bool store, unsigned neg, int mt,
-                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, bool plainbar, double (&tr)[6]) {
-#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, neg, mt, lane, team, wl, tailC, barA, parity, plainbar, tr)
+                                             int lane, int team, int wl, double2* __restrict__ tailC, uint64_t* barA, unsigned parity, double (&tr)[6]) {
+#define WB_HS_STEP(r) hs_warp_step<S, FIRST, (r) < S::ROLES ? (r) : 0>(sfrag, state, A, sub, needO, needE, store, neg, mt, lane, team, wl, tailC, barA, parity, tr)
     if (rho == 0) WB_HS_STEP(0);
     else if (rho == 1) WB_HS_STEP(1);
     else if (rho == 2 || S::ROLES == 3) WB_HS_STEP(2);
@@ -465,7 +471,7 @@ __device__ __forceinline__ void hs_role_step(int rho, const double2* __restrict_
 
 template <class S, bool PAD>
 __global__ void __launch_bounds__(32 * S::WARPS, 1)
-haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, int m_true, long long skew_cycles, int plainbar_i) {
+haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* __restrict__ partials, int m_true, long long skew_cycles) {
     // m: the TRUE number of vertex pairs (PAD: smaller than S::M, the matrix is treated as padded with zero rows / columns;
     // a run-time m costs the exact shapes 2 - 3 %, hence the separate instances)
     constexpr int TF = S::TF, PM = S::M, TW = S::TW, NQ = S::NQ;
@@ -491,7 +497,6 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
         while (clock64() - t0 < skew_cycles) __nanosleep(200);
     }
 
-    const bool plainbar = plainbar_i != 0;
     const int g = lane >> 2, t = lane & 3, q = S::q(lane);
     const int rho = wl / S::SUBS, sub = wl % S::SUBS;
     const int nprod = (m - 1) >> 1, K = nprod + 1;
@@ -526,8 +531,8 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
             double tr[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
             const bool store = k < nprod;
             const unsigned parity = uses++ & 1u;            // phase of the split barrier: one use per product
-            if (k == 1) hs_role_step<S, true>(rho, sfrag, state, A, sub, needO, needE, store, neg, m, lane, team, wl, tailC, barA, parity, plainbar, tr);   // B_1 = A' from global memory
-            else hs_role_step<S, false>(rho, sfrag, state, A, sub, needO, needE, store, neg, m, lane, team, wl, tailC, barA, parity, plainbar, tr);
+            if (k == 1) hs_role_step<S, PAD ? 2 : 1>(rho, sfrag, state, A, sub, needO, needE, store, neg, m, lane, team, wl, tailC, barA, parity, tr);   // B_1 = A' from global memory
+            else hs_role_step<S, 0>(rho, sfrag, state, A, sub, needO, needE, store, neg, m, lane, team, wl, tailC, barA, parity, tr);
             // per-row trace shares of this warp: reduce over the four lanes of a row, park them for the team
 #pragma unroll
             for (int c = 0; c < 6; ++c) {
@@ -601,8 +606,7 @@ static int launch_haf_sym(const double* dA, int n, uint64_t j0, uint64_t j1, dou
     WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
     const char* ek = getenv("WB200_HS_SKEW");
     const long long skew = ek ? atoll(ek) : (S::TAIL ? 20000 : 0);
-    const char* ep = getenv("WB200_HS_PLAINBAR");
-    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, n / 2, skew, ep ? atoi(ep) : 0);
+    kern<<<grid, 32 * S::WARPS, S::BYTES, st>>>(dA, j0, j1, partials, n / 2, skew);
     WB_CUDA(cudaGetLastError());
     *grid_out = grid;
     return WB200_OK;
