@@ -142,7 +142,7 @@ def haf_sym_entries(n):
     and of the tail pair; the tail pair's panel only its own 2 x 2 block.  Sizes with n/2 = 2, 3 (mod 4) run zero-padded in
     the next whole-tile shape: only the entries of real vertices are counted."""
     m = n // 2
-    if n % 2 or not 36 <= n <= 58:
+    if n % 2 or not 36 <= n <= 64:
         return 0
     if m % 4 == 1:                                   # whole tiles + one tail pair
         TF = m // 4

@@ -46,7 +46,7 @@ int wb200_fp64_peak(int device, int kind, double* tflops);
  * [0, 2^(n/2-1)) as in :433/:536.  D = NULL: hafnian; D != NULL (n complex): loop hafnian.
  * Final scale (caller): 0.5^(n/2-1).
  * Two kernels serve this entry: the row-panel kernel (hafnian_dmma.cu, every size) and, for D = NULL, even n in
- * [36, 58] and ranges of at least 8 groups of four subsets per SM, the symmetric-half kernel
+ * [36, 64] and ranges of at least 8 groups of four subsets per SM, the symmetric-half kernel
  * (hafnian_sym.cu: only the tiles on and above the diagonal of every product, 1.3 - 1.5 x faster).  Environment:
  * WB200_HAF_SYM=0 forces the row-panel kernel, =4 the one-team shape of the symmetric-half kernel (n = 48 / 50). */
 size_t wb200_hafnian_workspace_bytes(int n);

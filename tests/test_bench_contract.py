@@ -57,10 +57,10 @@ def test_headline_metric_and_inputs():
     units, mine, ref, _, _ = bench.units_and_flops("hafnian", 50)
     # symmetric-half kernel: 1444 of the 2500 entries of each of the 12 products (hafnian_sym.cu)
     assert units == 1 << 24 and ref == 8 * 50**3 * 24 and mine == 8 * 50 * 1444 * 12
-    assert bench.haf_sym_entries(48) == 1344 and bench.haf_sym_entries(56) == 1792 and bench.haf_sym_entries(60) == 0 and bench.haf_sym_entries(40) == 960
+    assert bench.haf_sym_entries(48) == 1344 and bench.haf_sym_entries(56) == 1792 and bench.haf_sym_entries(34) == 0 and bench.haf_sym_entries(64) == 2304 and bench.haf_sym_entries(40) == 960
     assert bench.haf_sym_entries(46) == 1236 < bench.haf_sym_entries(48)       # padded to the 48 shape: only real entries count
     assert bench.units_and_flops("lhaf", 50)[1] == 8 * 50**3 * 12            # loops stay on the row-panel kernel
-    assert bench.units_and_flops("hafnian", 56)[1] == 8 * 56 * 1792 * 13 and bench.units_and_flops("hafnian", 60)[1] == 8 * 60**3 * 14
+    assert bench.units_and_flops("hafnian", 56)[1] == 8 * 56 * 1792 * 13 and bench.units_and_flops("hafnian", 34)[1] == 8 * 34**3 * 8
     kind, n, U = bench.make_input("perm32")
     assert U.shape == (32, 32) and np.linalg.norm(U, 2) <= 1 + 1e-12          # block of a unitary
     assert bench.units_and_flops("perm", 32)[0] == 1 << 31

@@ -1,4 +1,4 @@
-"""Symmetric-half hafnian kernel (thewalrus_b200/csrc/hafnian_sym.cu; even n in [36, 58] (whole-tile shapes, one-pair tails, and the sizes that run zero-padded in them), no loops, large ranges) against
+"""Symmetric-half hafnian kernel (thewalrus_b200/csrc/hafnian_sym.cu; even n in [36, 64] (whole-tile shapes, one-pair tails, and the sizes that run zero-padded in them), no loops, large ranges) against
 (i) the C oracle's restatement of the reference sum (thewalrus/_hafnian.py:416-467) on the same subset ranges,
 (ii) the row-panel kernel on the same ranges (WB200_HAF_SYM=0), (iii) exact closed forms of complete hafnians.
 The complete n = 50 / 56 goldens of tests/test_gpu_fullsize.py run through this kernel too (it is the default for these sizes).
@@ -39,7 +39,7 @@ def _range(Ax, j0, j1, sym):
             os.environ["WB200_HAF_SYM"] = old
 
 
-@pytest.mark.parametrize("n", [36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58])
+@pytest.mark.parametrize("n", [36, 38, 40, 42, 44, 46, 48, 50, 52, 54, 56, 58, 60, 62, 64])
 @pytest.mark.parametrize("real", [False, True])
 def test_sym_kernel_ranges_match_oracle_and_row_panel_kernel(n, real):
     """Aligned, ragged and offset ranges (the kernel works on groups of four subsets; a range need not be a multiple)."""

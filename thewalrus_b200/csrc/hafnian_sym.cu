@@ -101,7 +101,7 @@ __device__ __forceinline__ unsigned hs_sign(unsigned neg, int p) {
 // know the true size.
 __device__ __forceinline__ unsigned hs_negmask(uint64_t jq, int mt) {
     const unsigned kept = __brev((unsigned)jq) >> (32 - mt);         // bit p = bit mt - 1 - p of jq (thewalrus/_hafnian.py:162-180)
-    return ~kept & ((1u << mt) - 1u);
+    return ~kept & (mt >= 32 ? 0xffffffffu : (1u << mt) - 1u);          // mt <= 32: jq < 2^31
 }
 
 // One row of Y_k = B_k S, read just in time: chunk kap, position t of the lane.  Y_k[v][c] = delta_c B_k[v][sigma(c)], with
@@ -502,7 +502,7 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
     const int nprod = (m - 1) >> 1, K = nprod + 1;
     const uint64_t ngroups = (j1 - j0 + NQ - 1) / NQ;
 
-    const double inv_lane = 1.0 / (double)(lane ? lane : 1);
+    const double inv_idx = 1.0 / (double)(lane + 1);
     unsigned uses = 0;
     cdd acc;
     acc.re = {0.0, 0.0};
@@ -559,35 +559,36 @@ haf_sym_kernel(const double* __restrict__ A, uint64_t j0, uint64_t j1, double* _
         }
         S::sync(team);                         // the last step's traces are in P
         // ---- series c_s = (1/s) sum_i (p_i / 2) c_(s-i), first warp of the team, "push" form: lane l holds the partial sum of
-        // target index l for each of the NQ subsets (independent chains); step s: lane s finishes c_s, one broadcast, and every
-        // lane l > s adds F_(l-s) c_s.  (The first version split each inner sum over 8 lanes with two FP64 divisions and three
+        // coefficient l + 1 for each of the NQ subsets (independent chains); step s: lane s - 1 finishes c_s, one broadcast, and
+        // every lane of a later coefficient c adds F_(c-s) c_s.  (The first version split each inner sum over 8 lanes with two FP64 divisions and three
         // shuffle levels per step: 28 k cycles per group, 8 % of the kernel.)
         if (wl == 0) {
+            const int idx = lane + 1;                                       // this lane's coefficient index (m <= 32 fits a warp)
             double ar[NQ], ai[NQ];
 #pragma unroll
             for (int qq = 0; qq < NQ; ++qq) {
-                const double2 f = (lane >= 1 && lane <= m) ? P2[qq * (PM + 2) + lane] : make_double2(0.0, 0.0);
+                const double2 f = idx <= m ? P2[qq * (PM + 2) + idx] : make_double2(0.0, 0.0);
                 ar[qq] = 0.5 * f.x; ai[qq] = 0.5 * f.y;                    // c_0 = 1
             }
             for (int sidx = 1; sidx < m; ++sidx) {
-                const bool tgt = lane > sidx && lane <= m;
+                const bool tgt = idx > sidx && idx <= m;
 #pragma unroll
                 for (int qq = 0; qq < NQ; ++qq) {
-                    const double cr = shfl_d(ar[qq] * inv_lane, sidx), ci = shfl_d(ai[qq] * inv_lane, sidx);
-                    const double2 f = tgt ? P2[qq * (PM + 2) + lane - sidx] : make_double2(0.0, 0.0);
+                    const double cr = shfl_d(ar[qq] * inv_idx, sidx - 1), ci = shfl_d(ai[qq] * inv_idx, sidx - 1);
+                    const double2 f = tgt ? P2[qq * (PM + 2) + idx - sidx] : make_double2(0.0, 0.0);
                     const double fr = 0.5 * f.x, fi = 0.5 * f.y;
                     ar[qq] = fma(fr, cr, ar[qq]); ar[qq] = fma(-fi, ci, ar[qq]);
                     ai[qq] = fma(fr, ci, ai[qq]); ai[qq] = fma(fi, cr, ai[qq]);
                 }
             }
-            if (lane == m) {
+            if (idx == m) {
 #pragma unroll
                 for (int qq = 0; qq < NQ; ++qq) {
                     const uint64_t jj = j0 + NQ * G + qq;
                     if (jj < j1) {
                         const double sg = ((m - __popcll(jj)) & 1) ? -1.0 : 1.0;
-                        dd_add(acc.re, sg * ar[qq] * inv_lane);
-                        dd_add(acc.im, sg * ai[qq] * inv_lane);
+                        dd_add(acc.re, sg * ar[qq] * inv_idx);
+                        dd_add(acc.im, sg * ai[qq] * inv_idx);
                     }
                 }
             }
@@ -612,12 +613,12 @@ static int launch_haf_sym(const double* dA, int n, uint64_t j0, uint64_t j1, dou
     return WB200_OK;
 }
 
-// Used by wb200_hafnian_dev for even n in [36, 58] without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
+// Used by wb200_hafnian_dev for even n in [36, 64] without loops (env WB200_HAF_SYM=0 keeps the row-panel kernel, =4 the
 // one-team shape for n = 48 / 50).  Shapes: m = n / 2 = 0 or 1 (mod 4) - whole tiles of four vertex pairs plus at most one
-// tail pair - that fit in shared memory: two teams of two subsets up to n = 50, one team of two subsets for n = 56 / 58;
+// tail pair - that fit in shared memory: two teams of two subsets up to n = 50, one team of two subsets for n = 56 / 58 / 64;
 // m = 2 or 3 (mod 4) run zero-padded in the next whole-tile shape (n = 46 as 48, 54 as 56: 1.40x / 1.43x the row-panel
 // kernel; two padded pairs - 36, 44, 52 - still 1.03x / 1.13x / 1.20x).  Returns WB200_ENOSUP for other sizes.
-bool haf_sym_supports(int n) { return n >= 36 && n <= 58 && (n & 1) == 0; }
+bool haf_sym_supports(int n) { return n >= 36 && n <= 64 && (n & 1) == 0; }
 
 int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* partials, int sms, int* grid_out, cudaStream_t st) {
     const char* es = getenv("WB200_HAF_SYM");
@@ -634,6 +635,8 @@ int haf_sym_launch(const double* dA, int n, uint64_t j0, uint64_t j1, double* pa
         case 52: case 54:
         case 56: return launch_haf_sym<HsShape<7, false, 2, 1>>(dA, n, j0, j1, partials, sms, grid_out, st);
         case 58: return launch_haf_sym<HsShape<7, true, 2, 1>>(dA, n, j0, j1, partials, sms, grid_out, st);
+        case 60: case 62:
+        case 64: return launch_haf_sym<HsShape<8, false, 2, 1>>(dA, n, j0, j1, partials, sms, grid_out, st);
         default: return WB200_ENOSUP;
     }
 }

@@ -11,7 +11,7 @@ from thewalrus_b200 import _engine
 
 rng = np.random.default_rng(5)
 grid = int(sys.argv[1]) if len(sys.argv) > 1 else 8          # a few CTAs' worth of groups is enough for the tools
-for n, mode in ((38, "1"), (40, "1"), (42, "1"), (44, "1"), (46, "1"), (48, "1"), (48, "4"), (50, "1"), (50, "4"), (54, "1"), (56, "1"), (58, "1")):
+for n, mode in ((38, "1"), (40, "1"), (42, "1"), (44, "1"), (46, "1"), (48, "1"), (48, "4"), (50, "1"), (50, "4"), (54, "1"), (56, "1"), (58, "1"), (60, "1"), (62, "1"), (64, "1")):
     os.environ["WB200_HAF_SYM"] = mode
     G = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
     A = G + G.T
