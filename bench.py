@@ -43,10 +43,10 @@ SECONDARY = ["hafnian24", "perm32", "tor48", "gbs16"]
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the `ncu --set full` captures
 # under profiles/ (file named next to each number)
 MEASURED_TRAFFIC = {
-    # haf_sym_kernel, complete 2^24-subset launch inside bench.py: 23.5 MB read + 144.7 MB written in 4.3 s.  The writes are the
+    # haf_sym_kernel, complete 2^24-subset launch inside bench.py: 19.1 MB read + 94.2 MB written in 4.3 s.  The writes are the
     # dirty lines of the 256 MiB L2-flush fill that precedes every timed launch, evicted while the kernel runs; the same kernel
     # on 2^18 subsets without a flush before it moves 0.5 MB (profiles/r02_ncu_haf50_sym.txt)
-    "hafnian50": (23511040 + 144741120, "profiles/r02_launches_hafnian50_final2.csv"),
+    "hafnian50": (19121920 + 94205184, "profiles/r02_launches_hafnian50_final3.csv"),
     "perm32": (79104, "profiles/r01_ncu_perm32_v3.txt"),
     "tor48": (73216, "profiles/r01_ncu_tor48_v3b.txt"),
 }
