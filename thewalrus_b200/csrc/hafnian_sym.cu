@@ -1,42 +1,45 @@
-// Hafnian, all edge repetitions 1, Glynn sieve — SYMMETRIC-HALF tensor-core kernel for n = 48 and n = 50.
+// Hafnian, all edge repetitions 1, Glynn sieve — SYMMETRIC-HALF tensor-core kernel for even n from 36 to 64.
 //
 // Same sum as haf_dmma_kernel (thewalrus/_hafnian.py:416-467 + charpoly.powertrace + f), same row-panel products
 // row c of B_(k+1) = (row c of B_k) S_j A'  on DMMA.8x8x4 with trace pairing.  What is new: B_k = M_j^(k-1) A' is
 // SYMMETRIC, so of every product only the tiles on and above the diagonal are computed:
 // the row panel of vertex pair i (tile tau_i = i / 4) computes the N-tiles tau' >= tau_i (+ the packed tail tile) and
 // the tiles below the diagonal are the transposes of what the other panels computed.  At n = 50 that is 96.5 tile
-// units per product and group instead of 162.5 (0.59 of the DMMAs).
+// units per product and group of four subsets instead of 162.5 (0.59 of the DMMAs).
 //
 // That couples the panels of a group: all of them must finish product k before any starts product k + 1, and every
-// panel needs entries other panels computed.  So the iterates of ONE group of four subsets live in shared memory
-// (4 x n x (n + 1) complex = 164 KB at n = 50, next to the 46 KB fragment table of A') and the 12 warps of the CTA advance
-// that group together, two barriers per product: [all panels read their rows of B_k and compute] | barrier |
+// panel needs entries other panels computed.  So the iterates of the groups in flight live in shared memory
+// (four subsets x n x (n + 1) complex = 164 KB at n = 50, next to the 46 KB fragment table of A') and the warps of a team
+// advance their group together, two barriers per product: [all panels read their rows of B_k and compute] | barrier |
 // [write the computed tiles] | barrier.  A panel writes ONLY what it computed (its rows, the columns of tiles >= its own
 // and the tail columns); the entries of earlier tiles are read column-wise from the rows of the panels that computed
-// them (row stride n + 1, subset stride = 16 words mod 32: both access patterns are bank-conflict free).
+// them (row stride n + 1, subset stride = 16 words mod 32: both access patterns are bank-conflict free).  The first
+// barrier is split-phase (mbarrier): arrive after the K loop, wait before the stores, the trace pairing in between.
 //
-// Work split: each warp owns two row panels whose tile counts add up to the same number (tau and 5 - tau: 8 tile units
-// with the tail tile) and walks K ONCE for both - the later tile's panel needs a subset of the other's fragments, so
-// every 16-byte fragment load feeds both and two independent panels' DMMAs interleave.  The K loop is rolled (one
-// iteration = one K tile = 64 DMMAs, the next tile's row entries prefetched): fully unrolled, ptxas hoists ~30 fragment
-// loads and spills the accumulators.  The tail panel (vertex pair 24 at n = 50: only its 2 x 2 tail block is new) is
-// split over K across the 12 warps and summed by warp 0 while the others store.
+// Work split: each warp owns two row panels whose tile counts add up to the same number for every warp (HsShape: roles)
+// and walks K ONCE for both - the later tile's panel needs a subset of the other's fragments, so every 16-byte fragment
+// load feeds both and two independent panels' DMMAs interleave.  The K loop is rolled (one iteration = one K tile, the
+// next tile's row entries prefetched): fully unrolled, ptxas hoists ~30 fragment loads and spills the accumulators.  The
+// tail panel (vertex pair 24 at n = 50: only its 2 x 2 tail block is new) is split over K across the team's warps and
+// summed by the team's first warp while the others store.
 //
 // The power traces stay warp-local although no warp ever sees a whole row of B_(k+1): with U = B_a S, V = B_b,
 //     tr(M^(a+b)) = sum_(x,y) V[x][y] delta_x U[sigma(x)][y]
 // and the term of (y, x) equals the term of (x, y) (both B_a and B_b are symmetric), so every COMPUTED entry (x, y) of
 // a strictly-upper tile counts twice and the entries of the diagonal tiles once - the same partner-row inner products
 // as haf_advance, restricted to the computed tiles, with a weight.  (NumPy emulation of exactly this bookkeeping
-// against the oracle: 3e-15, see DESIGN 3.1.)  Per product every warp leaves its trace shares in shared memory; after
-// the barrier warp w sums the 24 shares of one (trace kind, subset) in a fixed shuffle tree.  The series of a group
-// (thewalrus/_hafnian.py:183-214, f) runs on warp 0 in "push" form, four subsets as four independent chains.
+// against the oracle: 3e-15, see DESIGN 3.1b.)  Per product every warp leaves its trace shares in shared memory; after
+// the barrier warp w sums the shares of one (trace kind, subset) in a fixed shuffle tree.  The series of a group
+// (thewalrus/_hafnian.py:183-214, f) runs on the team's first warp in "push" form, one independent chain per subset.
 //
-// Measured on B200 (profiles/r02_haf_sym_*.txt): n = 50: 3.79e6 subsets/s against 2.75e6 of the row-panel kernel
-// (1.38x) at 0.59 of its DMMAs - tensor pipe 75 % busy (row-panel kernel: 92 %): the two barriers per product, the
-// store phase and the pairing phase of all warps at once cost what the row-panel kernel overlaps.
+// Shapes (HsShape, haf_sym_launch): whole tiles of four vertex pairs plus at most one packed tail pair - n = 40, 42, 48, 50
+// (two teams of 6 warps, two subsets each), 56, 58, 64 (one team of 8 warps, two subsets); the sizes in between run
+// zero-padded in the next whole-tile shape.  Loop hafnians, other sizes and short ranges stay on haf_dmma_kernel.
 //
-// Shape: TF = 6 full tiles (24 vertex pairs = 12 warps x 2 panels) with no tail (n = 48) or a one-pair packed tail
-// (n = 50).  Everything else, and the loop hafnian, stays on haf_dmma_kernel.
+// Measured on B200 (profiles/r02_haf_sym_vs_panel.txt, r02_ncu_haf50_sym.txt): n = 50: 3.87e6 subsets/s against 2.75e6 of
+// the row-panel kernel (1.41x) at 0.59 of its DMMAs, n = 56: 2.86e6 against 1.90e6 (1.51x) - tensor pipe 78 - 81 % busy
+// (row-panel kernel: 92 %): the barriers, the store phase and the pairing phase of all warps at once cost what the
+// row-panel kernel overlaps (profiles/r02_haf_sym_phase_costs.txt).
 #include <stdlib.h>
 #include "common.cuh"
 #include "haf_dmma.cuh"
