@@ -194,6 +194,13 @@ int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, doubl
                   void* d_workspace, size_t workspace_bytes, void* stream);
 int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
                    double* kernel_ms);
+/* the same for a REAL symmetric O (2N x 2N doubles, not interleaved complex): the subset tree runs in real arithmetic
+ * (numba specialises the reference's njit kernels on the dtype the same way, thewalrus/_torontonian.py:123, 157, 189).
+ * Same prefixes, same workspace size, same outputs. */
+int wb200_tor_f64_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                      void* d_workspace, size_t workspace_bytes, void* stream);
+int wb200_tor_f64_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
+                       double* kernel_ms);
 
 /* ---- loop torontonian -------------------------------------------------------------------------------
  * Replaces rec_ltorontonian / recursiveLTor / numba_ltor (thewalrus/_torontonian.py:276-345, 369-412):

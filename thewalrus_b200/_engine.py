@@ -4,6 +4,7 @@ PyTorch is used only for what it is good at here: device buffers, the current CU
 ``torch.distributed``.  All arithmetic happens inside libwalrus_b200.so.
 """
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -196,8 +197,15 @@ def tor_range(O, p0, p1, device=None, gamma=None):
     N = O.shape[0] // 2
     if lib.wb200_tor_workspace_bytes(N) == 0:
         raise NotImplementedError(f"torontonian kernel supports 2..32 modes, got {N}")
-    O, pO = _lib.as_c128(O)
     out = np.empty(2)
+    if gamma is None and (not np.iscomplexobj(O) or not np.any(np.asarray(O).imag)):
+        # real symmetric O: the tree runs in real arithmetic (wb200_tor_f64_host); WB200_TOR_REAL=0 keeps the complex kernel
+        if os.environ.get("WB200_TOR_REAL", "1") != "0":
+            Or = np.ascontiguousarray(np.asarray(O).real, dtype=np.float64)
+            rc = lib.wb200_tor_f64_host(idx, _lib.dptr(Or), N, p0, p1, _lib.dptr(out), None)
+            _lib.check(rc, "wb200_tor_f64_host")
+            return out
+    O, pO = _lib.as_c128(O)
     if gamma is None:
         rc = lib.wb200_tor_host(idx, pO, N, p0, p1, _lib.dptr(out), None)
     else:

@@ -76,6 +76,9 @@ SIGNATURES = {
     "wb200_tor_dev": (ctypes.c_int, [_vp, ctypes.c_int, _u64, _u64, _vp, _vp, ctypes.c_size_t, _vp]),
     "wb200_tor_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, ctypes.c_int, _u64, _u64, _c_double_p,
                                       _c_double_p]),
+    "wb200_tor_f64_dev": (ctypes.c_int, [_vp, ctypes.c_int, _u64, _u64, _vp, _vp, ctypes.c_size_t, _vp]),
+    "wb200_tor_f64_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, ctypes.c_int, _u64, _u64, _c_double_p,
+                                          _c_double_p]),
     "wb200_ltor_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int, _u64, _u64, _vp, _vp, ctypes.c_size_t, _vp]),
     "wb200_ltor_host": (ctypes.c_int, [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int, _u64, _u64, _c_double_p,
                                        _c_double_p]),

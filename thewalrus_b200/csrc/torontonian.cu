@@ -41,6 +41,22 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) {  // a * conj(b)
     return make_double2(fma(a.x, b.x, a.y * b.y), fma(a.y, b.x, -a.x * b.y));
 }
 
+// Scalar type of the tree: double2 (Hermitian I - O) or double (REAL SYMMETRIC O, e.g. real squeezing through a real
+// interferometer: a quarter of the multiplications per Schur-complement entry and half the shared memory per node).
+template <typename T> struct TorS;
+template <> struct TorS<double2> {
+    static __device__ __forceinline__ double re(double2 a) { return a.x; }
+    static __device__ __forceinline__ double absq(double2 a) { return a.x * a.x + a.y * a.y; }
+    static __device__ __forceinline__ double2 mulc(double2 a, double2 b) { return cmulc(a, b); }
+    static __device__ __forceinline__ void subs(double2& v, double2 q, double s) { v.x -= q.x * s; v.y -= q.y * s; }
+};
+template <> struct TorS<double> {
+    static __device__ __forceinline__ double re(double a) { return a; }
+    static __device__ __forceinline__ double absq(double a) { return a * a; }
+    static __device__ __forceinline__ double mulc(double a, double b) { return a * b; }
+    static __device__ __forceinline__ void subs(double& v, double q, double s) { v = fma(-q, s, v); }
+};
+
 // interleave modes and form B = I - O.  Loop torontonian (gamma != nullptr): B is bordered by one extra
 // row/column  B[2N][c] = gamma_c, B[c][2N] = conj(gamma_c), B[2N][2N] = 0.  Eliminating a pivot k of the
 // bordered Hermitian matrix updates the border row exactly like the forward substitution of the reference
@@ -70,6 +86,16 @@ __global__ void tor_prep_kernel(const double2* __restrict__ O, const double2* __
     }
 }
 
+// real symmetric O (torontonian only): the same interleaving, B = I - O in doubles
+__global__ void tor_prep_real_kernel(const double* __restrict__ O, int N, double* __restrict__ B) {
+    const int n2 = 2 * N;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n2 * n2; idx += gridDim.x * blockDim.x) {
+        const int r = idx / n2, c = idx % n2;
+        const int sr = (r >> 1) + (r & 1) * N, sc = (c >> 1) + (c & 1) * N;
+        B[idx] = (r == c ? 1.0 : 0.0) - O[(size_t)sr * n2 + sc];
+    }
+}
+
 // Lower-triangle enumeration: el -> (r, c), r >= c, el = r (r + 1) / 2 + c.
 __device__ __forceinline__ void tri_decode(int el, int& r, int& c) {
     int rr = (int)((__fsqrt_rn((float)(8 * el + 1)) - 1.0f) * 0.5f);   // exact up to one unit for el < 2^20
@@ -81,8 +107,9 @@ __device__ __forceinline__ void tri_decode(int el, int& r, int& c) {
 
 // 1 / d1 and 1 / d2 of the two pivots of a leading mode (d2 = t11 - |e|^2 / d1) from ONE division:
 // with w = d1 t11 - |e|^2 = d1 d2 and q = 1 / (d1 w):  1 / d1 = q w,  1 / d2 = d1 / w = q d1^2.
-__device__ __forceinline__ void pivot_inverses(double d1, double t11, double2 e, double& i1, double& i2, double& d1d2) {
-    const double w = fma(d1, t11, -(e.x * e.x + e.y * e.y));
+template <typename T>
+__device__ __forceinline__ void pivot_inverses(double d1, double t11, T e, double& i1, double& i2, double& d1d2) {
+    const double w = fma(d1, t11, -TorS<T>::absq(e));
     const double q = 1.0 / (d1 * w);
     i1 = q * w;
     i2 = q * d1 * d1;
@@ -92,25 +119,27 @@ __device__ __forceinline__ void pivot_inverses(double d1, double t11, double2 e,
 // One entry of the Schur complement of the leading mode (rows/cols 0, 1) of the Hermitian matrix P (stride ld):
 // both scalar pivots fused.  Reads only the lower triangle of P (columns 0, 1 and the entry itself), so it can
 // run in place.  r, c >= 2 index P.
-__device__ __forceinline__ double2 schur_entry(const double2* P, int ld, int r, int c, double2 e, double i1, double i2) {
-    double2 v = P[r * ld + c];
-    const double2 a = P[r * ld], b = P[c * ld];
-    double2 ur = P[r * ld + 1], uc = P[c * ld + 1];
-    { const double2 q = cmulc(a, e); ur.x -= q.x * i1; ur.y -= q.y * i1; }
-    { const double2 q = cmulc(b, e); uc.x -= q.x * i1; uc.y -= q.y * i1; }
-    { const double2 q = cmulc(a, b); v.x -= q.x * i1; v.y -= q.y * i1; }
-    { const double2 q = cmulc(ur, uc); v.x -= q.x * i2; v.y -= q.y * i2; }
+template <typename T>
+__device__ __forceinline__ T schur_entry(const T* P, int ld, int r, int c, T e, double i1, double i2) {
+    using X = TorS<T>;
+    T v = P[r * ld + c];
+    const T a = P[r * ld], b = P[c * ld];
+    T ur = P[r * ld + 1], uc = P[c * ld + 1];
+    X::subs(ur, X::mulc(a, e), i1);
+    X::subs(uc, X::mulc(b, e), i1);
+    X::subs(v, X::mulc(a, b), i1);
+    X::subs(v, X::mulc(ur, uc), i2);
     return v;
 }
 
 // Eliminate the leading mode of P (dim x dim, stride ld) into Q (stride ldq; Q may be P + 2 (ld + 1) with ldq = ld:
 // in place).  Lower triangle only.  All threads of the CTA take part; returns d1 * d2.
-template <int THREADS>
-__device__ double eliminate_into(const double2* P, int ld, int dim, double2* Q, int ldq) {
+template <int THREADS, typename T>
+__device__ double eliminate_into(const T* P, int ld, int dim, T* Q, int ldq) {
     __syncthreads();
-    const double2 e = P[ld];
+    const T e = P[ld];
     double i1, i2, d1d2;
-    pivot_inverses(P[0].x, P[ld + 1].x, e, i1, i2, d1d2);
+    pivot_inverses(TorS<T>::re(P[0]), TorS<T>::re(P[ld + 1]), e, i1, i2, d1d2);
     const int cd = dim - 2, tri = cd * (cd + 1) / 2;
     for (int el = threadIdx.x; el < tri; el += THREADS) {
         int r, c;
@@ -122,34 +151,36 @@ __device__ double eliminate_into(const double2* P, int ld, int dim, double2* Q, 
 }
 
 struct TorParams {
-    const double2* B;   // interleaved (bordered) I - O
+    const void* B;      // interleaved (bordered) I - O: double2, or double for the real-symmetric torontonian
     int N, P, g, DC;    // modes, prefix modes, log2 prefixes per CTA, BFS modes
     int off_depth, off_pool, off_desc;   // shared-memory layout, in double2 units from the start
     uint64_t p0, p1;
 };
 
 // finish a 2-mode (4x4 Hermitian, stride ld, lower triangle) node in registers: 4 subsets
-__device__ __forceinline__ double tail2(const double2* T, int ld, double det, double sgn) {
-    const double t00 = T[0].x, t11 = T[ld + 1].x, t22 = T[2 * ld + 2].x, t33 = T[3 * ld + 3].x;
-    const double2 t10 = T[ld], t20 = T[2 * ld], t30 = T[3 * ld], t21 = T[2 * ld + 1], t31 = T[3 * ld + 1],
-                  t32 = T[3 * ld + 2];
+template <typename TT>
+__device__ __forceinline__ double tail2(const TT* T, int ld, double det, double sgn) {
+    using X = TorS<TT>;
+    const double t00 = X::re(T[0]), t11 = X::re(T[ld + 1]), t22 = X::re(T[2 * ld + 2]), t33 = X::re(T[3 * ld + 3]);
+    const TT t10 = T[ld], t20 = T[2 * ld], t30 = T[3 * ld], t21 = T[2 * ld + 1], t31 = T[3 * ld + 1],
+             t32 = T[3 * ld + 2];
     double sum = rsqrt(det);                                         // {}: two exclusions, sign unchanged
-    const double detB = t22 * t33 - (t32.x * t32.x + t32.y * t32.y);  // {m1}
+    const double detB = t22 * t33 - X::absq(t32);                    // {m1}
     sum -= rsqrt(det * detB);
     const double i1 = 1.0 / t00;
-    const double d2 = t11 - (t10.x * t10.x + t10.y * t10.y) * i1;
+    const double d2 = t11 - X::absq(t10) * i1;
     sum -= rsqrt(det * t00 * d2);                                    // {m0}
     // {m0, m1}: Schur complement of mode 0 on the m1 block
     const double i2 = 1.0 / d2;
-    double2 u2 = t21, u3 = t31;   // column 1 after pivot 1
-    { double2 q = cmulc(t20, t10); u2.x -= q.x * i1; u2.y -= q.y * i1; }
-    { double2 q = cmulc(t30, t10); u3.x -= q.x * i1; u3.y -= q.y * i1; }
-    const double s22 = t22 - (t20.x * t20.x + t20.y * t20.y) * i1 - (u2.x * u2.x + u2.y * u2.y) * i2;
-    const double s33 = t33 - (t30.x * t30.x + t30.y * t30.y) * i1 - (u3.x * u3.x + u3.y * u3.y) * i2;
-    double2 s32 = t32;
-    { double2 q = cmulc(t30, t20); s32.x -= q.x * i1; s32.y -= q.y * i1; }
-    { double2 q = cmulc(u3, u2); s32.x -= q.x * i2; s32.y -= q.y * i2; }
-    const double detS = s22 * s33 - (s32.x * s32.x + s32.y * s32.y);
+    TT u2 = t21, u3 = t31;   // column 1 after pivot 1
+    X::subs(u2, X::mulc(t20, t10), i1);
+    X::subs(u3, X::mulc(t30, t10), i1);
+    const double s22 = t22 - X::absq(t20) * i1 - X::absq(u2) * i2;
+    const double s33 = t33 - X::absq(t30) * i1 - X::absq(u3) * i2;
+    TT s32 = t32;
+    X::subs(s32, X::mulc(t30, t20), i1);
+    X::subs(s32, X::mulc(u3, u2), i2);
+    const double detS = s22 * s33 - X::absq(s32);
     sum += rsqrt(det * t00 * d2 * detS);
     return sgn * sum;
 }
@@ -203,9 +234,10 @@ __host__ __device__ __forceinline__ int tor_ld(int dim) { return dim | 1; }
 constexpr int TOR_MAXG = 5;
 constexpr int TOR_MAXNODES = 128;   // 2-mode tail nodes of a 9-mode breadth-first expansion
 
-// Shared-memory plan (double2 units): T (n2^2) | depth buffers of the prefix DFS | include-children pool of the
+// Shared-memory plan (units of the scalar type, double2 or double): T (n2^2) | depth buffers of the prefix DFS | include-children pool of the
 // breadth-first expansion | node descriptors.  Returns the total in bytes.
-__host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, int* off_depth, int* off_pool, int* off_desc) {
+__host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, int* off_depth, int* off_pool, int* off_desc,
+                                                size_t elem = sizeof(double2)) {
     const int n2 = 2 * N + aug, dg = 2 * (DC + g) + aug;
     int off = n2 * tor_ld(n2);
     *off_depth = off;
@@ -215,7 +247,7 @@ __host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, i
     *off_desc = off;
     // descriptors: 2 x (ptr, ld) int + 2 x (det, sgn) double per node, ping-pong, + inv1/inv2 per parent
     const size_t desc = (size_t)TOR_MAXNODES * (2 * 2 * sizeof(int) + 2 * 2 * sizeof(double)) + 2 * 64 * sizeof(double);
-    return (size_t)off * sizeof(double2) + desc;
+    return (((size_t)off * elem + 15) & ~(size_t)15) + desc;
 }
 
 // AUG = 0: torontonian; AUG = 1: loop torontonian (every matrix carries the border row/column).
@@ -229,14 +261,16 @@ __host__ __device__ inline size_t tor_smem_plan(int N, int aug, int g, int DC, i
 // next prefix costs ONE elimination (the level whose bit turns 0 -> 1; the levels below restart as exclusions).
 // The last DC modes are expanded breadth-first: level l has 2^l nodes, each served by 256 / 2^l threads, the
 // included children go to a pool that stays alive until the 2-mode tails have been summed in registers.
-template <int AUG, int THREADS>
+template <int AUG, int THREADS, typename T = double2>
 __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __restrict__ partials) {
+    static_assert(AUG == 0 || sizeof(T) == sizeof(double2), "the loop torontonian has a complex border: complex only");
     constexpr int LOG_THREADS = THREADS == 512 ? 9 : (THREADS == 256 ? 8 : 7);
     static_assert(THREADS == 128 || THREADS == 256 || THREADS == 512, "power of two, at least one thread per parent node");
     extern __shared__ __align__(16) double smem_tor[];
     const int N = p.N, n2 = 2 * N + AUG, DC = p.DC, g = p.g, P = p.P;
     const int dg = 2 * (DC + g) + AUG, ldT = tor_ld(n2);
-    double2* S = reinterpret_cast<double2*>(smem_tor);
+    T* S = reinterpret_cast<T*>(smem_tor);
+    const T* Bg = static_cast<const T*>(p.B);
     int* ptrA = reinterpret_cast<int*>(S + p.off_desc);
     int* ldA = ptrA + TOR_MAXNODES;
     int* ptrB = ldA + TOR_MAXNODES;
@@ -258,12 +292,12 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
     for (uint64_t grp = ngroups_first + blockIdx.x; grp < ngroups_last; grp += gridDim.x) {
         // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0), in place on T
         __syncthreads();
-        for (int idx = tid; idx < n2 * n2; idx += THREADS) S[(idx / n2) * ldT + idx % n2] = p.B[idx];
+        for (int idx = tid; idx < n2 * n2; idx += THREADS) S[(idx / n2) * ldT + idx % n2] = Bg[idx];
         double det0 = 1.0, sgn0 = 1.0;
         const int lead = P - g;
         for (int i = 0; i < lead; ++i) {
             const bool inc = (grp >> (lead - 1 - i)) & 1ull;
-            double2* V = S + 2 * i * (ldT + 1);
+            T* V = S + 2 * i * (ldT + 1);
             if (inc) det0 *= eliminate_into<THREADS>(V, ldT, n2 - 2 * i, V + 2 * (ldT + 1), ldT);
             else sgn0 = -sgn0;
         }
@@ -315,12 +349,12 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
                 const int cd = dim - 2, tri = cd * (cd + 1) / 2, cld = tor_ld(cd), csz = cd * cld;
                 const int nd = tid >> shift, lane = tid & ((1 << shift) - 1), step = 1 << shift;
                 const int myptr = pc[nd], myld = lc[nd];
-                const double2* Pn = S + myptr;
-                double2* Qn = S + pool + nd * csz;
+                const T* Pn = S + myptr;
+                T* Qn = S + pool + nd * csz;
                 // every thread of the node derives the two pivots itself: no separate pivot pass, one barrier per level
-                const double2 e = Pn[myld];
+                const T e = Pn[myld];
                 double i1, i2, d1d2;
-                pivot_inverses(Pn[0].x, Pn[myld + 1].x, e, i1, i2, d1d2);
+                pivot_inverses(TorS<T>::re(Pn[0]), TorS<T>::re(Pn[myld + 1]), e, i1, i2, d1d2);
                 if (lane == 0) {
                     const double dt = dc[nd], sg = sc[nd];
                     pn[2 * nd] = myptr + 2 * (myld + 1); ln[2 * nd] = myld; dn[2 * nd] = dt; sn[2 * nd] = -sg;   // exclude
@@ -338,7 +372,7 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
             }
             // ---- 2-mode nodes finished by single threads
             for (int nd = tid; nd < nodes; nd += THREADS) {
-                if (AUG) dd_add(acc, tail2_loop(S + pc[nd], lc[nd], dc[nd], sc[nd]));
+                if constexpr (AUG != 0) dd_add(acc, tail2_loop(S + pc[nd], lc[nd], dc[nd], sc[nd]));
                 else dd_add(acc, tail2(S + pc[nd], lc[nd], dc[nd], sc[nd]));
             }
         }
@@ -561,7 +595,7 @@ __global__ void __launch_bounds__(32 * T4_MAXW) tor4_kernel(TorParams p, int off
     for (uint64_t grp = ngroups_first + blockIdx.x; grp < ngroups_last; grp += gridDim.x) {
         // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0), in place on T
         __syncthreads();
-        for (int idx = tid; idx < n2 * n2; idx += threads) S[(idx / n2) * ldT + idx % n2] = p.B[idx];
+        for (int idx = tid; idx < n2 * n2; idx += threads) S[(idx / n2) * ldT + idx % n2] = static_cast<const double2*>(p.B)[idx];
         __syncthreads();
         double det0 = 1.0, sgn0 = 1.0;
         const int lead = P - g;
@@ -676,9 +710,10 @@ extern "C" size_t wb200_tor_workspace_bytes(int n_modes) {
     return tor_ws_partials_offset(n_modes) + sizeof(double) * 4 * TOR_MAX_GRID;
 }
 
-// shared launcher: dGamma == nullptr -> torontonian, else loop torontonian
+// shared launcher: dGamma == nullptr -> torontonian, else loop torontonian; real_O: dO is a REAL symmetric 2N x 2N matrix
+// (torontonian only) and the tree runs in real arithmetic
 static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
-                      void* d_workspace, size_t workspace_bytes, void* stream) {
+                      void* d_workspace, size_t workspace_bytes, void* stream, bool real_O = false) {
     if (!dO || !d_out4 || !d_workspace) { set_error("tor: null pointer"); return WB200_EINVAL; }
     uint64_t total = 0;
     int rc = wb200_tor_num_prefixes(n_modes, &total);
@@ -697,7 +732,7 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     double* dpart = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(d_workspace) + tor_ws_partials_offset(N));
     p.B = dB;
     const char* ev4 = getenv("WB200_TOR_V4");
-    if (!aug && p.DC == T4_DC && ev4 && atoi(ev4)) {
+    if (!aug && !real_O && p.DC == T4_DC && ev4 && atoi(ev4)) {
         // v4 EXPERIMENT (opt-in, WB200_TOR_V4=1): warp-autonomous tensor-core expansion (tor4_kernel).  Correct (same
         // parity tests pass), but 2.5 ms at 2N = 48 against 1.22 ms for the breadth-first kernel below: the depth-first
         // chain of a warp is one long latency chain (pivot loads -> FP64 division -> fragment vectors -> DMMA -> store,
@@ -732,6 +767,24 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     }
     // small problems (or thin multi-GPU shards): fewer prefixes per CTA so that every SM gets a group
     while (p.g > 0 && ((p1 - p0) >> p.g) < 2ull * (uint64_t)sms) --p.g;
+    if (real_O) {
+        const size_t shm = tor_smem_plan(N, 0, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc, sizeof(double));
+        if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
+        auto kern = tor_kernel<0, TOR_THREADS, double>;
+        WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+        const uint64_t groups = ((p1 + (1ull << p.g) - 1) >> p.g) - (p0 >> p.g);
+        int occ = 1;
+        WB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TOR_THREADS, shm));
+        if (occ < 1) occ = 1;
+        const uint64_t slots = (uint64_t)sms * occ;
+        int grid = (int)(groups < slots ? (groups ? groups : 1) : slots);
+        if (grid > TOR_MAX_GRID) grid = TOR_MAX_GRID;
+        tor_prep_real_kernel<<<8, 256, 0, st>>>(dO, N, reinterpret_cast<double*>(dB));
+        kern<<<grid, TOR_THREADS, shm, st>>>(p, dpart);
+        final_reduce_kernel<<<1, 32, 0, st>>>(dpart, grid, d_out4);
+        WB_CUDA(cudaGetLastError());
+        return WB200_OK;
+    }
     const size_t shm = tor_smem_plan(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc);
     if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
     if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1, TOR_THREADS_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -757,6 +810,11 @@ extern "C" int wb200_tor_dev(const double* dO, int n_modes, uint64_t p0, uint64_
     return tor_launch(dO, nullptr, n_modes, p0, p1, d_out4, d_workspace, workspace_bytes, stream);
 }
 
+extern "C" int wb200_tor_f64_dev(const double* dO, int n_modes, uint64_t p0, uint64_t p1, double* d_out4,
+                                 void* d_workspace, size_t workspace_bytes, void* stream) {
+    return tor_launch(dO, nullptr, n_modes, p0, p1, d_out4, d_workspace, workspace_bytes, stream, true);
+}
+
 extern "C" int wb200_ltor_dev(const double* dO, const double* dGamma, int n_modes, uint64_t p0, uint64_t p1,
                               double* d_out4, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (!dGamma) { set_error("ltor: null gamma"); return WB200_EINVAL; }
@@ -764,7 +822,7 @@ extern "C" int wb200_ltor_dev(const double* dO, const double* dGamma, int n_mode
 }
 
 static int tor_host_impl(int device, const double* O, const double* gamma, int n_modes, uint64_t p0, uint64_t p1,
-                         double out2[2], double* kernel_ms) {
+                         double out2[2], double* kernel_ms, bool real_O = false) {
     if (!O || !out2) { set_error("tor: null pointer"); return WB200_EINVAL; }
     uint64_t total = 0;
     int rc = wb200_tor_num_prefixes(n_modes, &total);
@@ -773,10 +831,11 @@ static int tor_host_impl(int device, const double* O, const double* gamma, int n
     WB_CUDA(cudaSetDevice(device));
     DevBufT dO, dG, dws, dout;
     const size_t wsb = wb200_tor_workspace_bytes(n_modes);
-    WB_POOL(pool_alloc(&dO.p, sizeof(double) * 2 * n2 * n2));
+    const size_t obytes = sizeof(double) * (real_O ? 1 : 2) * n2 * n2;
+    WB_POOL(pool_alloc(&dO.p, obytes));
     WB_POOL(pool_alloc(&dws.p, wsb));
     WB_POOL(pool_alloc(&dout.p, sizeof(double) * 4));
-    WB_CUDA(cudaMemcpy(dO.p, O, sizeof(double) * 2 * n2 * n2, cudaMemcpyHostToDevice));
+    WB_CUDA(cudaMemcpy(dO.p, O, obytes, cudaMemcpyHostToDevice));
     if (gamma) {
         WB_POOL(pool_alloc(&dG.p, sizeof(double) * 2 * n2));
         WB_CUDA(cudaMemcpy(dG.p, gamma, sizeof(double) * 2 * n2, cudaMemcpyHostToDevice));
@@ -787,7 +846,7 @@ static int tor_host_impl(int device, const double* O, const double* gamma, int n
         WB_CUDA(cudaEventCreate(&e1));
         WB_CUDA(cudaEventRecord(e0, 0));
     }
-    rc = tor_launch((const double*)dO.p, (const double*)dG.p, n_modes, p0, p1, (double*)dout.p, dws.p, wsb, nullptr);
+    rc = tor_launch((const double*)dO.p, (const double*)dG.p, n_modes, p0, p1, (double*)dout.p, dws.p, wsb, nullptr, real_O);
     if (rc) { if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return rc; }
     if (kernel_ms) {
         WB_CUDA(cudaEventRecord(e1, 0));
@@ -807,6 +866,11 @@ static int tor_host_impl(int device, const double* O, const double* gamma, int n
 extern "C" int wb200_tor_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
                               double* kernel_ms) {
     return tor_host_impl(device, O, nullptr, n_modes, p0, p1, out2, kernel_ms);
+}
+
+extern "C" int wb200_tor_f64_host(int device, const double* O, int n_modes, uint64_t p0, uint64_t p1, double out2[2],
+                                  double* kernel_ms) {
+    return tor_host_impl(device, O, nullptr, n_modes, p0, p1, out2, kernel_ms, true);
 }
 
 extern "C" int wb200_ltor_host(int device, const double* O, const double* gamma, int n_modes, uint64_t p0, uint64_t p1,
