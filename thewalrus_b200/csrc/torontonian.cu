@@ -201,12 +201,7 @@ __device__ __forceinline__ double pivot5(double2 (&a)[5][5]) {
 }
 
 // loop torontonian: finish a 2-mode bordered (5x5, stride ld) node, 4 subsets; exponent = -corner / 2
-__device__ __forceinline__ double tail2_loop(const double2* T, int ld, double det, double sgn) {
-    double2 a[5][5];
-#pragma unroll
-    for (int r = 0; r < 5; ++r)
-#pragma unroll
-        for (int c = 0; c <= r; ++c) a[r][c] = T[r * ld + c];
+__device__ __forceinline__ double tail2_loop_body(double2 (&a)[5][5], double det, double sgn) {
     double sum = exp(-0.5 * a[4][4].x) * rsqrt(det);                          // {}
     {                                                                         // {m1}: pivots 2, 3
         const double d1 = a[2][2].x, i1 = 1.0 / d1;
@@ -225,6 +220,111 @@ __device__ __forceinline__ double tail2_loop(const double2* T, int ld, double de
     const double p3 = pivot5<3>(a);
     sum += exp(-0.5 * a[4][4].x) * rsqrt(det01 * p2 * p3);                    // {m0, m1}
     return sgn * sum;
+}
+__device__ __forceinline__ double tail2_loop(const double2* T, int ld, double det, double sgn) {       // square storage (v4)
+    double2 a[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = T[r * ld + c];
+    return tail2_loop_body(a, det, sgn);
+}
+__device__ __forceinline__ double tail2_loop_p(const double2* T, int k, double det, double sgn) {      // packed view (T, k)
+    double2 a[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+        const int rb = ((r + k) * (r + k + 1) >> 1) + k;
+#pragma unroll
+        for (int c = 0; c <= r; ++c) a[r][c] = T[rb + c];
+    }
+    return tail2_loop_body(a, det, sgn);
+}
+
+// ---- packed lower triangles (tor_kernel) -------------------------------------------------------------------------------
+// A node of the subset tree is a VIEW (ptr, k) of a stored Hermitian matrix: the packed lower triangle at S + ptr
+// (row r starts at r (r + 1) / 2) with the leading k rows and columns dropped.  Element (r, c), r >= c, of the view:
+__device__ __forceinline__ int tv_row(int k, int r) { const int rr = r + k; return ((rr * (rr + 1)) >> 1) + k; }
+__host__ __device__ __forceinline__ int tor_tri(int dim) { return dim * (dim + 1) / 2; }
+// Round 1 stored full squares with an odd stride (tor_ld): twice the shared memory, ONE CTA per SM at 2N = 48.  Packed,
+// two CTAs of the complex kernel (four of the real one) share an SM and cover each other's barriers.
+
+// One entry of the Schur complement of the leading mode (rows/cols 0, 1) of the view (P, k): both scalar pivots fused.
+// Reads only columns 0, 1 and the entry itself, so it can run in place.  r, c >= 2 index the view.
+template <typename T>
+__device__ __forceinline__ T schur_entry_p(const T* P, int k, int r, int c, T e, double i1, double i2) {
+    using X = TorS<T>;
+    const int rb = tv_row(k, r), cb = tv_row(k, c);
+    T v = P[rb + c];
+    const T a = P[rb], b = P[cb];
+    T ur = P[rb + 1], uc = P[cb + 1];
+    X::subs(ur, X::mulc(a, e), i1);
+    X::subs(uc, X::mulc(b, e), i1);
+    X::subs(v, X::mulc(a, b), i1);
+    X::subs(v, X::mulc(ur, uc), i2);
+    return v;
+}
+
+// Eliminate the leading mode of the view (P, k) of dimension dim into the view (Q, kq) (Q == P, kq == k + 2: in place).
+// All threads of the CTA take part; returns d1 * d2.
+template <int THREADS, typename T>
+__device__ double eliminate_into_p(const T* P, int k, int dim, T* Q, int kq) {
+    __syncthreads();
+    const int r1 = tv_row(k, 1);
+    const T e = P[r1];
+    double i1, i2, d1d2;
+    pivot_inverses(TorS<T>::re(P[tv_row(k, 0)]), TorS<T>::re(P[r1 + 1]), e, i1, i2, d1d2);
+    const int cd = dim - 2, tri = cd * (cd + 1) / 2;
+    for (int el = threadIdx.x; el < tri; el += THREADS) {
+        int r, c;
+        tri_decode(el, r, c);
+        Q[tv_row(kq, r) + c] = schur_entry_p(P, k, r + 2, c + 2, e, i1, i2);
+    }
+    __syncthreads();
+    return d1d2;
+}
+
+// finish a 2-mode (4x4 Hermitian) node (T, k) in registers: 4 subsets
+template <typename TT>
+__device__ __forceinline__ double tail2_p(const TT* T, int k, double det, double sgn) {
+    using X = TorS<TT>;
+    const int r0 = tv_row(k, 0), r1 = tv_row(k, 1), r2 = tv_row(k, 2), r3 = tv_row(k, 3);
+    const double t00 = X::re(T[r0]), t11 = X::re(T[r1 + 1]), t22 = X::re(T[r2 + 2]), t33 = X::re(T[r3 + 3]);
+    const TT t10 = T[r1], t20 = T[r2], t30 = T[r3], t21 = T[r2 + 1], t31 = T[r3 + 1], t32 = T[r3 + 2];
+    double sum = rsqrt(det);                                         // {}: two exclusions, sign unchanged
+    const double detB = t22 * t33 - X::absq(t32);                    // {m1}
+    sum -= rsqrt(det * detB);
+    const double i1 = 1.0 / t00;
+    const double d2 = t11 - X::absq(t10) * i1;
+    sum -= rsqrt(det * t00 * d2);                                    // {m0}
+    // {m0, m1}: Schur complement of mode 0 on the m1 block
+    const double i2 = 1.0 / d2;
+    TT u2 = t21, u3 = t31;   // column 1 after pivot 1
+    X::subs(u2, X::mulc(t20, t10), i1);
+    X::subs(u3, X::mulc(t30, t10), i1);
+    const double s22 = t22 - X::absq(t20) * i1 - X::absq(u2) * i2;
+    const double s33 = t33 - X::absq(t30) * i1 - X::absq(u3) * i2;
+    TT s32 = t32;
+    X::subs(s32, X::mulc(t30, t20), i1);
+    X::subs(s32, X::mulc(u3, u2), i2);
+    const double detS = s22 * s33 - X::absq(s32);
+    sum += rsqrt(det * t00 * d2 * detS);
+    return sgn * sum;
+}
+
+// Shared-memory plan of tor_kernel (units of the scalar type): T (packed n2) | depth buffers of the prefix DFS | include-
+// children pool of the breadth-first expansion | node descriptors.  Returns the total in bytes.
+__host__ __device__ inline size_t tor_smem_plan_p(int N, int aug, int g, int DC, int* off_depth, int* off_pool, int* off_desc,
+                                                  size_t elem) {
+    const int n2 = 2 * N + aug, dg = 2 * (DC + g) + aug;
+    int off = tor_tri(n2);
+    *off_depth = off;
+    for (int k = 1; k <= g; ++k) off += tor_tri(dg - 2 * k);
+    *off_pool = off;
+    for (int l = 0, dim = 2 * DC + aug; dim > 4 + aug; ++l, dim -= 2) off += (1 << l) * tor_tri(dim - 2);
+    off = (off + 1) & ~1;                                            // descriptors (int / double) start 16-byte aligned
+    *off_desc = off;
+    const size_t desc = (size_t)128 * (2 * 2 * sizeof(int) + 2 * 2 * sizeof(double)) + 2 * 64 * sizeof(double);
+    return (size_t)off * elem + desc;
 }
 
 // Row stride of a stored dim x dim matrix: odd, so that the column reads P[r * ld] / P[r * ld + 1] of a quarter
@@ -268,11 +368,11 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
     static_assert(THREADS == 128 || THREADS == 256 || THREADS == 512, "power of two, at least one thread per parent node");
     extern __shared__ __align__(16) double smem_tor[];
     const int N = p.N, n2 = 2 * N + AUG, DC = p.DC, g = p.g, P = p.P;
-    const int dg = 2 * (DC + g) + AUG, ldT = tor_ld(n2);
+    const int dg = 2 * (DC + g) + AUG;
     T* S = reinterpret_cast<T*>(smem_tor);
     const T* Bg = static_cast<const T*>(p.B);
     int* ptrA = reinterpret_cast<int*>(S + p.off_desc);
-    int* ldA = ptrA + TOR_MAXNODES;
+    int* ldA = ptrA + TOR_MAXNODES;          // (the k of a view: leading rows / columns dropped)
     int* ptrB = ldA + TOR_MAXNODES;
     int* ldB = ptrB + TOR_MAXNODES;
     double* detA = reinterpret_cast<double*>(ldB + TOR_MAXNODES);
@@ -292,21 +392,24 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
     for (uint64_t grp = ngroups_first + blockIdx.x; grp < ngroups_last; grp += gridDim.x) {
         // ---- phase A: common leading modes 0 .. P-g-1 (bits of grp, most significant = mode 0), in place on T
         __syncthreads();
-        for (int idx = tid; idx < n2 * n2; idx += THREADS) S[(idx / n2) * ldT + idx % n2] = Bg[idx];
+        for (int el = tid; el < tor_tri(n2); el += THREADS) {      // lower triangle of the (bordered) I - O, packed
+            int r, c;
+            tri_decode(el, r, c);
+            S[el] = Bg[r * n2 + c];
+        }
         double det0 = 1.0, sgn0 = 1.0;
         const int lead = P - g;
         for (int i = 0; i < lead; ++i) {
             const bool inc = (grp >> (lead - 1 - i)) & 1ull;
-            T* V = S + 2 * i * (ldT + 1);
-            if (inc) det0 *= eliminate_into<THREADS>(V, ldT, n2 - 2 * i, V + 2 * (ldT + 1), ldT);
+            if (inc) det0 *= eliminate_into_p<THREADS>(S, 2 * i, n2 - 2 * i, S, 2 * i + 2);     // in place
             else sgn0 = -sgn0;
         }
         // ---- phase B: the 2^g prefixes of this group, depth-first
         int nptr[TOR_MAXG + 1], nld[TOR_MAXG + 1];
         double ndet[TOR_MAXG + 1], nsgn[TOR_MAXG + 1];
-        nptr[0] = 2 * lead * (ldT + 1); nld[0] = ldT; ndet[0] = det0; nsgn[0] = sgn0;
+        nptr[0] = 0; nld[0] = 2 * lead; ndet[0] = det0; nsgn[0] = sgn0;       // (nptr, nld) = the view (ptr, k)
 #pragma unroll
-        for (int k = 1; k <= TOR_MAXG; ++k) { nptr[k] = 0; nld[k] = 1; ndet[k] = 1.0; nsgn[k] = 1.0; }
+        for (int k = 1; k <= TOR_MAXG; ++k) { nptr[k] = 0; nld[k] = 0; ndet[k] = 1.0; nsgn[k] = 1.0; }
         int cur = -1;
         for (int sub = 0; sub < (1 << g); ++sub) {
             const uint64_t pfx = (grp << g) + sub;
@@ -318,19 +421,19 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
 #pragma unroll
             for (int lvl = 0; lvl < TOR_MAXG; ++lvl) {
                 if (lvl < g) {
-                    const int dim = dg - 2 * lvl, cdim = dim - 2, cld = tor_ld(cdim);
+                    const int dim = dg - 2 * lvl, cdim = dim - 2;
                     if (lvl >= first) {
                         const bool inc = (sub >> (g - 1 - lvl)) & 1;
                         if (inc) {
-                            ndet[lvl + 1] = ndet[lvl] * eliminate_into<THREADS>(S + nptr[lvl], nld[lvl], dim, S + dbuf, cld);
+                            ndet[lvl + 1] = ndet[lvl] * eliminate_into_p<THREADS>(S + nptr[lvl], nld[lvl], dim, S + dbuf, 0);
                             nsgn[lvl + 1] = nsgn[lvl];
-                            nptr[lvl + 1] = dbuf; nld[lvl + 1] = cld;
+                            nptr[lvl + 1] = dbuf; nld[lvl + 1] = 0;
                         } else {
                             ndet[lvl + 1] = ndet[lvl]; nsgn[lvl + 1] = -nsgn[lvl];
-                            nptr[lvl + 1] = nptr[lvl] + 2 * (nld[lvl] + 1); nld[lvl + 1] = nld[lvl];
+                            nptr[lvl + 1] = nptr[lvl]; nld[lvl + 1] = nld[lvl] + 2;
                         }
                     }
-                    dbuf += cdim * cld;
+                    dbuf += tor_tri(cdim);
                 }
             }
             // ---- breadth-first expansion of the last DC modes
@@ -346,23 +449,24 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
             int nodes = 1, shift = LOG_THREADS, pool = p.off_pool;
             __syncthreads();
             for (int dim = 2 * DC + AUG; dim > 4 + AUG; dim -= 2) {
-                const int cd = dim - 2, tri = cd * (cd + 1) / 2, cld = tor_ld(cd), csz = cd * cld;
+                const int cd = dim - 2, tri = cd * (cd + 1) / 2, csz = tri;
                 const int nd = tid >> shift, lane = tid & ((1 << shift) - 1), step = 1 << shift;
                 const int myptr = pc[nd], myld = lc[nd];
                 const T* Pn = S + myptr;
                 T* Qn = S + pool + nd * csz;
                 // every thread of the node derives the two pivots itself: no separate pivot pass, one barrier per level
-                const T e = Pn[myld];
+                const int r1 = tv_row(myld, 1);
+                const T e = Pn[r1];
                 double i1, i2, d1d2;
-                pivot_inverses(TorS<T>::re(Pn[0]), TorS<T>::re(Pn[myld + 1]), e, i1, i2, d1d2);
+                pivot_inverses(TorS<T>::re(Pn[tv_row(myld, 0)]), TorS<T>::re(Pn[r1 + 1]), e, i1, i2, d1d2);
                 if (lane == 0) {
                     const double dt = dc[nd], sg = sc[nd];
-                    pn[2 * nd] = myptr + 2 * (myld + 1); ln[2 * nd] = myld; dn[2 * nd] = dt; sn[2 * nd] = -sg;   // exclude
-                    pn[2 * nd + 1] = pool + nd * csz; ln[2 * nd + 1] = cld; dn[2 * nd + 1] = dt * d1d2; sn[2 * nd + 1] = sg;
+                    pn[2 * nd] = myptr; ln[2 * nd] = myld + 2; dn[2 * nd] = dt; sn[2 * nd] = -sg;   // exclude: the same storage, two more rows dropped
+                    pn[2 * nd + 1] = pool + nd * csz; ln[2 * nd + 1] = 0; dn[2 * nd + 1] = dt * d1d2; sn[2 * nd + 1] = sg;
                 }
                 for (int el = lane; el < tri; el += step) {
                     const uchar2 rc = tri_rc[el];
-                    Qn[rc.x * cld + rc.y] = schur_entry(Pn, myld, rc.x + 2, rc.y + 2, e, i1, i2);
+                    Qn[el] = schur_entry_p(Pn, myld, rc.x + 2, rc.y + 2, e, i1, i2);
                 }
                 __syncthreads();
                 pool += nodes * csz;
@@ -372,8 +476,8 @@ __global__ void __launch_bounds__(THREADS) tor_kernel(TorParams p, double* __res
             }
             // ---- 2-mode nodes finished by single threads
             for (int nd = tid; nd < nodes; nd += THREADS) {
-                if constexpr (AUG != 0) dd_add(acc, tail2_loop(S + pc[nd], lc[nd], dc[nd], sc[nd]));
-                else dd_add(acc, tail2(S + pc[nd], lc[nd], dc[nd], sc[nd]));
+                if constexpr (AUG != 0) dd_add(acc, tail2_loop_p(S + pc[nd], lc[nd], dc[nd], sc[nd]));
+                else dd_add(acc, tail2_p(S + pc[nd], lc[nd], dc[nd], sc[nd]));
             }
         }
     }
@@ -676,7 +780,7 @@ static void tor_shape(int N, int aug, int* P, int* g, int* DC) {
     *P = N - *DC;
     *g = *P < TOR_G ? *P : TOR_G;
     int a, b, c;
-    while (*g > 0 && tor_smem_plan(N, aug, *g, *DC, &a, &b, &c) > (size_t)WB_TOR_SMEM_KB * 1024) --*g;
+    while (*g > 0 && tor_smem_plan_p(N, aug, *g, *DC, &a, &b, &c, sizeof(double2)) > (size_t)WB_TOR_SMEM_KB * 1024) --*g;
 }
 
 struct DevBufT {
@@ -768,7 +872,7 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
     // small problems (or thin multi-GPU shards): fewer prefixes per CTA so that every SM gets a group
     while (p.g > 0 && ((p1 - p0) >> p.g) < 2ull * (uint64_t)sms) --p.g;
     if (real_O) {
-        const size_t shm = tor_smem_plan(N, 0, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc, sizeof(double));
+        const size_t shm = tor_smem_plan_p(N, 0, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc, sizeof(double));
         if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
         auto kern = tor_kernel<0, TOR_THREADS, double>;
         WB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
@@ -785,7 +889,7 @@ static int tor_launch(const double* dO, const double* dGamma, int n_modes, uint6
         WB_CUDA(cudaGetLastError());
         return WB200_OK;
     }
-    const size_t shm = tor_smem_plan(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc);
+    const size_t shm = tor_smem_plan_p(N, aug, p.g, p.DC, &p.off_depth, &p.off_pool, &p.off_desc, sizeof(double2));
     if (shm > 226 * 1024) { set_error("tor: %d modes need %zu bytes of shared memory", N, shm); return WB200_ENOSUP; }
     if (aug) WB_CUDA(cudaFuncSetAttribute(tor_kernel<1, TOR_THREADS_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
     else WB_CUDA(cudaFuncSetAttribute(tor_kernel<0, TOR_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
