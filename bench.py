@@ -48,7 +48,7 @@ MEASURED_TRAFFIC = {
     # on 2^18 subsets without a flush before it moves 0.5 MB (profiles/r02_ncu_haf50_sym.txt)
     "hafnian50": (19121920 + 94205184, "profiles/r02_launches_hafnian50_final3.csv"),
     "perm32": (79104, "profiles/r01_ncu_perm32_v3.txt"),
-    "tor48": (73216, "profiles/r01_ncu_tor48_v3b.txt"),
+    "tor48": (73216, "profiles/r01_ncu_tor48_v3b.txt (round-1 kernel, square storage; the packed kernel of round 2 was not re-captured)"),
 }
 GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_fullsize.json")
 
